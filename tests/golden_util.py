@@ -1,0 +1,91 @@
+"""Replays a golden trace (tests/golden/*.npz, minted from the reference's own env.py by
+oracle/make_golden.py) through any lockstep stepper and compares every step."""
+import glob
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+NB = 512
+
+
+def trace_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, '*.npz'))
+                  if not p.endswith('known_answers.npz'))
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLDEN, name + '.npz')))
+
+
+def map_info(G):
+    d = G['map_data']
+    return dict(data=d, origin=tuple(G['map_origin']), resolution=float(G['map_resolution']),
+                width=d.shape[1], height=d.shape[0])
+
+
+def geom_dims(G):
+    md = max(G['discs'].shape[1], len(G['discs0']), 1)
+    ms = max(G['segs'].shape[1], len(G['segs0']), 1)
+    return md, ms
+
+
+def pad(a, n, w):
+    out = np.zeros((1, n, w), np.float32)
+    a = np.asarray(a, np.float32).reshape(-1, w)
+    out[0, :len(a)] = a
+    return out, np.array([len(a)], np.int32)
+
+
+def replay(G, stepper, pose_tol=1e-9, reward_tol=1e-9, check_hits=True):
+    """stepper: object with reset_obs(...)/step(...) and numpy attrs obs, tail64, reward,
+    done, is_success, is_crash, distance, hits, state (rows px,py,th first), steps.
+    Integer/flag outputs and the float32 scan are compared bit-exactly."""
+    md, ms = geom_dims(G)
+    d0, nd0 = pad(G['discs0'], md, 3)
+    s0, ns0 = pad(G['segs0'], ms, 4)
+    n0 = np.zeros((1, 2, NB), np.float32)
+    n0[0, 0] = G['noise0']
+    stepper.reset_obs(d0, nd0, s0, ns0, n0)
+    obs = np.asarray(stepper.obs)[0]
+    assert np.array_equal(obs[:NB], G['obs0'][:NB].astype(np.float32)), 'first scan'
+    assert np.allclose(np.asarray(stepper.tail64)[0], G['obs0'][NB:], rtol=0, atol=pose_tol)
+    if check_hits:
+        assert np.array_equal(_mask_hits(np.asarray(stepper.hits)[0], stepper), _mask_hits(G['hits0'], stepper))
+    T = len(G['actions'])
+    for t in range(T):
+        dd, nd = pad(G['discs'][t][:G['ndisc'][t]], md, 3)
+        ss, ns = pad(G['segs'][t][:G['nseg'][t]], ms, 4)
+        stepper.step(G['actions'][t][None].astype(np.float32), dd, nd, ss, ns, G['noise'][t][None])
+        obs = np.asarray(stepper.obs)[0]
+        tag = 'step %d' % t
+        assert np.array_equal(obs[:NB], G['scan'][t]), tag + ' scan'
+        assert np.allclose(np.asarray(stepper.tail64)[0], G['tail'][t], rtol=0, atol=pose_tol), tag
+        assert np.allclose(obs[NB:], G['tail'][t].astype(np.float32), rtol=1e-6, atol=1e-6), tag
+        assert abs(float(np.asarray(stepper.reward)[0]) - G['reward'][t]) <= reward_tol, tag + ' reward'
+        assert int(np.asarray(stepper.done)[0]) == int(G['done'][t]), tag + ' done'
+        assert int(np.asarray(stepper.is_success)[0]) == int(G['is_success'][t]), tag
+        assert int(np.asarray(stepper.is_crash)[0]) == int(G['is_crash'][t]), tag
+        assert abs(float(np.asarray(stepper.distance)[0]) - G['distance'][t]) <= 1e-6, tag
+        assert int(np.asarray(stepper.steps)[0]) == int(G['steps'][t]), tag + ' step count'
+        st = np.asarray(stepper.state)[:3, 0]
+        assert np.allclose(st, G['state'][t], rtol=0, atol=pose_tol), tag + ' pose'
+        if check_hits:
+            assert np.array_equal(_mask_hits(np.asarray(stepper.hits)[0], stepper), _mask_hits(G['hits'][t], stepper)), \
+                tag + ' hit cells'
+    return T
+
+
+def far_filter(h):
+    """Hit cells farther than 500.5 cells (25 m) from the origin are not observable in the
+    reference (env.py:435 clips the range): blank them on both sides of the comparison."""
+    h = np.array(h, np.int16)
+    d2 = h[:, 0].astype(np.int64) ** 2 + h[:, 1].astype(np.int64) ** 2
+    h[d2 > 500.5 ** 2] = -32768
+    return h
+
+
+def _mask_hits(h, stepper):
+    """A stepper that stops marching at 25 m (+2 cells) reports 'no hit' for farther cells;
+    the reference marches on to W*H cells (env.py:337) and clips the range afterwards."""
+    return far_filter(h) if getattr(stepper, 'early_stop', False) else np.asarray(h)
