@@ -1,0 +1,155 @@
+/*
+ * navgym_b200.h — C ABI of libnavgym_b200.so, the sm_100a implementation of nav-gym's
+ * NavGym-v0 per-step hot path.
+ *
+ * Plain C types only (pointers, sizes, one POD argument block); no torch / C++ types cross
+ * this boundary.  All *_dev pointers are CUDA device pointers; `stream` is a cudaStream_t
+ * passed as void* (NULL = legacy default stream).  Every launcher is asynchronous with
+ * respect to the host unless its name ends in _host; return value 0 = success, otherwise a
+ * cudaError_t (text via navgym_error_string()).  There is NO CPU fallback: with no device
+ * every call fails.
+ *
+ * Citations are relative to /root/reference/nav_gym/src/nav_gym_env/ (the reference) and
+ * name the interface each entry point replaces.
+ */
+#ifndef NAVGYM_B200_H
+#define NAVGYM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NAVGYM_NUM_BEAMS 512   /* keti_robot.py:48 n_angles */
+#define NAVGYM_OBS_TAIL 7      /* prev_pose(2) pose(2) vel(2) yaw(1), env.py:455 */
+#define NAVGYM_HIT_NONE (-32768)
+#define NAVGYM_MAX_DISC 64     /* per-env capacity of the kernel's staging buffers */
+#define NAVGYM_MAX_SEG 128
+
+/* rows of the structure-of-arrays float64 state block state[NAVGYM_NS][num_envs] */
+enum {
+    NAVGYM_S_PX = 0, NAVGYM_S_PY, NAVGYM_S_TH,   /* robot pose (keti_robot.py:56-58) */
+    NAVGYM_S_GX, NAVGYM_S_GY,                    /* goal */
+    NAVGYM_S_PPX, NAVGYM_S_PPY, NAVGYM_S_PYAW,   /* pose / yaw fields of prev_obs (env.py:726) */
+    NAVGYM_S_PV, NAVGYM_S_PW,                    /* prev_action (env.py:725) */
+    NAVGYM_NS
+};
+
+/* One occupancy map of the pool (reference map_info dict, map_generator.py:113-122). */
+typedef struct {
+    int32_t W, H;            /* cells */
+    int64_t edt_offset;      /* element offset of this map's float EDT in edt_pool */
+    double ox, oy, res;      /* origin [m], resolution [m/cell] */
+    int64_t spawn_offset;    /* first row of this map's spawn tuples in spawn_pool */
+    int32_t spawn_count;     /* 0 = map has no spawn pool */
+    int32_t _pad;
+} navgym_map_t;
+
+/* Argument block of the fused step / reset kernels.  Layouts:
+ *   state   f64 [NAVGYM_NS][num_envs]         steps    i32 [num_envs]
+ *   actions f32 [num_envs][2]                 map_id   i32 [num_envs]
+ *   discs   f32 [num_envs][max_disc][3] (x,y,r)   ndisc i32 [num_envs]
+ *   segs    f32 [num_envs][max_seg][4] (ax,ay,bx,by)  nseg i32 [num_envs]
+ *   noise   f32 [num_envs][2][512] additive, slot 0 = the step's scan, slot 1 = the crash
+ *           re-scan (parity traces); NULL -> Philox N(0, noise_std[env]) (production)
+ *   obs     f32 [num_envs][obs_stride], first 512+7 columns written per row
+ *   tail64  f64 [num_envs][7]   (the 7 trailing observation fields in float64, env.py:455)
+ *   hits    i16 [num_envs][512][2] hit cell minus origin cell of the step's first scan, or
+ *           NAVGYM_HIT_NONE; NULL = not recorded
+ */
+typedef struct {
+    /* ---- constants (reference kwargs, __init__.py:6-38) ---- */
+    double dt;               /* time_step */
+    double dist_thresh;      /* distance_threshold */
+    double min_turn_radius;  /* min_turning_radius */
+    double r_scale, r_success, r_crash, r_progress, r_forward, r_rotation, r_discomfort;
+    float range_max;         /* keti_robot.py:47 */
+    float t_stop;            /* march limit in cells (reference: W*H, env.py:337) */
+    int32_t cell_rule;       /* 0: float64 cell division (NumPy 1.x), 1: float32 (NumPy 2) */
+    int32_t max_disc, max_seg;
+    int32_t num_envs;
+    int32_t obs_stride;      /* floats per obs row, >= 519 */
+    int32_t auto_reset;      /* 1: on done draw a spawn tuple and return the new first obs */
+    int32_t max_episode_steps; /* 0 = none (the reference has no time limit) */
+    int32_t num_maps;
+    int32_t resample_map;    /* 1: auto-reset also draws a new map id */
+    uint64_t seed;
+    int64_t env_offset;      /* global index of env 0 (multi-GPU sharding) */
+    float noise_lo, noise_hi; /* scan_noise_std range resampled at auto-reset */
+    /* ---- device pointers ---- */
+    const navgym_map_t *maps;
+    const float *edt_pool;
+    const double *spawn_pool;   /* [rows][5] = sx, sy, gx, gy, theta */
+    int32_t *map_id;
+    const double *lin;          /* [512] beam angle table (env.py:388-390) */
+    const float *thr, *dthr;    /* [512] crash / discomfort thresholds (env.py:162-180) */
+    double *state;
+    int32_t *steps;
+    int32_t *episodes;          /* [num_envs] episode counter (RNG stream id) */
+    const float *actions;
+    const float *discs;
+    const int32_t *ndisc;
+    const float *segs;
+    const int32_t *nseg;
+    const float *noise;
+    float *noise_std;           /* [num_envs] */
+    float *obs;
+    double *tail64;
+    float *reward;
+    uint8_t *done, *is_success, *is_crash, *truncated;
+    float *distance;
+    int16_t *hits;
+} navgym_step_args_t;
+
+/* ---- fused hot path: NavGymEnv.step (env.py:591-728) over num_envs environments ------ */
+int navgym_step_batch(const navgym_step_args_t *args, void *stream);
+/* first observation of an episode, NavGymEnv.reset's tail (env.py:822-831) */
+int navgym_reset_obs_batch(const navgym_step_args_t *args, void *stream);
+
+/* ---- inner native boundary: range_libc --------------------------------------------- */
+/* PyOMap(bool[H,W]) + PyRayMarching(omap, max_range) (env.py:337-340): exact Euclidean
+ * distance transform of occ_dev (u8, non-zero = occupied, [H][W], row = y) into dist_dev. */
+int navgym_edt_build(const uint8_t *occ_dev, int H, int W, float *dist_dev, int32_t *scratch_dev,
+                     void *stream);
+/* PyRayMarching.calc_range_many(ins f32[N,3], outs f32[N]) (env.py:425), ranges in cells. */
+int navgym_calc_range_many(const float *dist_dev, int W, int H, const float *ins_dev,
+                           float *outs_dev, int N, float max_range, float t_stop,
+                           int16_t *hits_dev, void *stream);
+
+/* Host-buffer drop-ins with the lifetime of the reference's Python objects. */
+typedef struct navgym_raymarching navgym_raymarching_t;
+navgym_raymarching_t *navgym_raymarching_create_host(const uint8_t *occ_host, int H, int W,
+                                                     float max_range);
+int navgym_raymarching_calc_range_many_host(navgym_raymarching_t *rm, const float *ins_host,
+                                            float *outs_host, int N);
+const float *navgym_raymarching_edt_dev(const navgym_raymarching_t *rm);
+void navgym_raymarching_destroy(navgym_raymarching_t *rm);
+
+/* ---- inner native boundary: pymap2d ------------------------------------------------ */
+/* render_contours_in_lidar(ranges, angles, flat, lidar_xy) (env.py:430-431) with the
+ * polygons already flattened to closed segments segs[S][4]; in-place min. */
+int navgym_render_segments_in_lidar(float *ranges_dev, const float *headings_dev, int K,
+                                    const float *segs_dev, int S, float ox, float oy,
+                                    void *stream);
+/* CMap2D.render_agents_in_lidar (env.py:432) with agents reduced to discs[D][3]. */
+int navgym_render_discs_in_lidar(float *ranges_dev, const float *headings_dev, int K,
+                                 const float *discs_dev, int D, float ox, float oy,
+                                 void *stream);
+int navgym_render_in_lidar_host(float *ranges_host, const float *headings_host, int K,
+                                const float *segs_host, int S, const float *discs_host, int D,
+                                float ox, float oy);
+
+/* ---- misc -------------------------------------------------------------------------- */
+const char *navgym_error_string(int code);
+int navgym_device_count(void);
+int navgym_abi_version(void);
+int navgym_sizeof_step_args(void);   /* layout check for FFI bindings */
+int navgym_sizeof_map(void);
+/* kernels launched by this library since load (for bench.py's gpu_launches) */
+uint64_t navgym_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,144 @@
+"""Loader for libnavgym_b200.so (the C ABI declared in include/navgym_b200.h).
+
+The library is built in-tree by :func:`build` (called from ``__graft_entry__.build``) with
+``nvcc -gencode arch=compute_100a,code=sm_100a``.  There is no CPU fallback: if the shared
+object is missing or no CUDA device is present the product raises.
+"""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+SRC = os.path.join(_PKG, 'csrc', 'navgym_b200.cu')
+HDR = os.path.join(_ROOT, 'include', 'navgym_b200.h')
+SO = os.path.join(_PKG, 'libnavgym_b200.so')
+
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-fmad=false',
+              '-shared', '-Xcompiler', '-fPIC', '-std=c++17']
+
+NB = 512
+OBS_TAIL = 7
+OBS_DIM = NB + OBS_TAIL
+HIT_NONE = -32768
+MAX_DISC = 64
+MAX_SEG = 128
+NS = 10
+S_PX, S_PY, S_TH, S_GX, S_GY, S_PPX, S_PPY, S_PYAW, S_PV, S_PW = range(NS)
+
+
+def _nvcc():
+    for c in (shutil.which('nvcc'), '/usr/local/cuda/bin/nvcc'):
+        if c and os.path.exists(c):
+            return c
+    return None
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA library for sm_100a (cross-compiles without a GPU)."""
+    if not force and os.path.exists(SO):
+        newest = max(os.path.getmtime(SRC), os.path.getmtime(HDR))
+        if os.path.getmtime(SO) >= newest:
+            return SO
+    nvcc = _nvcc()
+    if nvcc is None:
+        raise RuntimeError('nvcc not found: cannot build %s' % SO)
+    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', SO, SRC]
+    subprocess.check_call(cmd)
+    return SO
+
+
+class MapT(C.Structure):
+    _fields_ = [('W', C.c_int32), ('H', C.c_int32), ('edt_offset', C.c_int64),
+                ('ox', C.c_double), ('oy', C.c_double), ('res', C.c_double),
+                ('spawn_offset', C.c_int64), ('spawn_count', C.c_int32), ('_pad', C.c_int32)]
+
+
+_P = C.c_void_p
+
+
+class StepArgs(C.Structure):
+    _fields_ = [
+        ('dt', C.c_double), ('dist_thresh', C.c_double), ('min_turn_radius', C.c_double),
+        ('r_scale', C.c_double), ('r_success', C.c_double), ('r_crash', C.c_double),
+        ('r_progress', C.c_double), ('r_forward', C.c_double), ('r_rotation', C.c_double),
+        ('r_discomfort', C.c_double),
+        ('range_max', C.c_float), ('t_stop', C.c_float),
+        ('cell_rule', C.c_int32), ('max_disc', C.c_int32), ('max_seg', C.c_int32),
+        ('num_envs', C.c_int32), ('obs_stride', C.c_int32), ('auto_reset', C.c_int32),
+        ('max_episode_steps', C.c_int32), ('num_maps', C.c_int32), ('resample_map', C.c_int32),
+        ('seed', C.c_uint64), ('env_offset', C.c_int64),
+        ('noise_lo', C.c_float), ('noise_hi', C.c_float),
+        ('maps', _P), ('edt_pool', _P), ('spawn_pool', _P), ('map_id', _P),
+        ('lin', _P), ('thr', _P), ('dthr', _P),
+        ('state', _P), ('steps', _P), ('episodes', _P), ('actions', _P),
+        ('discs', _P), ('ndisc', _P), ('segs', _P), ('nseg', _P),
+        ('noise', _P), ('noise_std', _P),
+        ('obs', _P), ('tail64', _P), ('reward', _P),
+        ('done', _P), ('is_success', _P), ('is_crash', _P), ('truncated', _P),
+        ('distance', _P), ('hits', _P),
+    ]
+
+
+EXPORTS = [
+    'navgym_step_batch', 'navgym_reset_obs_batch', 'navgym_edt_build', 'navgym_calc_range_many',
+    'navgym_raymarching_create_host', 'navgym_raymarching_calc_range_many_host',
+    'navgym_raymarching_edt_dev', 'navgym_raymarching_destroy',
+    'navgym_render_segments_in_lidar', 'navgym_render_discs_in_lidar', 'navgym_render_in_lidar_host',
+    'navgym_error_string', 'navgym_device_count', 'navgym_abi_version', 'navgym_launch_count',
+    'navgym_sizeof_step_args', 'navgym_sizeof_map',
+]
+
+_lib = None
+
+
+def load():
+    """dlopen the C-ABI library.  Raises if it has not been built (no fallback path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO):
+        raise RuntimeError(
+            '%s is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+            '(nav_gym_b200 has no CPU fallback)' % SO)
+    lib = C.CDLL(SO)
+    lib.navgym_step_batch.argtypes = [C.POINTER(StepArgs), _P]
+    lib.navgym_reset_obs_batch.argtypes = [C.POINTER(StepArgs), _P]
+    lib.navgym_edt_build.argtypes = [_P, C.c_int, C.c_int, _P, _P, _P]
+    lib.navgym_calc_range_many.argtypes = [_P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_float,
+                                           C.c_float, _P, _P]
+    lib.navgym_raymarching_create_host.restype = _P
+    lib.navgym_raymarching_create_host.argtypes = [_P, C.c_int, C.c_int, C.c_float]
+    lib.navgym_raymarching_calc_range_many_host.argtypes = [_P, _P, _P, C.c_int]
+    lib.navgym_raymarching_edt_dev.restype = _P
+    lib.navgym_raymarching_edt_dev.argtypes = [_P]
+    lib.navgym_raymarching_destroy.restype = None
+    lib.navgym_raymarching_destroy.argtypes = [_P]
+    lib.navgym_render_segments_in_lidar.argtypes = [_P, _P, C.c_int, _P, C.c_int, C.c_float,
+                                                    C.c_float, _P]
+    lib.navgym_render_discs_in_lidar.argtypes = [_P, _P, C.c_int, _P, C.c_int, C.c_float,
+                                                 C.c_float, _P]
+    lib.navgym_render_in_lidar_host.argtypes = [_P, _P, C.c_int, _P, C.c_int, _P, C.c_int,
+                                                C.c_float, C.c_float]
+    lib.navgym_error_string.restype = C.c_char_p
+    lib.navgym_error_string.argtypes = [C.c_int]
+    lib.navgym_launch_count.restype = C.c_uint64
+    if lib.navgym_sizeof_step_args() != C.sizeof(StepArgs) or lib.navgym_sizeof_map() != C.sizeof(MapT):
+        raise RuntimeError('libnavgym_b200.so ABI mismatch with nav_gym_b200/_lib.py (rebuild)')
+    _lib = lib
+    return lib
+
+
+def check(code, what=''):
+    if code != 0:
+        msg = load().navgym_error_string(int(code))
+        raise RuntimeError('libnavgym_b200 %s failed: CUDA error %d (%s)'
+                           % (what, code, msg.decode() if msg else '?'))
+
+
+def require_device():
+    lib = load()
+    if lib.navgym_device_count() <= 0:
+        raise RuntimeError('nav_gym_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+    return lib

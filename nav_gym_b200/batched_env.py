@@ -1,0 +1,217 @@
+"""BatchedNavGym — thousands of NavGym-v0 environments stepped in lockstep on one B200.
+
+Host-side mirror of the reference's NavGymEnv.step contract (env.py:591-728) for a batch:
+``step(actions[B,2]) -> obs[B,519], reward[B], done[B], info`` with every tensor resident on
+the device.  All arithmetic happens in the hand-written sm_100a kernels of
+csrc/navgym_b200.cu, reached through the C ABI of include/navgym_b200.h via ctypes; torch is
+used only for device memory and streams.  There is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import NB, NS, OBS_DIM
+from .robot import KetiRobot, beam_table, closed_segments
+
+DEFAULT_REWARD = dict(reward_scale=15., reward_success_factor=1, reward_crash_factor=1,
+                      reward_progress_factor=0.001, reward_forward_factor=0.0,
+                      reward_rotation_factor=0.005, reward_discomfort_factor=0.01)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def scan_thresholds(device):
+    """_make_scan_threshold / _make_scan_discomfort_threshold (env.py:162-180): the inflated
+    footprints rendered into a 25 m scan from the origin at heading 0, on the GPU."""
+    lib = _lib.require_device()
+    head = beam_table().astype(np.float32)  # float32(lin + float32(0))
+    out = []
+    for fp in (KetiRobot.threshold_footprint, KetiRobot.discomfort_threshold_footprint):
+        ranges = np.full(NB, KetiRobot.range_max, np.float32)
+        segs = np.ascontiguousarray(closed_segments(fp))
+        _lib.check(lib.navgym_render_in_lidar_host(
+            ranges.ctypes.data_as(C.c_void_p), head.ctypes.data_as(C.c_void_p), NB,
+            segs.ctypes.data_as(C.c_void_p), len(segs), None, 0, 0.0, 0.0), 'render_in_lidar_host')
+        out.append(np.clip(ranges, 0, KetiRobot.range_max))
+    return out
+
+
+class MapPool(object):
+    """Occupancy maps resident in HBM as exact float32 Euclidean distance transforms
+    (what range_libc's PyRayMarching holds per map, env.py:337-340), plus optional per-map
+    spawn pools of (start, goal, theta) tuples for device-side auto-reset."""
+
+    def __init__(self, maps, device, spawn_pools=None):
+        lib = _lib.require_device()
+        self.device = torch.device(device)
+        self.maps = maps
+        n = len(maps)
+        sizes = [int(m['width']) * int(m['height']) for m in maps]
+        self.edt_pool = torch.empty(sum(sizes), dtype=torch.float32, device=self.device)
+        carr = (_lib.MapT * n)()
+        off, soff = 0, 0
+        spawn_rows = []
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            for i, m in enumerate(maps):
+                H, W = int(m['height']), int(m['width'])
+                occ = torch.from_numpy(np.ascontiguousarray(np.asarray(m['data']) >= 0.1).astype(np.uint8))
+                occ = occ.to(self.device)
+                scratch = torch.empty(H * W, dtype=torch.int32, device=self.device)
+                dist = self.edt_pool[off:off + H * W]
+                _lib.check(lib.navgym_edt_build(_ptr(occ), H, W, _ptr(dist), _ptr(scratch),
+                                                C.c_void_p(stream)), 'edt_build')
+                cnt = 0
+                if spawn_pools is not None and spawn_pools[i] is not None and len(spawn_pools[i]):
+                    sp = np.ascontiguousarray(spawn_pools[i], np.float64).reshape(-1, 5)
+                    spawn_rows.append(sp)
+                    cnt = len(sp)
+                carr[i] = _lib.MapT(W, H, off, float(m['origin'][0]), float(m['origin'][1]),
+                                    float(m['resolution']), soff, cnt, 0)
+                off += H * W
+                soff += cnt
+            torch.cuda.synchronize(self.device)
+        raw = np.frombuffer(bytes(carr), dtype=np.uint8).copy()
+        self.maps_dev = torch.from_numpy(raw).to(self.device)
+        self.spawn_pool = None
+        if spawn_rows:
+            self.spawn_pool = torch.from_numpy(np.concatenate(spawn_rows)).to(self.device)
+        self.num_maps = n
+
+    def edt(self, i):
+        m = self.maps[i]
+        H, W = int(m['height']), int(m['width'])
+        off = sum(int(q['width']) * int(q['height']) for q in self.maps[:i])
+        return self.edt_pool[off:off + H * W].view(H, W)
+
+
+class BatchedNavGym(object):
+    def __init__(self, num_envs, maps, device='cuda:0', map_id=None, spawn_pools=None,
+                 time_step=0.2, distance_threshold=0.5, min_turning_radius=0.0,
+                 max_disc=0, max_seg=0, seed=0, env_offset=0, auto_reset=False,
+                 max_episode_steps=0, resample_map=False, scan_noise_std_range=(0.0, 0.05),
+                 cell_rule='numpy1', early_stop=True, record_hits=False, **reward):
+        self.lib = _lib.require_device()
+        self.device = torch.device(device)
+        self.B = B = int(num_envs)
+        self.pool = maps if isinstance(maps, MapPool) else MapPool(maps, self.device, spawn_pools)
+        dev = self.device
+        rp = dict(DEFAULT_REWARD)
+        rp.update(reward)
+        if max_disc > _lib.MAX_DISC or max_seg > _lib.MAX_SEG:
+            raise ValueError('max_disc <= %d and max_seg <= %d' % (_lib.MAX_DISC, _lib.MAX_SEG))
+        self.max_disc, self.max_seg = int(max_disc), int(max_seg)
+        f32, f64, i32, u8 = torch.float32, torch.float64, torch.int32, torch.uint8
+        self.state = torch.zeros(NS, B, dtype=f64, device=dev)
+        self.steps = torch.zeros(B, dtype=i32, device=dev)
+        self.episodes = torch.zeros(B, dtype=i32, device=dev)
+        mid = np.zeros(B, np.int32) if map_id is None else np.asarray(map_id, np.int32)
+        self.map_id = torch.from_numpy(mid).to(dev)
+        self.noise_std = torch.zeros(B, dtype=f32, device=dev)
+        self.obs = torch.zeros(B, OBS_DIM, dtype=f32, device=dev)
+        self.tail64 = torch.zeros(B, 7, dtype=f64, device=dev)
+        self.reward = torch.zeros(B, dtype=f32, device=dev)
+        self.done = torch.zeros(B, dtype=u8, device=dev)
+        self.is_success = torch.zeros(B, dtype=u8, device=dev)
+        self.is_crash = torch.zeros(B, dtype=u8, device=dev)
+        self.truncated = torch.zeros(B, dtype=u8, device=dev)
+        self.distance = torch.zeros(B, dtype=f32, device=dev)
+        self.hits = torch.zeros(B, NB, 2, dtype=torch.int16, device=dev) if record_hits else None
+        self.lin = torch.from_numpy(beam_table()).to(dev)
+        thr, dthr = scan_thresholds(dev)
+        self.scan_threshold, self.scan_discomfort_threshold = thr, dthr
+        self.thr = torch.from_numpy(thr).to(dev)
+        self.dthr = torch.from_numpy(dthr).to(dev)
+        self.early_stop = bool(early_stop)
+        t_stop = KetiRobot.range_max / 0.05 + 2.0 if early_stop else 3.0e38
+        if early_stop:
+            res = min(float(m['resolution']) for m in self.pool.maps)
+            t_stop = KetiRobot.range_max / res + 2.0
+        a = _lib.StepArgs()
+        a.dt, a.dist_thresh, a.min_turn_radius = time_step, distance_threshold, min_turning_radius
+        a.r_scale = rp['reward_scale']
+        a.r_success, a.r_crash = rp['reward_success_factor'], rp['reward_crash_factor']
+        a.r_progress, a.r_forward = rp['reward_progress_factor'], rp['reward_forward_factor']
+        a.r_rotation, a.r_discomfort = rp['reward_rotation_factor'], rp['reward_discomfort_factor']
+        a.range_max, a.t_stop = KetiRobot.range_max, t_stop
+        a.cell_rule = {'numpy1': 0, 'numpy2': 1}[cell_rule]
+        a.max_disc, a.max_seg = self.max_disc, self.max_seg
+        a.num_envs, a.obs_stride = B, OBS_DIM
+        a.auto_reset, a.max_episode_steps = int(auto_reset), int(max_episode_steps)
+        a.num_maps, a.resample_map = self.pool.num_maps, int(resample_map)
+        a.seed, a.env_offset = int(seed), int(env_offset)
+        a.noise_lo, a.noise_hi = scan_noise_std_range
+        a.maps, a.edt_pool = _ptr(self.pool.maps_dev), _ptr(self.pool.edt_pool)
+        a.spawn_pool = _ptr(self.pool.spawn_pool)
+        a.map_id, a.lin, a.thr, a.dthr = _ptr(self.map_id), _ptr(self.lin), _ptr(self.thr), _ptr(self.dthr)
+        a.state, a.steps, a.episodes = _ptr(self.state), _ptr(self.steps), _ptr(self.episodes)
+        a.noise_std = _ptr(self.noise_std)
+        a.obs, a.tail64, a.reward = _ptr(self.obs), _ptr(self.tail64), _ptr(self.reward)
+        a.done, a.is_success, a.is_crash = _ptr(self.done), _ptr(self.is_success), _ptr(self.is_crash)
+        a.truncated, a.distance, a.hits = _ptr(self.truncated), _ptr(self.distance), _ptr(self.hits)
+        self.args = a
+        self._keep = None
+
+    # -------------------------------------------------------------------------------------
+    def set_state(self, start, goal, theta, noise_std=None):
+        """start/goal [B,2], theta [B] (numpy or tensors); prev fields are set by reset()."""
+        t = lambda x: torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x,
+                                      dtype=torch.float64, device=self.device)
+        s, g = t(start), t(goal)
+        self.state[_lib.S_PX], self.state[_lib.S_PY] = s[:, 0], s[:, 1]
+        self.state[_lib.S_TH] = t(theta)
+        self.state[_lib.S_GX], self.state[_lib.S_GY] = g[:, 0], g[:, 1]
+        if noise_std is not None:
+            self.noise_std.copy_(torch.as_tensor(noise_std, dtype=torch.float32, device=self.device))
+
+    def _geom(self, discs, ndisc, segs, nseg, noise, actions=None):
+        a = self.args
+        keep = []
+
+        def dev(x, dtype):
+            if x is None:
+                return None
+            if not torch.is_tensor(x):
+                x = torch.from_numpy(np.ascontiguousarray(x))
+            x = x.to(device=self.device, dtype=dtype).contiguous()
+            keep.append(x)
+            return x
+        d, nd = dev(discs, torch.float32), dev(ndisc, torch.int32)
+        s, ns = dev(segs, torch.float32), dev(nseg, torch.int32)
+        nz = dev(noise, torch.float32)
+        if d is not None:
+            assert d.numel() == self.B * self.max_disc * 3 and nd.numel() == self.B
+        if s is not None:
+            assert s.numel() == self.B * self.max_seg * 4 and ns.numel() == self.B
+        if nz is not None:
+            assert nz.numel() == self.B * 2 * NB
+        a.discs, a.ndisc, a.segs, a.nseg, a.noise = _ptr(d), _ptr(nd), _ptr(s), _ptr(ns), _ptr(nz)
+        if actions is not None:
+            act = dev(actions, torch.float32)
+            assert act.numel() == self.B * 2
+            a.actions = _ptr(act)
+        self._keep = keep
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def reset(self, discs=None, ndisc=None, segs=None, nseg=None, noise=None):
+        """First observation of an episode from the state set by set_state (env.py:822-831)."""
+        self._geom(discs, ndisc, segs, nseg, noise)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.navgym_reset_obs_batch(C.byref(self.args), self._stream()), 'reset')
+        return self.obs
+
+    def step(self, actions, discs=None, ndisc=None, segs=None, nseg=None, noise=None):
+        """One lockstep NavGymEnv.step.  Returned tensors are owned by the env and overwritten
+        by the next call (clone to keep)."""
+        self._geom(discs, ndisc, segs, nseg, noise, actions)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.navgym_step_batch(C.byref(self.args), self._stream()), 'step')
+        info = dict(is_success=self.is_success, is_crash=self.is_crash, distance=self.distance,
+                    episode_step=self.steps, truncated=self.truncated)
+        return self.obs, self.reward, self.done, info

@@ -1,0 +1,141 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle
+and the golden fixtures.  Integer / flag outputs and float32 scans bit-exact; float64 poses
+within 1e-9 m, rewards within 1e-6 (float32 output of a float64 sum)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+import synth
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _maps(seed=0):
+    rng = np.random.RandomState(seed)
+    return [synth.indoor_map(rng), synth.outdoor_map(rng), synth.outdoor_map(rng, size=300, n_obs=25)]
+
+
+def test_thresholds_match_oracle():
+    from nav_gym_b200.batched_env import scan_thresholds
+    thr, dthr = scan_thresholds('cuda:0')
+    assert np.array_equal(thr, orc.footprint_threshold(orc.THRESHOLD_FOOTPRINT))
+    assert np.array_equal(dthr, orc.footprint_threshold(orc.DISCOMFORT_FOOTPRINT))
+
+
+@pytest.mark.parametrize('name', gu.trace_names()[:2] + ['synthetic'])
+def test_edt_exact(name):
+    from nav_gym_b200.batched_env import MapPool
+    maps = _maps() if name == 'synthetic' else [gu.map_info(gu.load(name))]
+    empty = dict(data=np.zeros((64, 96), np.int8), origin=(0, 0), resolution=0.05, width=96, height=64)
+    one = dict(data=np.zeros((50, 40), np.int8), origin=(0, 0), resolution=0.05, width=40, height=50)
+    one['data'][17, 3] = 100
+    maps = maps + [empty, one]
+    pool = MapPool(maps, 'cuda:0')
+    for i, m in enumerate(maps):
+        want = orc.edt(np.asarray(m['data']) >= 0.1)
+        got = pool.edt(i).cpu().numpy()
+        assert np.array_equal(got, want), 'map %d' % i
+
+
+def test_calc_range_many_bit_exact():
+    from nav_gym_b200 import natives
+    rng = np.random.RandomState(3)
+    for m in _maps(1):
+        occ = np.ascontiguousarray(np.asarray(m['data']) >= 0.1)
+        dist = orc.edt(occ)
+        H, W = occ.shape
+        n = 20000
+        ins = np.column_stack([rng.randint(0, W, n), rng.randint(0, H, n),
+                               rng.uniform(-7, 7, n)]).astype(np.float32)
+        rm = natives.PyRayMarching(natives.PyOMap(occ), W * H)
+        outs = np.zeros(n, np.float32)
+        rm.calc_range_many(ins, outs)
+        want, hits = orc.calc_range_many(dist, ins, float(W * H), want_hits=True)
+        assert np.array_equal(outs, want)
+        got_r, got_h = rm.calc_range_many_with_hits(ins)
+        assert np.array_equal(got_r, want) and np.array_equal(got_h, hits.astype(np.int16))
+
+
+@pytest.mark.parametrize('early_stop', [False, True])
+@pytest.mark.parametrize('name', gu.trace_names())
+def test_cuda_replays_reference_trace(name, early_stop):
+    import cuda_util
+    G = gu.load(name)
+    st = cuda_util.golden_stepper(G, early_stop)
+    assert np.array_equal(st.env.scan_threshold, G['thr'])
+    assert np.array_equal(st.env.scan_discomfort_threshold, G['dthr'])
+    gu.replay(G, st, pose_tol=1e-9, reward_tol=2e-6)
+
+
+@pytest.mark.parametrize('B,T,seed', [(256, 40, 0), (1024, 12, 1)])
+def test_batched_step_matches_oracle(B, T, seed):
+    """Many envs over several maps, pedestrians as discs + box segments, injected noise,
+    random actions: every step compared with the oracle's lockstep batch."""
+    import cuda_util
+    rng = np.random.RandomState(seed)
+    maps = _maps(seed + 10)
+    map_id = rng.randint(0, len(maps), B).astype(np.int32)
+    edts = [orc.edt(np.asarray(m['data']) >= 0.1) for m in maps]
+    start = np.zeros((B, 2))
+    for i, m in enumerate(maps):
+        sel = np.where(map_id == i)[0]
+        start[sel] = synth.free_poses(rng, m, len(sel), 14, edts[i])
+    goal = start + rng.uniform(-3, 3, (B, 2))
+    theta = rng.uniform(0, 2 * np.pi, B)
+    md, ms = 12, 16
+    o = orc.OracleBatch(maps, map_id, start, goal, theta, params=dict(t_stop=502.0), max_disc=md, max_seg=ms)
+    c = cuda_util.CudaStepper(maps, map_id, start, goal, theta, max_disc=md, max_seg=ms, early_stop=True)
+    geom = synth.random_geometry(rng, B, start, md, ms)
+    noise = (0.02 * rng.randn(B, 2, 512)).astype(np.float32)
+    o.reset_obs(*geom, noise=noise)
+    c.reset_obs(*geom, noise=noise)
+    _compare(o, c, 'reset', first=True)
+    n_crash = n_succ = n_disc = 0
+    for t in range(T):
+        act = rng.uniform([-0.1, -0.7], [0.55, 0.7], (B, 2)).astype(np.float32)
+        pos = o.state[:2].T.copy()
+        geom = synth.random_geometry(rng, B, pos, md, ms)
+        noise = (0.02 * rng.randn(B, 2, 512)).astype(np.float32)
+        o.step(act, *geom, noise=noise)
+        c.step(act, *geom, noise=noise)
+        _compare(o, c, 'step %d' % t)
+        n_crash += int(o.is_crash.sum())
+        n_succ += int(o.is_success.sum())
+    assert n_crash > 0 and n_succ > 0
+
+
+def _compare(o, c, tag, first=False):
+    assert np.array_equal(c.hits, o.hits), tag + ' hit cells'
+    assert np.array_equal(c.obs[:, :512], o.obs[:, :512]), tag + ' scan'
+    assert np.array_equal(c.steps, o.steps), tag
+    assert np.allclose(c.state, o.state, rtol=0, atol=1e-9), tag + ' state'
+    assert np.allclose(c.tail64, o.tail64, rtol=0, atol=1e-9), tag + ' tail'
+    assert np.allclose(c.obs[:, 512:], o.obs[:, 512:], rtol=1e-6, atol=1e-6), tag
+    if not first:
+        assert np.array_equal(c.done, o.done), tag + ' done'
+        assert np.array_equal(c.is_crash, o.is_crash), tag + ' crash'
+        assert np.array_equal(c.is_success, o.is_success), tag + ' success'
+        assert np.allclose(c.reward, o.reward, rtol=1e-6, atol=2e-6), tag + ' reward'
+        assert np.allclose(c.distance, o.distance, rtol=1e-6, atol=1e-5), tag
+
+
+def test_abi_host_render_matches_oracle():
+    from nav_gym_b200 import natives
+    rng = np.random.RandomState(5)
+    K = 512
+    angles = np.linspace(-3.141592, 3.141592 - 0.0122718463, K) + np.float32(1.234)
+    for _ in range(5):
+        lidar = rng.uniform(2, 8, 2).astype(np.float32)
+        contours = [(lidar + rng.uniform(-4, 4, 2) + np.array([[0.3, 0.2], [-0.3, 0.2], [-0.3, -0.2], [0.3, -0.2]])).tolist()
+                    for _ in range(6)]
+        r1 = np.full(K, 25, np.float32)
+        natives.render_contours_in_lidar(r1, angles, natives.flatten_contours(contours), lidar)
+        r2 = np.full(K, 25, np.float32)
+        _, dirs = orc.beam_dirs(np.float32(0), lin=angles.astype(np.float32).astype(np.float64))
+        orc.render_contours(r2, dirs, orc.flatten_contours(contours), lidar)
+        assert np.array_equal(r1, r2)
+        assert (r1 < 25).any()
