@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(NB, 2) step_kernel(const navgym_step_args_t a)
         float rc = march(a.edt_pool + sm.edt_off, sm.W, sm.H, (float)sm.ci, (float)sm.cj, dx, dy,
                          sm.max_range, fminf(a.t_stop, sm.max_range), hx, hy);
         r = __fmul_rn(rc, sm.res32);
-        if (pass == PASS_STEP && a.hits) {
+        if (pass == (IS_RESET_KERNEL ? PASS_RESET : PASS_STEP) && a.hits) {
             *reinterpret_cast<short2 *>(a.hits + ((size_t)e * NB + tid) * 2) =
                 make_short2((short)hx, (short)hy);
         }
