@@ -140,6 +140,12 @@ int navgym_render_in_lidar_host(float *ranges_host, const float *headings_host, 
                                 const float *segs_host, int S, const float *discs_host, int D,
                                 float ox, float oy);
 
+/* ---- reset path (host only) --------------------------------------------------------- */
+/* 4-connected BFS distance in cells over blocked[H][W] (non-zero = blocked), -1 where
+ * unreachable: the uniform-cost stand-in for pyastar2d.astar_path (env.py:343-354) used to
+ * precompute spawn pools. */
+void navgym_grid_bfs(const uint8_t *blocked, int H, int W, int sr, int sc, int32_t *dist);
+
 /* ---- misc -------------------------------------------------------------------------- */
 const char *navgym_error_string(int code);
 int navgym_device_count(void);

@@ -87,7 +87,7 @@ EXPORTS = [
     'navgym_raymarching_edt_dev', 'navgym_raymarching_destroy',
     'navgym_render_segments_in_lidar', 'navgym_render_discs_in_lidar', 'navgym_render_in_lidar_host',
     'navgym_error_string', 'navgym_device_count', 'navgym_abi_version', 'navgym_launch_count',
-    'navgym_sizeof_step_args', 'navgym_sizeof_map',
+    'navgym_sizeof_step_args', 'navgym_sizeof_map', 'navgym_grid_bfs',
 ]
 
 _lib = None
@@ -121,6 +121,8 @@ def load():
                                                  C.c_float, _P]
     lib.navgym_render_in_lidar_host.argtypes = [_P, _P, C.c_int, _P, C.c_int, _P, C.c_int,
                                                 C.c_float, C.c_float]
+    lib.navgym_grid_bfs.restype = None
+    lib.navgym_grid_bfs.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P]
     lib.navgym_error_string.restype = C.c_char_p
     lib.navgym_error_string.argtypes = [C.c_int]
     lib.navgym_launch_count.restype = C.c_uint64

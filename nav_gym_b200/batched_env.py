@@ -78,6 +78,8 @@ class MapPool(object):
         raw = np.frombuffer(bytes(carr), dtype=np.uint8).copy()
         self.maps_dev = torch.from_numpy(raw).to(self.device)
         self.spawn_pool = None
+        self.spawn_arrays = [None] * n if spawn_pools is None else [
+            None if p is None else np.asarray(p, np.float64).reshape(-1, 5) for p in spawn_pools]
         if spawn_rows:
             self.spawn_pool = torch.from_numpy(np.concatenate(spawn_rows)).to(self.device)
         self.num_maps = n
@@ -87,6 +89,24 @@ class MapPool(object):
         H, W = int(m['height']), int(m['width'])
         off = sum(int(q['width']) * int(q['height']) for q in self.maps[:i])
         return self.edt_pool[off:off + H * W].view(H, W)
+
+
+def filter_spawn_pool(map_info, pool, device='cuda:0', chunk=16384):
+    """Drop spawn tuples whose noise-free first scan already violates the discomfort threshold
+    (the reference re-samples such spawns, env.py:779-783)."""
+    pool = np.asarray(pool, np.float64).reshape(-1, 5)
+    if not len(pool):
+        return pool
+    mp = MapPool([map_info], device)
+    keep = []
+    for s in range(0, len(pool), chunk):
+        p = pool[s:s + chunk]
+        env = BatchedNavGym(len(p), mp, device=device)
+        env.set_state(p[:, 0:2], p[:, 2:4], p[:, 4])
+        obs = env.reset()
+        ok = ~(obs[:, :NB] < env.dthr[None, :]).any(dim=1)
+        keep.append(ok.cpu().numpy())
+    return pool[np.concatenate(keep)]
 
 
 class BatchedNavGym(object):
@@ -155,6 +175,7 @@ class BatchedNavGym(object):
         a.truncated, a.distance, a.hits = _ptr(self.truncated), _ptr(self.distance), _ptr(self.hits)
         self.args = a
         self._keep = None
+        self._act_dev = None
 
     # -------------------------------------------------------------------------------------
     def set_state(self, start, goal, theta, noise_std=None):
@@ -195,6 +216,38 @@ class BatchedNavGym(object):
             assert act.numel() == self.B * 2
             a.actions = _ptr(act)
         self._keep = keep
+
+    def reset_from_spawn_pool(self, rng=None, noise_std_range=None):
+        """Draw every env's (start, goal, theta) from its map's spawn pool (host RNG), set the
+        per-episode scan noise std (reference env_param 'scan_noise_std', __init__.py:36) and
+        compute the first observations."""
+        rng = np.random if rng is None else rng
+        pools = self.pool.spawn_arrays
+        mid = self.map_id.cpu().numpy()
+        rows = np.zeros((self.B, 5))
+        for i in np.unique(mid):
+            sel = np.where(mid == i)[0]
+            if pools[i] is None or not len(pools[i]):
+                raise ValueError('map %d has no spawn pool' % i)
+            rows[sel] = pools[i][rng.randint(len(pools[i]), size=len(sel))]
+        lo, hi = (self.args.noise_lo, self.args.noise_hi) if noise_std_range is None else noise_std_range
+        self.set_state(rows[:, 0:2], rows[:, 2:4], rows[:, 4],
+                       noise_std=rng.uniform(lo, hi, self.B).astype(np.float32))
+        return self.reset()
+
+    def step_host(self, actions_host, obs_host, reward_host, done_host):
+        """The same step for callers that live on the host (the reference's calling
+        convention): pinned host actions in, pinned host obs / reward / done out; the copies
+        ride the env's stream and the call returns when the results have landed."""
+        if self._act_dev is None:
+            self._act_dev = torch.empty(self.B, 2, dtype=torch.float32, device=self.device)
+        self._act_dev.copy_(actions_host, non_blocking=True)
+        self.step(self._act_dev)
+        obs_host.copy_(self.obs, non_blocking=True)
+        reward_host.copy_(self.reward, non_blocking=True)
+        done_host.copy_(self.done, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return obs_host, reward_host, done_host
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

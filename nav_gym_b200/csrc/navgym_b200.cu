@@ -643,6 +643,33 @@ int navgym_raymarching_calc_range_many_host(navgym_raymarching_t *rm, const floa
     return (int)err;
 }
 
+// Reset-path host helper (no device work): 4-connected BFS distance over a grid, the
+// uniform-cost equivalent of pyastar2d.astar_path (reference env.py:343-354).
+void navgym_grid_bfs(const uint8_t *blocked, int H, int W, int sr, int sc, int32_t *dist)
+{
+    size_t n = (size_t)H * W;
+    for (size_t i = 0; i < n; i++) dist[i] = -1;
+    if (sr < 0 || sc < 0 || sr >= H || sc >= W || blocked[(size_t)sr * W + sc]) return;
+    int32_t *queue = new int32_t[n];
+    size_t head = 0, tail = 0;
+    queue[tail++] = sr * W + sc;
+    dist[(size_t)sr * W + sc] = 0;
+    const int dr[4] = {1, -1, 0, 0}, dc[4] = {0, 0, 1, -1};
+    while (head < tail) {
+        int32_t cur = queue[head++];
+        int r = cur / W, c = cur % W;
+        for (int k = 0; k < 4; k++) {
+            int nr = r + dr[k], nc = c + dc[k];
+            if (nr < 0 || nc < 0 || nr >= H || nc >= W) continue;
+            size_t ni = (size_t)nr * W + nc;
+            if (blocked[ni] || dist[ni] >= 0) continue;
+            dist[ni] = dist[cur] + 1;
+            queue[tail++] = (int32_t)ni;
+        }
+    }
+    delete[] queue;
+}
+
 const float *navgym_raymarching_edt_dev(const navgym_raymarching_t *rm) { return rm ? rm->dist : nullptr; }
 
 void navgym_raymarching_destroy(navgym_raymarching_t *rm)
