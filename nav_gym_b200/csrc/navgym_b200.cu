@@ -24,6 +24,7 @@
 #include <math_constants.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/navgym_b200.h"
@@ -170,9 +171,67 @@ __device__ __forceinline__ void beam_window(float phi0, float width, float theta
     if (cnt > NB) cnt = NB;
 }
 
-template <bool IS_RESET_KERNEL>
-__global__ void __launch_bounds__(NB, 2) step_kernel(const navgym_step_args_t a)
+// R rays of one thread marched in lockstep: the R dependent-load chains are independent of
+// each other, so each iteration has R EDT gathers in flight per thread (latency hiding by
+// ILP instead of by occupancy).  Per ray the arithmetic is exactly march()'s.
+template <int R>
+__device__ __forceinline__ void march_multi(const float *__restrict__ dist, int W, int H, float x0,
+                                            float y0, const float (&dx)[R], const float (&dy)[R],
+                                            float max_range, float t_stop, float (&rc)[R],
+                                            int (&hx)[R], int (&hy)[R])
 {
+    float t[R];
+    bool act[R];
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+        t[j] = 0.0f;
+        act[j] = 0.0f < t_stop;
+        rc[j] = max_range;
+        hx[j] = HIT_NONE;
+        hy[j] = HIT_NONE;
+    }
+    for (;;) {
+        float d[R];
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            d[j] = 1.0f;
+            if (act[j]) {
+                int px = __float2int_rz(__fmaf_rn(dx[j], t[j], x0));
+                int py = __float2int_rz(__fmaf_rn(dy[j], t[j], y0));
+                if ((unsigned)px >= (unsigned)W || (unsigned)py >= (unsigned)H) act[j] = false;
+                else d[j] = __ldg(dist + (size_t)py * W + px);
+            }
+        }
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            if (act[j]) {
+                if (d[j] <= 0.0f) {
+                    float xd = __fsub_rn((float)__float2int_rz(__fmaf_rn(dx[j], t[j], x0)), x0);
+                    float yd = __fsub_rn((float)__float2int_rz(__fmaf_rn(dy[j], t[j], y0)), y0);
+                    hx[j] = (int)xd;
+                    hy[j] = (int)yd;
+                    rc[j] = __fsqrt_rn(__fadd_rn(__fmul_rn(xd, xd), __fmul_rn(yd, yd)));
+                    act[j] = false;
+                } else {
+                    t[j] = __fadd_rn(t[j], fmaxf(__fmul_rn(d[j], 0.999f), 1.0f));
+                    act[j] = t[j] < t_stop;
+                }
+            }
+            any |= act[j];
+        }
+        if (!any) break;
+    }
+}
+
+// One CTA = one environment; TPB threads, each owning R = 512 / TPB beams (tid, tid + TPB, ...:
+// a warp's lanes hold adjacent beams, whose gathers share cache lines).
+template <bool IS_RESET_KERNEL, int TPB>
+__global__ void __launch_bounds__(TPB, (TPB >= 512 ? 2 : (TPB == 256 ? 4 : 8)))
+step_kernel(const navgym_step_args_t a)
+{
+    constexpr int R = NB / TPB;
+    constexpr int NW = TPB / 32;
     __shared__ StepSmem sm;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -237,13 +296,11 @@ __global__ void __launch_bounds__(NB, 2) step_kernel(const navgym_step_args_t a)
     {
         int nd = a.discs ? min(a.ndisc[e], min(a.max_disc, NAVGYM_MAX_DISC)) : 0;
         int ns = a.segs ? min(a.nseg[e], min(a.max_seg, NAVGYM_MAX_SEG)) : 0;
-        for (int i = tid; i < nd * 3; i += NB) sm.discs[i] = a.discs[(size_t)e * a.max_disc * 3 + i];
-        for (int i = tid; i < ns * 4; i += NB) sm.segs[i] = a.segs[(size_t)e * a.max_seg * 4 + i];
+        for (int i = tid; i < nd * 3; i += TPB) sm.discs[i] = a.discs[(size_t)e * a.max_disc * 3 + i];
+        for (int i = tid; i < ns * 4; i += TPB) sm.segs[i] = a.segs[(size_t)e * a.max_seg * 4 + i];
         if (tid == 0) { sm.nd = nd; sm.ns = ns; }
     }
-    const double lin_k = a.lin[tid];
-    const float thr_k = a.thr[tid], dthr_k = a.dthr[tid];
-    float r = 0.0f;
+    float r[R];
     int pass = IS_RESET_KERNEL ? PASS_RESET : PASS_STEP;
 
     for (;;) {
@@ -258,29 +315,43 @@ __global__ void __launch_bounds__(NB, 2) step_kernel(const navgym_step_args_t a)
             sm.max_range = (float)((double)m.W * (double)m.H);
         }
         __syncthreads();
-        // ---- beam direction + occupancy-grid march (env.py:388-390, 420-426)
-        const float h = (float)__dadd_rn(lin_k, (double)sm.lt);
-        double sd, cd;
-        sincos((double)h, &sd, &cd);
-        const float dx = (float)cd, dy = (float)sd;
-        int hx, hy;
-        float rc = march(a.edt_pool + sm.edt_off, sm.W, sm.H, (float)sm.ci, (float)sm.cj, dx, dy,
-                         sm.max_range, fminf(a.t_stop, sm.max_range), hx, hy);
-        r = __fmul_rn(rc, sm.res32);
-        if (pass == (IS_RESET_KERNEL ? PASS_RESET : PASS_STEP) && a.hits) {
-            *reinterpret_cast<short2 *>(a.hits + ((size_t)e * NB + tid) * 2) =
-                make_short2((short)hx, (short)hy);
+        // ---- beam directions + occupancy-grid march (env.py:388-390, 420-426)
+        float dx[R], dy[R];
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            const float h = (float)__dadd_rn(a.lin[tid + j * TPB], (double)sm.lt);
+            double sd, cd;
+            sincos((double)h, &sd, &cd);
+            dx[j] = (float)cd;
+            dy[j] = (float)sd;
+        }
+        {
+            float rc[R];
+            int hx[R], hy[R];
+            march_multi<R>(a.edt_pool + sm.edt_off, sm.W, sm.H, (float)sm.ci, (float)sm.cj, dx, dy,
+                           sm.max_range, fminf(a.t_stop, sm.max_range), rc, hx, hy);
+            const bool rec = pass == (IS_RESET_KERNEL ? PASS_RESET : PASS_STEP) && a.hits;
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                r[j] = __fmul_rn(rc[j], sm.res32);
+                if (rec)
+                    *reinterpret_cast<short2 *>(a.hits + ((size_t)e * NB + tid + j * TPB) * 2) =
+                        make_short2((short)hx[j], (short)hy[j]);
+            }
         }
         const int nobs = sm.nd + sm.ns;
         if (nobs > 0) {
             // ---- pedestrians: segments (env.py:430-431) and discs (env.py:432), min-merged.
             // One warp per obstacle, lanes across the beams of its angular window.
-            sm.scan[tid] = __float_as_int(r);
-            sm.dx[tid] = dx;
-            sm.dy[tid] = dy;
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                sm.scan[tid + j * TPB] = __float_as_int(r[j]);
+                sm.dx[tid + j * TPB] = dx[j];
+                sm.dy[tid + j * TPB] = dy[j];
+            }
             __syncthreads();
             const float ox = sm.lx, oy = sm.ly, th = sm.lt;
-            for (int o = warp; o < nobs; o += NB / 32) {
+            for (int o = warp; o < nobs; o += NW) {
                 int k0, cnt;
                 if (o < sm.ns) {
                     const float ax = sm.segs[4 * o], ay = sm.segs[4 * o + 1];
@@ -299,44 +370,59 @@ __global__ void __launch_bounds__(NB, 2) step_kernel(const navgym_step_args_t a)
                     }
                 } else {
                     const int q = o - sm.ns;
-                    const float X = sm.discs[3 * q], Y = sm.discs[3 * q + 1], R = sm.discs[3 * q + 2];
+                    const float X = sm.discs[3 * q], Y = sm.discs[3 * q + 1], Rd = sm.discs[3 * q + 2];
                     float cx = X - ox, cy = Y - oy;
                     float dc = sqrtf(cx * cx + cy * cy);
-                    if (dc <= R * 1.05f + 1e-3f) { k0 = 0; cnt = NB; }
+                    if (dc <= Rd * 1.05f + 1e-3f) { k0 = 0; cnt = NB; }
                     else {
-                        float half = asinf(fminf(R / dc, 1.0f)) * 1.01f + 1e-4f;
+                        float half = asinf(fminf(Rd / dc, 1.0f)) * 1.01f + 1e-4f;
                         beam_window(atan2f(cy, cx) - half, 2.0f * half, th, k0, cnt);
                     }
                     for (int i = lane; i < cnt; i += 32) {
                         int k = (k0 + i) & (NB - 1);
-                        float t = disc_hit(ox, oy, sm.dx[k], sm.dy[k], X, Y, R);
+                        float t = disc_hit(ox, oy, sm.dx[k], sm.dy[k], X, Y, Rd);
                         if (t < CUDART_INF_F) atomicMin(&sm.scan[k], __float_as_int(t));
                     }
                 }
             }
             __syncthreads();
-            r = __int_as_float(sm.scan[tid]);
+#pragma unroll
+            for (int j = 0; j < R; j++) r[j] = __int_as_float(sm.scan[tid + j * TPB]);
         }
         // ---- clip + noise (env.py:435-440)
-        r = fminf(fmaxf(r, 0.0f), a.range_max);
-        if (r != a.range_max) {
-            if (a.noise) {
-                int slot = pass == PASS_RESCAN ? 1 : 0;
-                r = __fadd_rn(r, a.noise[((size_t)e * 2 + slot) * NB + tid]);
-            } else if (sm.noise_std > 0.0f) {
-                r = __fadd_rn(r, sm.noise_std * beam_normal(a.seed, (uint32_t)(a.env_offset + e),
-                                                           (uint32_t)sm.episode, (uint32_t)sm.steps,
-                                                           (uint32_t)pass, (uint32_t)tid));
+        bool c_any = false, d_any = false;
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            const int k = tid + j * TPB;
+            float v = fminf(fmaxf(r[j], 0.0f), a.range_max);
+            if (v != a.range_max) {
+                if (a.noise) {
+                    int slot = pass == PASS_RESCAN ? 1 : 0;
+                    v = __fadd_rn(v, a.noise[((size_t)e * 2 + slot) * NB + k]);
+                } else if (sm.noise_std > 0.0f) {
+                    v = __fadd_rn(v, sm.noise_std * beam_normal(a.seed, (uint32_t)(a.env_offset + e),
+                                                               (uint32_t)sm.episode, (uint32_t)sm.steps,
+                                                               (uint32_t)pass, (uint32_t)k));
+                }
             }
+            r[j] = v;
+            c_any |= v < a.thr[k];
+            d_any |= v < a.dthr[k];
         }
 
         if (pass == PASS_STEP) {
             // ---- reward / done / info on this observation (env.py:464-589)
-            const int crash = __syncthreads_or(r < thr_k);
-            const int discomf = __syncthreads_or(r < dthr_k) && !crash;
+            const int crash = __syncthreads_or(c_any);
+            const int discomf = __syncthreads_or(d_any) && !crash;
             if (discomf) {
-                float den = __fadd_rn(__fsub_rn(dthr_k, thr_k), 1e-6f);
-                double q = __ddiv_rn(__dsub_rn((double)r, (double)thr_k), (double)den);
+                double q = CUDART_INF;
+#pragma unroll
+                for (int j = 0; j < R; j++) {
+                    const int k = tid + j * TPB;
+                    const float thr_k = a.thr[k], dthr_k = a.dthr[k];
+                    float den = __fadd_rn(__fsub_rn(dthr_k, thr_k), 1e-6f);
+                    q = fmin(q, __ddiv_rn(__dsub_rn((double)r[j], (double)thr_k), (double)den));
+                }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) q = fmin(q, __shfl_xor_sync(0xffffffffu, q, o));
                 if (lane == 0) sm.red[warp] = q;
@@ -345,7 +431,7 @@ __global__ void __launch_bounds__(NB, 2) step_kernel(const navgym_step_args_t a)
             if (tid == 0) {
                 double mn = CUDART_INF;
                 if (discomf)
-                    for (int i = 0; i < NB / 32; i++) mn = fmin(mn, sm.red[i]);
+                    for (int i = 0; i < NW; i++) mn = fmin(mn, sm.red[i]);
                 const double px = sm.px, py = sm.py;
                 double dxg = __dsub_rn(sm.gx, px), dyg = __dsub_rn(sm.gy, py);
                 double dist = sqrt(__dadd_rn(__dmul_rn(dxg, dxg), __dmul_rn(dyg, dyg)));
@@ -414,7 +500,8 @@ __global__ void __launch_bounds__(NB, 2) step_kernel(const navgym_step_args_t a)
 
     // ---------------- epilogue: observation row + state (env.py:455, 725-727) -----------
     float *o = a.obs + (size_t)e * a.obs_stride;
-    o[tid] = r;
+#pragma unroll
+    for (int j = 0; j < R; j++) o[tid + j * TPB] = r[j];
     if (tid == 0) {
         double sn, cn;
         sincos(sm.th, &sn, &cn);
@@ -506,6 +593,30 @@ __global__ void render_in_lidar_kernel(float *__restrict__ ranges, const float *
 }
 
 // ------------------------------------------------------------------ C ABI
+// threads per environment (rays per thread = 512 / TPB); NAVGYM_TPB overrides for tuning runs
+static int g_tpb = 0;
+static int step_tpb()
+{
+    if (g_tpb == 0) {
+        const char *s = getenv("NAVGYM_TPB");
+        int v = s ? atoi(s) : 128;
+        g_tpb = (v == 512 || v == 256 || v == 128 || v == 64) ? v : 128;
+    }
+    return g_tpb;
+}
+
+template <bool RESET>
+static void launch_step(const navgym_step_args_t &a, cudaStream_t st)
+{
+    switch (step_tpb()) {
+    case 512: step_kernel<RESET, 512><<<a.num_envs, 512, 0, st>>>(a); break;
+    case 256: step_kernel<RESET, 256><<<a.num_envs, 256, 0, st>>>(a); break;
+    case 64: step_kernel<RESET, 64><<<a.num_envs, 64, 0, st>>>(a); break;
+    default: step_kernel<RESET, 128><<<a.num_envs, 128, 0, st>>>(a); break;
+    }
+    g_launches++;
+}
+
 #define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return (int)_e; } while (0)
 
 extern "C" {
@@ -526,8 +637,7 @@ int navgym_step_batch(const navgym_step_args_t *args, void *stream)
 {
     if (args->num_envs <= 0) return 0;
     if (args->obs_stride < OBS_DIM) return (int)cudaErrorInvalidValue;
-    step_kernel<false><<<args->num_envs, NB, 0, (cudaStream_t)stream>>>(*args);
-    g_launches++;
+    launch_step<false>(*args, (cudaStream_t)stream);
     return (int)cudaGetLastError();
 }
 
@@ -535,8 +645,7 @@ int navgym_reset_obs_batch(const navgym_step_args_t *args, void *stream)
 {
     if (args->num_envs <= 0) return 0;
     if (args->obs_stride < OBS_DIM) return (int)cudaErrorInvalidValue;
-    step_kernel<true><<<args->num_envs, NB, 0, (cudaStream_t)stream>>>(*args);
-    g_launches++;
+    launch_step<true>(*args, (cudaStream_t)stream);
     return (int)cudaGetLastError();
 }
 
