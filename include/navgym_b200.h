@@ -39,7 +39,7 @@ enum {
 /* One occupancy map of the pool (reference map_info dict, map_generator.py:113-122). */
 typedef struct {
     int32_t W, H;            /* cells */
-    int64_t edt_offset;      /* element offset of this map's float EDT in edt_pool */
+    int64_t edt_offset;      /* element offset of this map's float EDT ([H][W]) in edt_pool */
     double ox, oy, res;      /* origin [m], resolution [m/cell] */
     int64_t spawn_offset;    /* first row of this map's spawn tuples in spawn_pool */
     int32_t spawn_count;     /* 0 = map has no spawn pool */
@@ -76,10 +76,11 @@ typedef struct {
     int32_t resample_map;    /* 1: auto-reset also draws a new map id */
     uint64_t seed;
     int64_t env_offset;      /* global index of env 0 (multi-GPU sharding) */
+    int64_t _reserved;
     float noise_lo, noise_hi; /* scan_noise_std range resampled at auto-reset */
     /* ---- device pointers ---- */
     const navgym_map_t *maps;
-    const float *edt_pool;
+    const float *edt_pool;      /* per-map float EDTs as built by navgym_edt_build */
     const double *spawn_pool;   /* [rows][5] = sx, sy, gx, gy, theta */
     int32_t *map_id;
     const double *lin;          /* [512] beam angle table (env.py:388-390) */
@@ -124,6 +125,7 @@ navgym_raymarching_t *navgym_raymarching_create_host(const uint8_t *occ_host, in
 int navgym_raymarching_calc_range_many_host(navgym_raymarching_t *rm, const float *ins_host,
                                             float *outs_host, int N);
 const float *navgym_raymarching_edt_dev(const navgym_raymarching_t *rm);
+int navgym_raymarching_edt_host(const navgym_raymarching_t *rm, float *out_host); /* [H][W] */
 void navgym_raymarching_destroy(navgym_raymarching_t *rm);
 
 /* ---- inner native boundary: pymap2d ------------------------------------------------ */

@@ -13,7 +13,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SRC = os.path.join(_PKG, 'csrc', 'navgym_b200.cu')
 HDR = os.path.join(_ROOT, 'include', 'navgym_b200.h')
-SO = os.path.join(_PKG, 'libnavgym_b200.so')
+SO = os.environ.get('NAVGYM_LIB') or os.path.join(_PKG, 'libnavgym_b200.so')
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-fmad=false',
               '-shared', '-Xcompiler', '-fPIC', '-std=c++17']
@@ -69,6 +69,7 @@ class StepArgs(C.Structure):
         ('num_envs', C.c_int32), ('obs_stride', C.c_int32), ('auto_reset', C.c_int32),
         ('max_episode_steps', C.c_int32), ('num_maps', C.c_int32), ('resample_map', C.c_int32),
         ('seed', C.c_uint64), ('env_offset', C.c_int64),
+        ('_reserved', C.c_int64),
         ('noise_lo', C.c_float), ('noise_hi', C.c_float),
         ('maps', _P), ('edt_pool', _P), ('spawn_pool', _P), ('map_id', _P),
         ('lin', _P), ('thr', _P), ('dthr', _P),
@@ -84,7 +85,7 @@ class StepArgs(C.Structure):
 EXPORTS = [
     'navgym_step_batch', 'navgym_reset_obs_batch', 'navgym_edt_build', 'navgym_calc_range_many',
     'navgym_raymarching_create_host', 'navgym_raymarching_calc_range_many_host',
-    'navgym_raymarching_edt_dev', 'navgym_raymarching_destroy',
+    'navgym_raymarching_edt_dev', 'navgym_raymarching_edt_host', 'navgym_raymarching_destroy',
     'navgym_render_segments_in_lidar', 'navgym_render_discs_in_lidar', 'navgym_render_in_lidar_host',
     'navgym_error_string', 'navgym_device_count', 'navgym_abi_version', 'navgym_launch_count',
     'navgym_sizeof_step_args', 'navgym_sizeof_map', 'navgym_grid_bfs',
@@ -113,6 +114,7 @@ def load():
     lib.navgym_raymarching_calc_range_many_host.argtypes = [_P, _P, _P, C.c_int]
     lib.navgym_raymarching_edt_dev.restype = _P
     lib.navgym_raymarching_edt_dev.argtypes = [_P]
+    lib.navgym_raymarching_edt_host.argtypes = [_P, _P]
     lib.navgym_raymarching_destroy.restype = None
     lib.navgym_raymarching_destroy.argtypes = [_P]
     lib.navgym_render_segments_in_lidar.argtypes = [_P, _P, C.c_int, _P, C.c_int, C.c_float,

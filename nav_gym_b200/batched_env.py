@@ -41,19 +41,26 @@ def scan_thresholds(device):
 
 
 class MapPool(object):
-    """Occupancy maps resident in HBM as exact float32 Euclidean distance transforms
-    (what range_libc's PyRayMarching holds per map, env.py:337-340), plus optional per-map
-    spawn pools of (start, goal, theta) tuples for device-side auto-reset."""
+    """Occupancy maps resident in HBM as exact float32 Euclidean distance transforms, [H][W]
+    row-major per map (what range_libc's PyRayMarching holds per map, env.py:337-340), plus
+    optional per-map spawn pools of (start, goal, theta) tuples for device-side auto-reset."""
 
     def __init__(self, maps, device, spawn_pools=None):
         lib = _lib.require_device()
         self.device = torch.device(device)
         self.maps = maps
         n = len(maps)
-        sizes = [int(m['width']) * int(m['height']) for m in maps]
-        self.edt_pool = torch.empty(sum(sizes), dtype=torch.float32, device=self.device)
+        self.spawn_arrays = [None] * n if spawn_pools is None else [
+            None if p is None else np.asarray(p, np.float64).reshape(-1, 5) for p in spawn_pools]
+        self.num_maps = n
+        self.offsets = []
+        off = 0
+        for m in maps:
+            self.offsets.append(off)
+            off += int(m['height']) * int(m['width'])
+        self.edt_pool = torch.empty(off, dtype=torch.float32, device=self.device)
         carr = (_lib.MapT * n)()
-        off, soff = 0, 0
+        soff = 0
         spawn_rows = []
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
@@ -62,42 +69,36 @@ class MapPool(object):
                 occ = torch.from_numpy(np.ascontiguousarray(np.asarray(m['data']) >= 0.1).astype(np.uint8))
                 occ = occ.to(self.device)
                 scratch = torch.empty(H * W, dtype=torch.int32, device=self.device)
-                dist = self.edt_pool[off:off + H * W]
+                dist = self.edt_pool[self.offsets[i]:self.offsets[i] + H * W]
                 _lib.check(lib.navgym_edt_build(_ptr(occ), H, W, _ptr(dist), _ptr(scratch),
                                                 C.c_void_p(stream)), 'edt_build')
                 cnt = 0
-                if spawn_pools is not None and spawn_pools[i] is not None and len(spawn_pools[i]):
-                    sp = np.ascontiguousarray(spawn_pools[i], np.float64).reshape(-1, 5)
-                    spawn_rows.append(sp)
-                    cnt = len(sp)
-                carr[i] = _lib.MapT(W, H, off, float(m['origin'][0]), float(m['origin'][1]),
+                if self.spawn_arrays[i] is not None and len(self.spawn_arrays[i]):
+                    spawn_rows.append(self.spawn_arrays[i])
+                    cnt = len(self.spawn_arrays[i])
+                carr[i] = _lib.MapT(W, H, self.offsets[i], float(m['origin'][0]), float(m['origin'][1]),
                                     float(m['resolution']), soff, cnt, 0)
-                off += H * W
                 soff += cnt
             torch.cuda.synchronize(self.device)
         raw = np.frombuffer(bytes(carr), dtype=np.uint8).copy()
         self.maps_dev = torch.from_numpy(raw).to(self.device)
         self.spawn_pool = None
-        self.spawn_arrays = [None] * n if spawn_pools is None else [
-            None if p is None else np.asarray(p, np.float64).reshape(-1, 5) for p in spawn_pools]
         if spawn_rows:
             self.spawn_pool = torch.from_numpy(np.concatenate(spawn_rows)).to(self.device)
-        self.num_maps = n
 
     def edt(self, i):
         m = self.maps[i]
         H, W = int(m['height']), int(m['width'])
-        off = sum(int(q['width']) * int(q['height']) for q in self.maps[:i])
-        return self.edt_pool[off:off + H * W].view(H, W)
+        return self.edt_pool[self.offsets[i]:self.offsets[i] + H * W].view(H, W)
 
 
-def filter_spawn_pool(map_info, pool, device='cuda:0', chunk=16384):
+def filter_spawn_pool(map_info, pool, device='cuda:0', chunk=16384, map_pool=None):
     """Drop spawn tuples whose noise-free first scan already violates the discomfort threshold
     (the reference re-samples such spawns, env.py:779-783)."""
     pool = np.asarray(pool, np.float64).reshape(-1, 5)
     if not len(pool):
         return pool
-    mp = MapPool([map_info], device)
+    mp = map_pool if map_pool is not None else MapPool([map_info], device)
     keep = []
     for s in range(0, len(pool), chunk):
         p = pool[s:s + chunk]

@@ -134,27 +134,30 @@ __device__ __forceinline__ float beam_normal(uint64_t seed, uint32_t env, uint32
 }
 
 // ------------------------------------------------------------------ fused step kernel
-struct __align__(16) StepSmem {
-    int scan[NB];  // float bits; non-negative floats order like ints -> atomicMin works
-    float dx[NB], dy[NB];
-    float discs[NAVGYM_MAX_DISC * 3];
-    float segs[NAVGYM_MAX_SEG * 4];
-    double red[NB / 32];
-    double px, py, th;         // pose the current pass scans from
-    double ppx, ppy, pyaw;     // prev_obs fields
-    double gx, gy, pv, pw;
-    double c0, s0, c1, s1;     // cos/sin of theta before / after the turn
-    double reward, dist;
-    float lx, ly, lt;
-    float res32, max_range;
-    int ci, cj, W, H;
-    int nd, ns;
-    int map;
-    int steps, episode;
-    int crash, success, done, trunc;
-    int next_pass;
-    long long edt_off;
+// Optional per-phase cycle accounting (tools/phase_prof.py builds with -DNAVGYM_PROFILE).
+#ifdef NAVGYM_PROFILE
+__device__ unsigned long long g_prof[16];
+#define PROF_DECL long long _pt = clock64();
+#define PROF_MARK(i) do { if (tid == 0) { long long _n = clock64(); atomicAdd(&g_prof[i], (unsigned long long)(_n - _pt)); _pt = _n; } } while (0)
+#else
+#define PROF_DECL
+#define PROF_MARK(i)
+#endif
+
+struct EnvSmem {
+    int scan[NB];          // float bits of the ranges [m] (non-negative floats order like ints)
+    float2 dir[NB];        // beam directions (cos, sin) of the current pass
+    double red[16];
+    // per-environment scalars parked here between the phases that need them, so the march
+    // loop runs with a small register footprint
+    double px, py, th, gx, gy, ppx, ppy, pyaw, pv, pw, act_v, act_w;
+    int map, steps, episode, next_pass;
+    int next_beam;         // next undealt beam of the scan in flight
     float noise_std;
+    // per-pass scan setup
+    float lx, ly, lt, res32, max_range, t_stop;
+    int ci, cj, W, H;
+    long long edt_off;
 };
 
 enum { PASS_STEP = 0, PASS_RESCAN = 1, PASS_RESET = 2, PASS_END = 3 };
@@ -171,140 +174,114 @@ __device__ __forceinline__ void beam_window(float phi0, float width, float theta
     if (cnt > NB) cnt = NB;
 }
 
-// R rays of one thread marched in lockstep: the R dependent-load chains are independent of
-// each other, so each iteration has R EDT gathers in flight per thread (latency hiding by
-// ILP instead of by occupancy).  Per ray the arithmetic is exactly march()'s.
-template <int R>
-__device__ __forceinline__ void march_multi(const float *__restrict__ dist, int W, int H, float x0,
-                                            float y0, const float (&dx)[R], const float (&dy)[R],
-                                            float max_range, float t_stop, float (&rc)[R],
-                                            int (&hx)[R], int (&hy)[R])
+// float -> cell index with C truncation semantics for x > -1, without the conversion pipe:
+// 2^23 + x rounded toward zero leaves trunc(x) in the mantissa (x in [0, 2^23)).
+__device__ __forceinline__ int trunc_cell(float x)
 {
-    float t[R];
-    bool act[R];
-#pragma unroll
-    for (int j = 0; j < R; j++) {
-        t[j] = 0.0f;
-        act[j] = 0.0f < t_stop;
-        rc[j] = max_range;
-        hx[j] = HIT_NONE;
-        hy[j] = HIT_NONE;
-    }
-    for (;;) {
-        float d[R];
-#pragma unroll
-        for (int j = 0; j < R; j++) {
-            d[j] = 1.0f;
-            if (act[j]) {
-                int px = __float2int_rz(__fmaf_rn(dx[j], t[j], x0));
-                int py = __float2int_rz(__fmaf_rn(dy[j], t[j], y0));
-                if ((unsigned)px >= (unsigned)W || (unsigned)py >= (unsigned)H) act[j] = false;
-                else d[j] = __ldg(dist + (size_t)py * W + px);
-            }
-        }
-        bool any = false;
-#pragma unroll
-        for (int j = 0; j < R; j++) {
-            if (act[j]) {
-                if (d[j] <= 0.0f) {
-                    float xd = __fsub_rn((float)__float2int_rz(__fmaf_rn(dx[j], t[j], x0)), x0);
-                    float yd = __fsub_rn((float)__float2int_rz(__fmaf_rn(dy[j], t[j], y0)), y0);
-                    hx[j] = (int)xd;
-                    hy[j] = (int)yd;
-                    rc[j] = __fsqrt_rn(__fadd_rn(__fmul_rn(xd, xd), __fmul_rn(yd, yd)));
-                    act[j] = false;
-                } else {
-                    t[j] = __fadd_rn(t[j], fmaxf(__fmul_rn(d[j], 0.999f), 1.0f));
-                    act[j] = t[j] < t_stop;
-                }
-            }
-            any |= act[j];
-        }
-        if (!any) break;
-    }
+    return __float_as_int(__fadd_rz(fmaxf(x, 0.0f), 8388608.0f)) & 0x007fffff;
 }
 
-// One CTA = one environment; TPB threads, each owning R = 512 / TPB beams (tid, tid + TPB, ...:
-// a warp's lanes hold adjacent beams, whose gathers share cache lines).
-template <bool IS_RESET_KERNEL, int TPB>
-__global__ void __launch_bounds__(TPB, (TPB >= 512 ? 2 : (TPB == 256 ? 4 : 8)))
-step_kernel(const navgym_step_args_t a)
+__device__ __forceinline__ void normal4(uint64_t seed, uint32_t env, uint32_t episode, uint32_t step,
+                                        uint32_t slot, uint32_t group, float (&z)[4])
 {
-    constexpr int R = NB / TPB;
-    constexpr int NW = TPB / 32;
-    __shared__ StepSmem sm;
+    uint4 r = philox4x32_10(make_uint4(env, episode, step, (slot << 16) | group),
+                            make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    float r0 = sqrtf(-2.0f * __logf(u01(r.x))), r1 = sqrtf(-2.0f * __logf(u01(r.z)));
+    float s0, c0, s1, c1;
+    __sincosf(6.283185307179586f * u01(r.y), &s0, &c0);
+    __sincosf(6.283185307179586f * u01(r.w), &s1, &c1);
+    z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
+}
+
+// One CTA = one environment, WPE warps.  Lane l of warp w owns beams l + 32 (w + WPE i),
+// i = 0 .. 16/WPE - 1: at any moment the lanes of a warp work on neighbouring beams, whose
+// EDT gathers share sectors.  Each lane walks its beams through MARCH_SLOTS independent march
+// slots; a slot that finishes a beam immediately starts the lane's next one, so lanes stay
+// busy instead of idling until the slowest beam of a lockstep group ends, and MARCH_SLOTS
+// gathers per lane are in flight.  The three scans a step may need (the step's scan, the
+// crash re-scan env.py:718, the auto-reset first scan) run through ONE copy of the scan code
+// inside a CTA-uniform pass loop.
+template <bool IS_RESET_KERNEL, int WPE, int MARCH_SLOTS>
+__global__ void __launch_bounds__(WPE * 32, 1024 / (WPE * 32)) step_kernel(const navgym_step_args_t a)
+{
+    constexpr int BPL = NB / (32 * WPE);  // beams per lane
+    constexpr int TPB = WPE * 32;
+    static_assert(BPL >= MARCH_SLOTS && BPL % MARCH_SLOTS == 0, "beams per lane vs slots");
+    __shared__ EnvSmem sm;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int e = blockIdx.x;
     const int B = a.num_envs;
+    const unsigned FULL = 0xffffffffu;
     double *S = a.state;
 #define ST(f) S[(size_t)(f) * B + e]
+#define BEAM(i) (tid + TPB * (i))
 
-    // ---------------- prologue: state, kinematics (keti_robot.py:64-93) -----------------
+    PROF_DECL
+    // ---------------- prologue (warp 0): state (lane f holds row f), kinematics ----------
     if (warp == 0) {
-        double th0 = ST(NAVGYM_S_TH);
-        double v = 0, w = 0;
+        double sv = lane < NAVGYM_NS ? ST(lane) : 0.0;
+        double px = __shfl_sync(FULL, sv, NAVGYM_S_PX), py = __shfl_sync(FULL, sv, NAVGYM_S_PY);
+        double th0 = __shfl_sync(FULL, sv, NAVGYM_S_TH), th = th0;
+        double act_v = 0, act_w = 0;
+        int steps = a.steps[e];
         if (!IS_RESET_KERNEL) {
-            v = (double)a.actions[2 * e];
-            w = (double)a.actions[2 * e + 1];
+            const float2 av = *reinterpret_cast<const float2 *>(a.actions + 2 * (size_t)e);
+            double v = (double)av.x, w = (double)av.y;
+            if (a.min_turn_radius > 0) {  // env.py:595-600
+                double lim = __dmul_rn(fabs(w), a.min_turn_radius);
+                if (v >= 0) v = v > lim ? v : lim;
+                else v = v < -lim ? v : -lim;
+            }
+            act_v = a.min_turn_radius > 0 ? v : (double)av.x;  // env.py:725 (the clamp edits `action`)
+            act_w = (double)av.y;
+            double th1 = __dadd_rn(th0, __dmul_rn(w, a.dt));
+            double s_, c_;
+            sincos(lane == 0 ? th0 : th1, &s_, &c_);  // lanes 0 / 1 in parallel
+            double s0 = __shfl_sync(FULL, s_, 0), c0 = __shfl_sync(FULL, c_, 0);
+            double s1 = __shfl_sync(FULL, s_, 1), c1 = __shfl_sync(FULL, c_, 1);
+            // keti_robot.py:64-93
+            double rx = __dadd_rn(__dmul_rn(0.14474, c0), px);
+            double ry = __dadd_rn(__dmul_rn(0.14474, s0), py);
+            rx = __dadd_rn(rx, __dmul_rn(__dmul_rn(c1, v), a.dt));
+            ry = __dadd_rn(ry, __dmul_rn(__dmul_rn(s1, v), a.dt));
+            px = __dadd_rn(__dmul_rn(-0.14474, c1), rx);
+            py = __dadd_rn(__dmul_rn(-0.14474, s1), ry);
+            const double twopi = 6.283185307179586;
+            th = fmod(th1, twopi);
+            if (th != 0 && th < 0) th = __dadd_rn(th, twopi);
+            steps += 1;  // env.py:592
+        } else {
+            steps = 0;
         }
-        if (!IS_RESET_KERNEL && a.min_turn_radius > 0) {  // env.py:595-600
-            double lim = __dmul_rn(fabs(w), a.min_turn_radius);
-            if (v >= 0) v = v > lim ? v : lim;
-            else v = v < -lim ? v : -lim;
-        }
-        double th1 = __dadd_rn(th0, __dmul_rn(w, a.dt));
-        // lanes 0/1 evaluate the two sincos in parallel
-        double sv, cv;
-        sincos(lane == 0 ? th0 : th1, &sv, &cv);
-        double s1 = __shfl_sync(0xffffffffu, sv, 1), c1 = __shfl_sync(0xffffffffu, cv, 1);
         if (lane == 0) {
-            double px = ST(NAVGYM_S_PX), py = ST(NAVGYM_S_PY), thn = th0;
+            sm.px = px; sm.py = py; sm.th = th;
+            sm.act_v = act_v; sm.act_w = act_w;
             sm.map = a.map_id[e];
-            sm.steps = a.steps[e];
+            sm.steps = steps;
             sm.episode = a.episodes ? a.episodes[e] : 0;
             sm.noise_std = a.noise_std ? a.noise_std[e] : 0.0f;
-            if (!IS_RESET_KERNEL) {
-                double rx = __dadd_rn(__dmul_rn(0.14474, cv), px);
-                double ry = __dadd_rn(__dmul_rn(0.14474, sv), py);
-                rx = __dadd_rn(rx, __dmul_rn(__dmul_rn(c1, v), a.dt));
-                ry = __dadd_rn(ry, __dmul_rn(__dmul_rn(s1, v), a.dt));
-                px = __dadd_rn(__dmul_rn(-0.14474, c1), rx);
-                py = __dadd_rn(__dmul_rn(-0.14474, s1), ry);
-                const double twopi = 6.283185307179586;
-                thn = fmod(th1, twopi);
-                if (thn != 0 && thn < 0) thn = __dadd_rn(thn, twopi);
-                sm.steps += 1;  // env.py:592
-                sm.ppx = ST(NAVGYM_S_PPX); sm.ppy = ST(NAVGYM_S_PPY); sm.pyaw = ST(NAVGYM_S_PYAW);
-                sm.pv = ST(NAVGYM_S_PV); sm.pw = ST(NAVGYM_S_PW);
-                // prev_action after this step (env.py:725; the Ackermann clamp edits `action`)
-                ST(NAVGYM_S_PV) = a.min_turn_radius > 0 ? v : (double)a.actions[2 * e];
-                ST(NAVGYM_S_PW) = (double)a.actions[2 * e + 1];
-            } else {
-                sm.steps = 0;
-                sm.ppx = px; sm.ppy = py; sm.pv = 0; sm.pw = 0; sm.pyaw = 0;
-                ST(NAVGYM_S_PV) = 0; ST(NAVGYM_S_PW) = 0;
-            }
-            sm.px = px; sm.py = py; sm.th = thn;
-            sm.gx = ST(NAVGYM_S_GX); sm.gy = ST(NAVGYM_S_GY);
-            sm.next_pass = IS_RESET_KERNEL ? PASS_RESET : PASS_STEP;
-            sm.crash = 0; sm.success = 0; sm.done = 0; sm.trunc = 0;
-            sm.reward = 0; sm.dist = 0;
+            if (IS_RESET_KERNEL) { sm.ppx = px; sm.ppy = py; sm.pyaw = 0; sm.pv = 0; sm.pw = 0; }
+        }
+        if (lane == NAVGYM_S_GX) sm.gx = sv;
+        if (lane == NAVGYM_S_GY) sm.gy = sv;
+        if (!IS_RESET_KERNEL) {
+            if (lane == NAVGYM_S_PPX) sm.ppx = sv;
+            if (lane == NAVGYM_S_PPY) sm.ppy = sv;
+            if (lane == NAVGYM_S_PYAW) sm.pyaw = sv;
+            if (lane == NAVGYM_S_PV) sm.pv = sv;
+            if (lane == NAVGYM_S_PW) sm.pw = sv;
         }
     }
-    // obstacles of this env -> shared (they do not move within a step)
-    {
-        int nd = a.discs ? min(a.ndisc[e], min(a.max_disc, NAVGYM_MAX_DISC)) : 0;
-        int ns = a.segs ? min(a.nseg[e], min(a.max_seg, NAVGYM_MAX_SEG)) : 0;
-        for (int i = tid; i < nd * 3; i += TPB) sm.discs[i] = a.discs[(size_t)e * a.max_disc * 3 + i];
-        for (int i = tid; i < ns * 4; i += TPB) sm.segs[i] = a.segs[(size_t)e * a.max_seg * 4 + i];
-        if (tid == 0) { sm.nd = nd; sm.ns = ns; }
-    }
-    float r[R];
+    const int nd = a.discs ? min(a.ndisc[e], a.max_disc) : 0;
+    const int ns = a.segs ? min(a.nseg[e], a.max_seg) : 0;
     int pass = IS_RESET_KERNEL ? PASS_RESET : PASS_STEP;
+    float *orow = a.obs + (size_t)e * a.obs_stride;
 
     for (;;) {
-        // ---- per-pass setup by thread 0: float32 lidar pose, origin cell (env.py:386,419)
+        // ---- per-pass setup: float32 lidar pose, origin cell (env.py:386, 419)
+        if (WPE > 1) __syncthreads(); else __syncwarp();
+        PROF_MARK(0);
         if (tid == 0) {
             const navgym_map_t m = a.maps[sm.map];
             sm.lx = (float)sm.px; sm.ly = (float)sm.py; sm.lt = (float)sm.th;
@@ -313,211 +290,320 @@ step_kernel(const navgym_step_args_t a)
             sm.W = m.W; sm.H = m.H; sm.edt_off = m.edt_offset;
             sm.res32 = (float)m.res;
             sm.max_range = (float)((double)m.W * (double)m.H);
+            sm.t_stop = fminf(fminf(a.t_stop, sm.max_range), 8.0e6f);
+            sm.next_beam = TPB * MARCH_SLOTS;
         }
-        __syncthreads();
-        // ---- beam directions + occupancy-grid march (env.py:388-390, 420-426)
-        float dx[R], dy[R];
-#pragma unroll
-        for (int j = 0; j < R; j++) {
-            const float h = (float)__dadd_rn(a.lin[tid + j * TPB], (double)sm.lt);
+        if (WPE > 1) __syncthreads(); else __syncwarp();
+        const float lx = sm.lx, ly = sm.ly, lt = sm.lt;
+        PROF_MARK(1);
+        // ---- beam directions (env.py:388-390, 420-424)
+#pragma unroll 2
+        for (int i = 0; i < BPL; i++) {
+            const int k = BEAM(i);
+            const float h = (float)__dadd_rn(a.lin[k], (double)lt);
             double sd, cd;
             sincos((double)h, &sd, &cd);
-            dx[j] = (float)cd;
-            dy[j] = (float)sd;
+            sm.dir[k] = make_float2((float)cd, (float)sd);
         }
+        if (WPE > 1) __syncthreads(); else __syncwarp();  // any lane may be dealt any beam
+        PROF_MARK(2);
+        // ---- occupancy-grid march (env.py:425-426), MARCH_SLOTS beams in flight per lane.
+        // The loop only finds each beam's hit cell (packed into sm.scan); ranges are computed
+        // afterwards with all lanes active.  Every beam of a scan starts on the origin cell,
+        // so that first sample (t = 0) is taken once per environment: either the origin is
+        // occupied (all beams end there) or all beams advance by the same first step.
         {
-            float rc[R];
-            int hx[R], hy[R];
-            march_multi<R>(a.edt_pool + sm.edt_off, sm.W, sm.H, (float)sm.ci, (float)sm.cj, dx, dy,
-                           sm.max_range, fminf(a.t_stop, sm.max_range), rc, hx, hy);
-            const bool rec = pass == (IS_RESET_KERNEL ? PASS_RESET : PASS_STEP) && a.hits;
+            const int W = sm.W, H = sm.H, ci = sm.ci, cj = sm.cj;
+            const float x0 = (float)ci, y0 = (float)cj;
+            const float t_stop = sm.t_stop;
+            const float *dist = a.edt_pool + sm.edt_off;
+            asm volatile("" : "+l"(dist));  // keep base + offset folded into one register pair
+            const float d0 = __ldg(dist + cj * W + ci);   // origin cell is clipped into the map
+            const float t1 = fmaxf(__fmul_rn(d0, 0.999f), 1.0f);  // == 0.0f + first step
+            const bool origin_hit = d0 <= 0.0f, first_live = t1 < t_stop;
+            // Beams are dealt out dynamically: slot s of thread tid starts on beam s * TPB + tid
+            // and, whenever its beam ends, takes the next undealt beam of the environment from
+            // a shared counter.  Beams go out in increasing order, so at any moment the CTA
+            // works on a narrow window of neighbouring beams (shared sectors) while every lane
+            // stays busy until the scan runs out of beams.
+            int kb[MARCH_SLOTS];  // the slot's current beam, -1 = none left
+            float t[MARCH_SLOTS], dx[MARCH_SLOTS], dy[MARCH_SLOTS];
 #pragma unroll
-            for (int j = 0; j < R; j++) {
-                r[j] = __fmul_rn(rc[j], sm.res32);
-                if (rec)
-                    *reinterpret_cast<short2 *>(a.hits + ((size_t)e * NB + tid + j * TPB) * 2) =
-                        make_short2((short)hx[j], (short)hy[j]);
+            for (int s = 0; s < MARCH_SLOTS; s++) {
+                kb[s] = s * TPB + tid;
+                t[s] = t1;
+                const float2 dd = sm.dir[kb[s]];
+                dx[s] = dd.x;
+                dy[s] = dd.y;
+            }
+            if (origin_hit | !first_live) {
+#pragma unroll
+                for (int i = 0; i < BPL; i++)
+                    sm.scan[BEAM(i)] = origin_hit ? (cj << 16 | ci) : -1;
+            } else {
+                for (;;) {
+                    float d[MARCH_SLOTS];
+                    int cx[MARCH_SLOTS], cy[MARCH_SLOTS];
+                    bool inb[MARCH_SLOTS];
+#pragma unroll
+                    for (int s = 0; s < MARCH_SLOTS; s++) {
+                        cx[s] = __float2int_rz(__fmaf_rn(dx[s], t[s], x0));
+                        cy[s] = __float2int_rz(__fmaf_rn(dy[s], t[s], y0));
+                        inb[s] = ((unsigned)cx[s] < (unsigned)W) & ((unsigned)cy[s] < (unsigned)H);
+                        const unsigned idx = inb[s] ? (unsigned)(cy[s] * W + cx[s]) : 0u;
+                        d[s] = __ldg(dist + idx);
+                    }
+#pragma unroll
+                    for (int s = 0; s < MARCH_SLOTS; s++) {
+                        const bool hit = inb[s] & (d[s] <= 0.0f);
+                        float tn = __fadd_rn(t[s], fmaxf(__fmul_rn(d[s], 0.999f), 1.0f));
+                        const bool fin = !inb[s] | hit | !(tn < t_stop);
+                        if (fin & (kb[s] >= 0)) {
+                            // absolute hit cell, (y << 16 | x), or -1 for "no hit"
+                            sm.scan[kb[s]] = hit ? (cy[s] << 16 | cx[s]) : -1;
+                            const int k = atomicAdd(&sm.next_beam, 1);
+                            kb[s] = k < NB ? k : -1;
+                            tn = t1;
+                            if (k < NB) {
+                                const float2 dd = sm.dir[k];
+                                dx[s] = dd.x;
+                                dy[s] = dd.y;
+                            }
+                        }
+                        t[s] = tn;
+                    }
+                    bool live = false;
+#pragma unroll
+                    for (int s = 0; s < MARCH_SLOTS; s++) live |= kb[s] >= 0;
+                    if (!__any_sync(FULL, live)) break;
+                }
+            }
+            if (WPE > 1) __syncthreads(); else __syncwarp();
+            // ranges (env.py:426), all lanes active: sqrt(di^2 + dj^2) * resolution
+            const bool rec = pass == (IS_RESET_KERNEL ? PASS_RESET : PASS_STEP) && a.hits;
+            const float max_range = sm.max_range, res32 = sm.res32;
+#pragma unroll
+            for (int i = 0; i < BPL; i++) {
+                const int k = BEAM(i);
+                const int cell = sm.scan[k];
+                float rc = max_range;
+                int rel = (int)0x80008000;
+                if (cell != -1) {
+                    const int hx = (cell & 0xffff) - ci, hy = (cell >> 16) - cj;
+                    const float xd = (float)hx, yd = (float)hy;
+                    rc = __fsqrt_rn(__fadd_rn(__fmul_rn(xd, xd), __fmul_rn(yd, yd)));
+                    rel = (hx & 0xffff) | (hy << 16);
+                }
+                sm.scan[k] = __float_as_int(__fmul_rn(rc, res32));
+                if (rec) reinterpret_cast<int *>(a.hits)[(size_t)e * NB + k] = rel;
             }
         }
-        const int nobs = sm.nd + sm.ns;
-        if (nobs > 0) {
-            // ---- pedestrians: segments (env.py:430-431) and discs (env.py:432), min-merged.
-            // One warp per obstacle, lanes across the beams of its angular window.
-#pragma unroll
-            for (int j = 0; j < R; j++) {
-                sm.scan[tid + j * TPB] = __float_as_int(r[j]);
-                sm.dx[tid + j * TPB] = dx[j];
-                sm.dy[tid + j * TPB] = dy[j];
-            }
-            __syncthreads();
-            const float ox = sm.lx, oy = sm.ly, th = sm.lt;
-            for (int o = warp; o < nobs; o += NW) {
+        PROF_MARK(3);
+        // ---- pedestrians: segments (env.py:430-431) and discs (env.py:432), min-merged.
+        // One warp per obstacle, lanes across the beams of its angular window.
+        if (ns + nd > 0) {
+            if (WPE > 1) __syncthreads(); else __syncwarp();
+            const float *discs = a.discs + (size_t)e * a.max_disc * 3;
+            const float *segs = a.segs + (size_t)e * a.max_seg * 4;
+            for (int o = warp; o < ns + nd; o += WPE) {
                 int k0, cnt;
-                if (o < sm.ns) {
-                    const float ax = sm.segs[4 * o], ay = sm.segs[4 * o + 1];
-                    const float bx = sm.segs[4 * o + 2], by = sm.segs[4 * o + 3];
-                    float pa = atan2f(ay - oy, ax - ox), pb = atan2f(by - oy, bx - ox);
-                    float d = pb - pa;
-                    d -= 6.2831853f * rintf(d * 0.15915494f);
-                    float da2 = (ax - ox) * (ax - ox) + (ay - oy) * (ay - oy);
-                    float db2 = (bx - ox) * (bx - ox) + (by - oy) * (by - oy);
-                    if (fabsf(d) > 3.0f || da2 < 1e-6f || db2 < 1e-6f) { k0 = 0; cnt = NB; }
-                    else beam_window(d >= 0 ? pa : pb, fabsf(d), th, k0, cnt);
+                if (o < ns) {
+                    const float4 sg = *reinterpret_cast<const float4 *>(segs + 4 * o);
+                    const float ax = sg.x, ay = sg.y, bx = sg.z, by = sg.w;
+                    float pa = atan2f(ay - ly, ax - lx), pb = atan2f(by - ly, bx - lx);
+                    float dl = pb - pa;
+                    dl -= 6.2831853f * rintf(dl * 0.15915494f);
+                    float da2 = (ax - lx) * (ax - lx) + (ay - ly) * (ay - ly);
+                    float db2 = (bx - lx) * (bx - lx) + (by - ly) * (by - ly);
+                    if (fabsf(dl) > 3.0f || da2 < 1e-6f || db2 < 1e-6f) { k0 = 0; cnt = NB; }
+                    else beam_window(dl >= 0 ? pa : pb, fabsf(dl), lt, k0, cnt);
                     for (int i = lane; i < cnt; i += 32) {
-                        int k = (k0 + i) & (NB - 1);
-                        float t = seg_hit(ox, oy, sm.dx[k], sm.dy[k], ax, ay, bx, by);
-                        if (t < CUDART_INF_F) atomicMin(&sm.scan[k], __float_as_int(t));
+                        const int k = (k0 + i) & (NB - 1);
+                        const float tt = seg_hit(lx, ly, sm.dir[k].x, sm.dir[k].y, ax, ay, bx, by);
+                        if (tt < CUDART_INF_F) atomicMin(&sm.scan[k], __float_as_int(tt));
                     }
                 } else {
-                    const int q = o - sm.ns;
-                    const float X = sm.discs[3 * q], Y = sm.discs[3 * q + 1], Rd = sm.discs[3 * q + 2];
-                    float cx = X - ox, cy = Y - oy;
-                    float dc = sqrtf(cx * cx + cy * cy);
+                    const int q = o - ns;
+                    const float X = discs[3 * q], Y = discs[3 * q + 1], Rd = discs[3 * q + 2];
+                    const float cx = X - lx, cy = Y - ly;
+                    const float dc = sqrtf(cx * cx + cy * cy);
                     if (dc <= Rd * 1.05f + 1e-3f) { k0 = 0; cnt = NB; }
                     else {
-                        float half = asinf(fminf(Rd / dc, 1.0f)) * 1.01f + 1e-4f;
-                        beam_window(atan2f(cy, cx) - half, 2.0f * half, th, k0, cnt);
+                        const float half = asinf(fminf(Rd / dc, 1.0f)) * 1.01f + 1e-4f;
+                        beam_window(atan2f(cy, cx) - half, 2.0f * half, lt, k0, cnt);
                     }
                     for (int i = lane; i < cnt; i += 32) {
-                        int k = (k0 + i) & (NB - 1);
-                        float t = disc_hit(ox, oy, sm.dx[k], sm.dy[k], X, Y, Rd);
-                        if (t < CUDART_INF_F) atomicMin(&sm.scan[k], __float_as_int(t));
+                        const int k = (k0 + i) & (NB - 1);
+                        const float tt = disc_hit(lx, ly, sm.dir[k].x, sm.dir[k].y, X, Y, Rd);
+                        if (tt < CUDART_INF_F) atomicMin(&sm.scan[k], __float_as_int(tt));
                     }
                 }
             }
-            __syncthreads();
-#pragma unroll
-            for (int j = 0; j < R; j++) r[j] = __int_as_float(sm.scan[tid + j * TPB]);
+            if (WPE > 1) __syncthreads(); else __syncwarp();
         }
-        // ---- clip + noise (env.py:435-440)
+        PROF_MARK(4);
+        // ---- clip + noise (env.py:435-440), thresholds, observation row
         bool c_any = false, d_any = false;
+        {
+            const int nslot = pass == PASS_RESCAN ? 1 : 0;
+            const float noise_std = sm.noise_std;
+            const int steps = sm.steps, episode = sm.episode;
+            constexpr int G = BPL >= 4 ? 4 : BPL;
+#pragma unroll 1
+            for (int g = 0; g < BPL / G; g++) {
+                float z[4] = {0.f, 0.f, 0.f, 0.f};
+                if (!a.noise && noise_std > 0.0f)
+                    normal4(a.seed, (uint32_t)(a.env_offset + e), (uint32_t)episode, (uint32_t)steps,
+                            (uint32_t)pass, (uint32_t)(tid + TPB * g), z);
 #pragma unroll
-        for (int j = 0; j < R; j++) {
-            const int k = tid + j * TPB;
-            float v = fminf(fmaxf(r[j], 0.0f), a.range_max);
-            if (v != a.range_max) {
-                if (a.noise) {
-                    int slot = pass == PASS_RESCAN ? 1 : 0;
-                    v = __fadd_rn(v, a.noise[((size_t)e * 2 + slot) * NB + k]);
-                } else if (sm.noise_std > 0.0f) {
-                    v = __fadd_rn(v, sm.noise_std * beam_normal(a.seed, (uint32_t)(a.env_offset + e),
-                                                               (uint32_t)sm.episode, (uint32_t)sm.steps,
-                                                               (uint32_t)pass, (uint32_t)k));
+                for (int j = 0; j < G; j++) {
+                    const int k = BEAM(G * g + j);
+                    float v = fminf(fmaxf(__int_as_float(sm.scan[k]), 0.0f), a.range_max);
+                    if (v != a.range_max) {
+                        if (a.noise) v = __fadd_rn(v, a.noise[((size_t)e * 2 + nslot) * NB + k]);
+                        else if (noise_std > 0.0f) v = __fadd_rn(v, noise_std * z[j]);
+                    }
+                    sm.scan[k] = __float_as_int(v);
+                    orow[k] = v;
+                    c_any |= v < a.thr[k];
+                    d_any |= v < a.dthr[k];
                 }
             }
-            r[j] = v;
-            c_any |= v < a.thr[k];
-            d_any |= v < a.dthr[k];
         }
 
+        PROF_MARK(5);
         if (pass == PASS_STEP) {
             // ---- reward / done / info on this observation (env.py:464-589)
-            const int crash = __syncthreads_or(c_any);
-            const int discomf = __syncthreads_or(d_any) && !crash;
+            int crash, discomf;
+            if (WPE > 1) {
+                crash = __syncthreads_or(c_any);
+                discomf = __syncthreads_or(d_any) && !crash;
+            } else {
+                crash = __any_sync(FULL, c_any);
+                discomf = __any_sync(FULL, d_any) && !crash;
+            }
+            double mn = CUDART_INF;
             if (discomf) {
-                double q = CUDART_INF;
-#pragma unroll
-                for (int j = 0; j < R; j++) {
-                    const int k = tid + j * TPB;
+                for (int i = 0; i < BPL; i++) {
+                    const int k = BEAM(i);
                     const float thr_k = a.thr[k], dthr_k = a.dthr[k];
-                    float den = __fadd_rn(__fsub_rn(dthr_k, thr_k), 1e-6f);
-                    q = fmin(q, __ddiv_rn(__dsub_rn((double)r[j], (double)thr_k), (double)den));
+                    const float den = __fadd_rn(__fsub_rn(dthr_k, thr_k), 1e-6f);
+                    mn = fmin(mn, __ddiv_rn(__dsub_rn((double)__int_as_float(sm.scan[k]), (double)thr_k), (double)den));
                 }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) q = fmin(q, __shfl_xor_sync(0xffffffffu, q, o));
-                if (lane == 0) sm.red[warp] = q;
-                __syncthreads();
-            }
-            if (tid == 0) {
-                double mn = CUDART_INF;
-                if (discomf)
-                    for (int i = 0; i < NW; i++) mn = fmin(mn, sm.red[i]);
-                const double px = sm.px, py = sm.py;
-                double dxg = __dsub_rn(sm.gx, px), dyg = __dsub_rn(sm.gy, py);
-                double dist = sqrt(__dadd_rn(__dmul_rn(dxg, dxg), __dmul_rn(dyg, dyg)));
-                double dxp = __dsub_rn(sm.gx, sm.ppx), dyp = __dsub_rn(sm.gy, sm.ppy);
-                double pdist = sqrt(__dadd_rn(__dmul_rn(dxp, dxp), __dmul_rn(dyp, dyp)));
-                int success = dist < a.dist_thresh;
-                double r_s = success ? __dmul_rn(__dmul_rn(1.0, a.r_success), a.r_scale) : 0.0;
-                double r_c = crash ? __dmul_rn(__dmul_rn(-1.0, a.r_crash), a.r_scale) : 0.0;
-                double r_p = __dmul_rn(__dmul_rn(__dsub_rn(pdist, dist), a.r_progress), a.r_scale);
-                double r_f = __dmul_rn(__dmul_rn(sm.pv, a.r_forward), a.r_scale);
-                double r_r = __dmul_rn(__dmul_rn(__dmul_rn(-1.0, __dmul_rn(sm.pw, sm.pw)), a.r_rotation), a.r_scale);
-                double r_d = 0.0;
-                if (discomf)
-                    r_d = __dmul_rn(__dmul_rn(-__dsub_rn(1.0, mn), a.r_discomfort), a.r_scale);
-                double rew = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(r_s, r_c), r_p), r_f), r_r), r_d);
-                int trunc = a.max_episode_steps > 0 && sm.steps >= a.max_episode_steps && !(success || crash);
-                int done = success || crash || trunc;
-                sm.crash = crash; sm.success = success; sm.done = done; sm.trunc = trunc;
-                a.reward[e] = (float)rew;
-                a.done[e] = (uint8_t)done;
-                a.is_success[e] = (uint8_t)success;
-                a.is_crash[e] = (uint8_t)crash;
-                if (a.truncated) a.truncated[e] = (uint8_t)trunc;
-                a.distance[e] = (float)dist;
-                if (done && a.auto_reset) {
-                    sm.next_pass = PASS_RESET;
-                } else if (crash) {  // env.py:707-717: back to the pose / yaw of prev_obs
-                    sm.px = sm.ppx; sm.py = sm.ppy; sm.th = sm.pyaw;
-                    sm.next_pass = PASS_RESCAN;
-                } else {
-                    sm.next_pass = PASS_END;
+                for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(FULL, mn, o));
+                if (WPE > 1) {
+                    if (lane == 0) sm.red[warp] = mn;
+                    __syncthreads();
                 }
-                if (sm.next_pass == PASS_RESET) {
-                    // auto-reset: draw a spawn tuple (and a map) for the next episode
-                    uint4 rnd = philox4x32_10(make_uint4((uint32_t)(a.env_offset + e), (uint32_t)sm.episode,
-                                                         0x5eedu, 0xfffffff0u),
-                                              make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
-                    int map = sm.map;
-                    if (a.resample_map && a.num_maps > 1)
-                        map = (int)(((uint64_t)rnd.y * (uint64_t)a.num_maps) >> 32);
-                    const navgym_map_t m = a.maps[map];
-                    if (m.spawn_count > 0) {
-                        long long row = m.spawn_offset + (long long)(((uint64_t)rnd.x * (uint64_t)m.spawn_count) >> 32);
-                        const double *sp = a.spawn_pool + row * 5;
-                        sm.px = sp[0]; sm.py = sp[1]; sm.gx = sp[2]; sm.gy = sp[3]; sm.th = sp[4];
-                        sm.map = map;
-                    } else {  // no pool: restart from the rolled-back pose
+            }
+            if (warp == 0) {
+                if (WPE > 1 && discomf)
+                    for (int i = 0; i < WPE; i++) mn = fmin(mn, sm.red[i]);
+                // lanes 0 / 1: distance to goal from pose / prev_pose
+                const double gx = sm.gx, gy = sm.gy;
+                const double qx = lane == 0 ? sm.px : sm.ppx, qy = lane == 0 ? sm.py : sm.ppy;
+                const double ddx = __dsub_rn(gx, qx), ddy = __dsub_rn(gy, qy);
+                const double dq = sqrt(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)));
+                const double dist_g = __shfl_sync(FULL, dq, 0), pdist = __shfl_sync(FULL, dq, 1);
+                const int success = dist_g < a.dist_thresh;
+                const int trunc = a.max_episode_steps > 0 && sm.steps >= a.max_episode_steps && !(success || crash);
+                const int done = success || crash || trunc;
+                if (lane == 0) {
+                    const double pv = sm.pv, pw = sm.pw;
+                    double r_s = success ? __dmul_rn(__dmul_rn(1.0, a.r_success), a.r_scale) : 0.0;
+                    double r_c = crash ? __dmul_rn(__dmul_rn(-1.0, a.r_crash), a.r_scale) : 0.0;
+                    double r_p = __dmul_rn(__dmul_rn(__dsub_rn(pdist, dist_g), a.r_progress), a.r_scale);
+                    double r_f = __dmul_rn(__dmul_rn(pv, a.r_forward), a.r_scale);
+                    double r_r = __dmul_rn(__dmul_rn(__dmul_rn(-1.0, __dmul_rn(pw, pw)), a.r_rotation), a.r_scale);
+                    double r_d = 0.0;
+                    if (discomf) r_d = __dmul_rn(__dmul_rn(-__dsub_rn(1.0, mn), a.r_discomfort), a.r_scale);
+                    double rew = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(r_s, r_c), r_p), r_f), r_r), r_d);
+                    a.reward[e] = (float)rew;
+                    a.done[e] = (uint8_t)done;
+                    a.is_success[e] = (uint8_t)success;
+                    a.is_crash[e] = (uint8_t)crash;
+                    if (a.truncated) a.truncated[e] = (uint8_t)trunc;
+                    a.distance[e] = (float)dist_g;
+                    int next = PASS_END;
+                    if (done && a.auto_reset) {
+                        // auto-reset: draw a spawn tuple (and a map) for the next episode
+                        uint4 rnd = philox4x32_10(make_uint4((uint32_t)(a.env_offset + e), (uint32_t)sm.episode, 0x5eedu, 0xfffffff0u),
+                                                  make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+                        int nmap = sm.map;
+                        if (a.resample_map && a.num_maps > 1) nmap = (int)(((uint64_t)rnd.y * (uint64_t)a.num_maps) >> 32);
+                        const navgym_map_t m2 = a.maps[nmap];
+                        if (m2.spawn_count > 0) {
+                            const long long row = m2.spawn_offset + (long long)(((uint64_t)rnd.x * (uint64_t)m2.spawn_count) >> 32);
+                            const double *sp = a.spawn_pool + row * 5;
+                            sm.px = sp[0]; sm.py = sp[1]; sm.gx = sp[2]; sm.gy = sp[3]; sm.th = sp[4];
+                            sm.map = nmap;
+                        } else {  // no pool: restart from the rolled-back pose
+                            sm.px = sm.ppx; sm.py = sm.ppy; sm.th = sm.pyaw;
+                        }
+                        sm.noise_std = a.noise_lo + (a.noise_hi - a.noise_lo) * u01(rnd.z);
+                        sm.episode += 1;
+                        sm.steps = 0;
+                        sm.ppx = sm.px; sm.ppy = sm.py; sm.pv = 0; sm.pw = 0; sm.act_v = 0; sm.act_w = 0;
+                        next = PASS_RESET;
+                    } else if (crash) {  // env.py:707-717: back to the pose / yaw of prev_obs
                         sm.px = sm.ppx; sm.py = sm.ppy; sm.th = sm.pyaw;
+                        next = PASS_RESCAN;
                     }
-                    sm.noise_std = a.noise_lo + (a.noise_hi - a.noise_lo) * u01(rnd.z);
-                    sm.episode += 1;
-                    sm.steps = 0;
-                    sm.ppx = sm.px; sm.ppy = sm.py; sm.pv = 0; sm.pw = 0;
-                    ST(NAVGYM_S_PV) = 0; ST(NAVGYM_S_PW) = 0;
-                    ST(NAVGYM_S_GX) = sm.gx; ST(NAVGYM_S_GY) = sm.gy;
-                    a.map_id[e] = sm.map;
-                    if (a.noise_std) a.noise_std[e] = sm.noise_std;
+                    sm.next_pass = next;
                 }
             }
-            __syncthreads();
+            if (WPE > 1) __syncthreads(); else __syncwarp();
             pass = sm.next_pass;
             if (pass != PASS_END) continue;
         }
         break;
     }
 
-    // ---------------- epilogue: observation row + state (env.py:455, 725-727) -----------
-    float *o = a.obs + (size_t)e * a.obs_stride;
-#pragma unroll
-    for (int j = 0; j < R; j++) o[tid + j * TPB] = r[j];
-    if (tid == 0) {
+    PROF_MARK(6);
+    // ---------------- epilogue (warp 0): observation tail + state (env.py:455, 725-727) ---
+    if (warp == 0) {
         double sn, cn;
         sincos(sm.th, &sn, &cn);
-        double yaw = atan2(sn, cn);  // utils.py:5-9
-        double t7[7] = {sm.ppx, sm.ppy, sm.px, sm.py, sm.pv, sm.pw, yaw};
-#pragma unroll
-        for (int i = 0; i < 7; i++) {
-            o[NB + i] = (float)t7[i];
-            if (a.tail64) a.tail64[(size_t)e * 7 + i] = t7[i];
+        const double yaw = atan2(sn, cn);  // utils.py:5-9
+        double tv = 0.0;
+        switch (lane) {
+        case 0: tv = sm.ppx; break;
+        case 1: tv = sm.ppy; break;
+        case 2: tv = sm.px; break;
+        case 3: tv = sm.py; break;
+        case 4: tv = sm.pv; break;
+        case 5: tv = sm.pw; break;
+        case 6: tv = yaw; break;
         }
-        ST(NAVGYM_S_PX) = sm.px; ST(NAVGYM_S_PY) = sm.py; ST(NAVGYM_S_TH) = sm.th;
-        ST(NAVGYM_S_PPX) = sm.px; ST(NAVGYM_S_PPY) = sm.py; ST(NAVGYM_S_PYAW) = yaw;
-        a.steps[e] = sm.steps;
-        if (a.episodes) a.episodes[e] = sm.episode;
+        if (lane < 7) {
+            orow[NB + lane] = (float)tv;
+            if (a.tail64) a.tail64[(size_t)e * 7 + lane] = tv;
+        }
+        double nv = 0.0;
+        switch (lane) {
+        case NAVGYM_S_PX: nv = sm.px; break;
+        case NAVGYM_S_PY: nv = sm.py; break;
+        case NAVGYM_S_TH: nv = sm.th; break;
+        case NAVGYM_S_GX: nv = sm.gx; break;
+        case NAVGYM_S_GY: nv = sm.gy; break;
+        case NAVGYM_S_PPX: nv = sm.px; break;
+        case NAVGYM_S_PPY: nv = sm.py; break;
+        case NAVGYM_S_PYAW: nv = yaw; break;
+        case NAVGYM_S_PV: nv = sm.act_v; break;
+        case NAVGYM_S_PW: nv = sm.act_w; break;
+        }
+        if (lane < NAVGYM_NS) ST(lane) = nv;
+        if (lane == 0) {
+            a.steps[e] = sm.steps;
+            a.map_id[e] = sm.map;
+            if (a.episodes) a.episodes[e] = sm.episode;
+            if (a.noise_std) a.noise_std[e] = sm.noise_std;
+        }
     }
+    PROF_MARK(7);
 #undef ST
+#undef BEAM
 }
 
 // ------------------------------------------------------------------ EDT build kernels
@@ -593,26 +679,36 @@ __global__ void render_in_lidar_kernel(float *__restrict__ ranges, const float *
 }
 
 // ------------------------------------------------------------------ C ABI
-// threads per environment (rays per thread = 512 / TPB); NAVGYM_TPB overrides for tuning runs
-static int g_tpb = 0;
-static int step_tpb()
+// Launch shape of the fused kernel: warps per environment (WPE) and march slots per lane.
+// NAVGYM_WPE / NAVGYM_SLOTS override the defaults for tuning runs.
+static int env_int(const char *name, int dflt)
 {
-    if (g_tpb == 0) {
-        const char *s = getenv("NAVGYM_TPB");
-        int v = s ? atoi(s) : 128;
-        g_tpb = (v == 512 || v == 256 || v == 128 || v == 64) ? v : 128;
-    }
-    return g_tpb;
+    const char *s = getenv(name);
+    return s ? atoi(s) : dflt;
+}
+
+template <bool RESET, int WPE, int SLOTS>
+static void launch_one(const navgym_step_args_t &a, cudaStream_t st)
+{
+    step_kernel<RESET, WPE, SLOTS><<<a.num_envs, WPE * 32, 0, st>>>(a);
 }
 
 template <bool RESET>
 static void launch_step(const navgym_step_args_t &a, cudaStream_t st)
 {
-    switch (step_tpb()) {
-    case 512: step_kernel<RESET, 512><<<a.num_envs, 512, 0, st>>>(a); break;
-    case 256: step_kernel<RESET, 256><<<a.num_envs, 256, 0, st>>>(a); break;
-    case 64: step_kernel<RESET, 64><<<a.num_envs, 64, 0, st>>>(a); break;
-    default: step_kernel<RESET, 128><<<a.num_envs, 128, 0, st>>>(a); break;
+    static const int wpe = env_int("NAVGYM_WPE", 2), slots = env_int("NAVGYM_SLOTS", 1);
+    switch (wpe * 10 + slots) {
+    case 11: launch_one<RESET, 1, 1>(a, st); break;
+    case 12: launch_one<RESET, 1, 2>(a, st); break;
+    case 14: launch_one<RESET, 1, 4>(a, st); break;
+    case 22: launch_one<RESET, 2, 2>(a, st); break;
+    case 24: launch_one<RESET, 2, 4>(a, st); break;
+    case 41: launch_one<RESET, 4, 1>(a, st); break;
+    case 44: launch_one<RESET, 4, 4>(a, st); break;
+    case 81: launch_one<RESET, 8, 1>(a, st); break;
+    case 82: launch_one<RESET, 8, 2>(a, st); break;
+    case 42: launch_one<RESET, 4, 2>(a, st); break;
+    default: launch_one<RESET, 2, 1>(a, st); break;
     }
     g_launches++;
 }
@@ -620,6 +716,15 @@ static void launch_step(const navgym_step_args_t &a, cudaStream_t st)
 #define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return (int)_e; } while (0)
 
 extern "C" {
+
+#ifdef NAVGYM_PROFILE
+int navgym_debug_read_prof(unsigned long long *out, int reset)
+{
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_prof, sizeof(unsigned long long) * 16);
+    if (!e && reset) { unsigned long long z[16] = {0}; e = cudaMemcpyToSymbol(g_prof, z, sizeof(z)); }
+    return (int)e;
+}
+#endif
 
 int navgym_abi_version(void) { return 1; }
 int navgym_sizeof_step_args(void) { return (int)sizeof(navgym_step_args_t); }
@@ -780,6 +885,12 @@ void navgym_grid_bfs(const uint8_t *blocked, int H, int W, int sr, int sc, int32
 }
 
 const float *navgym_raymarching_edt_dev(const navgym_raymarching_t *rm) { return rm ? rm->dist : nullptr; }
+
+int navgym_raymarching_edt_host(const navgym_raymarching_t *rm, float *out_host)
+{
+    if (!rm) return (int)cudaErrorInvalidValue;
+    return (int)cudaMemcpy(out_host, rm->dist, (size_t)rm->H * rm->W * sizeof(float), cudaMemcpyDeviceToHost);
+}
 
 void navgym_raymarching_destroy(navgym_raymarching_t *rm)
 {

@@ -85,6 +85,12 @@ class PyRayMarching(object):
             C.c_void_p(torch.cuda.current_stream().cuda_stream)), 'calc_range_many')
         return d_out.cpu().numpy(), d_hit.cpu().numpy()
 
+    def edt_host(self):
+        """The distance image (float32 [H,W], cells) copied back to the host."""
+        out = np.empty((self.height, self.width), np.float32)
+        _lib.check(self._lib.navgym_raymarching_edt_host(C.c_void_p(self._h), _vp(out)), 'edt_host')
+        return out
+
     def __del__(self):
         h, self._h = getattr(self, '_h', None), None
         if h:

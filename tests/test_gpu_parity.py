@@ -28,7 +28,9 @@ def test_thresholds_match_oracle():
 
 @pytest.mark.parametrize('name', gu.trace_names()[:2] + ['synthetic'])
 def test_edt_exact(name):
+    """Device EDT (integer brute-force row pass) == oracle EDT (Felzenszwalb-Huttenlocher)."""
     from nav_gym_b200.batched_env import MapPool
+    from nav_gym_b200 import natives
     maps = _maps() if name == 'synthetic' else [gu.map_info(gu.load(name))]
     empty = dict(data=np.zeros((64, 96), np.int8), origin=(0, 0), resolution=0.05, width=96, height=64)
     one = dict(data=np.zeros((50, 40), np.int8), origin=(0, 0), resolution=0.05, width=40, height=50)
@@ -37,8 +39,10 @@ def test_edt_exact(name):
     pool = MapPool(maps, 'cuda:0')
     for i, m in enumerate(maps):
         want = orc.edt(np.asarray(m['data']) >= 0.1)
-        got = pool.edt(i).cpu().numpy()
-        assert np.array_equal(got, want), 'map %d' % i
+        assert np.array_equal(pool.edt(i).cpu().numpy(), want), 'map %d' % i
+    # the same transform behind the range_libc drop-in
+    rm = natives.PyRayMarching(natives.PyOMap(np.asarray(maps[0]['data']) >= 0.1), 1e6)
+    assert np.array_equal(rm.edt_host(), orc.edt(np.asarray(maps[0]['data']) >= 0.1))
 
 
 def test_calc_range_many_bit_exact():

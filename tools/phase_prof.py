@@ -1,0 +1,46 @@
+"""Per-phase cycle accounting of the fused step kernel (debug build with -DNAVGYM_PROFILE).
+Build here:   python tools/phase_prof.py build
+Run on GPU:   NAVGYM_LIB=tools/_prof/libnavgym_b200_prof.so python tools/phase_prof.py run"""
+import ctypes as C, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, 'tools', '_prof', 'libnavgym_b200_prof.so')
+if sys.argv[1] == 'build':
+    from nav_gym_b200 import _lib
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    for tag, extra in (('', []),):
+        out = OUT.replace('.so', tag + '.so')
+        subprocess.check_call(['nvcc'] + _lib.NVCC_FLAGS + ['-DNAVGYM_PROFILE'] + extra + ['-o', out, _lib.SRC])
+        print('built', out)
+else:
+    os.environ['NAVGYM_LIB'] = OUT.replace('.so', os.environ.get('NAVGYM_VARIANT', '') + '.so')
+    import numpy as np, torch
+    from nav_gym_b200 import _lib
+    from nav_gym_b200.batched_env import BatchedNavGym, MapPool, filter_spawn_pool
+    from bench import build_world
+    B = 4096
+    m, pool = build_world(0, 16384)
+    npool = int(os.environ.get('NAVGYM_POOL_N', '0'))
+    if npool: pool = pool[:npool]
+    mp = MapPool([m], 'cuda:0', spawn_pools=[pool])
+    env = BatchedNavGym(B, mp, seed=1, auto_reset=True)
+    env.reset_from_spawn_pool(np.random.RandomState(1))
+    act = torch.rand(B, 2, device='cuda') * torch.tensor([0.5, 1.28], device='cuda') + torch.tensor([0, -0.64], device='cuda')
+    if npool: act = act[:1].expand(B, 2).contiguous() * 0
+    for _ in range(10): env.step(act)
+    torch.cuda.synchronize()
+    lib = _lib.load()
+    buf = (C.c_ulonglong * 16)()
+    lib.navgym_debug_read_prof(buf, 1)
+    n = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): env.step(act)
+    e1.record(); torch.cuda.synchronize()
+    lib.navgym_debug_read_prof(buf, 1)
+    names = ['prologue(kinematics)', 'pass setup', 'beam dirs(sincos)', 'march', 'obstacles', 'clip+noise+obs', 'reward/branch', 'epilogue']
+    tot = sum(buf[:8])
+    print('ms/step %.3f' % (e0.elapsed_time(e1) / n))
+    for i, nm in enumerate(names):
+        print('%-22s %8.0f cycles/CTA  %5.1f%%' % (nm, buf[i] / (n * B), 100.0 * buf[i] / tot))
+    print('total %.0f cycles/CTA' % (tot / (n * B)))
