@@ -132,16 +132,52 @@ void nvo_edt(const uint8_t *occ, int H, int W, float *dist)
     free(d2);
 }
 
+/* ------------------------------------------------------- beam direction ----------- */
+/* cos / sin of a beam heading.  range_libc calls cosf/sinf; to make the
+ * direction a function of the heading bits alone — independent of which libm or GPU math
+ * library evaluates it — the canonical contract spells it out: Cody-Waite
+ * reduction by pi/2 in two fma steps, the fdlibm kernel polynomials in Horner/fma form,
+ * quadrant fix-up, result rounded to float.  Max error 1.8e-16 before that rounding; on 2e7
+ * random float headings in [-12, 18] the float result equalled correctly rounded cosf/sinf
+ * every time (oracle/README: sincos check). */
+static const double NV_TWO_OVER_PI = 6.36619772367581382433e-01;
+static const double NV_PIO2_HI = 1.57079632679489655800e+00, NV_PIO2_LO = 6.12323399573676603587e-17;
+static const double NV_S1 = -1.66666666666666324348e-01, NV_S2 = 8.33333333332248946124e-03,
+                    NV_S3 = -1.98412698298579493134e-04, NV_S4 = 2.75573137070700676789e-06,
+                    NV_S5 = -2.50507602534068634195e-08, NV_S6 = 1.58969099521155010221e-10;
+static const double NV_C1 = 4.16666666666666019037e-02, NV_C2 = -1.38888888888741095749e-03,
+                    NV_C3 = 2.48015872894767294178e-05, NV_C4 = -2.75573143513906633035e-07,
+                    NV_C5 = 2.08757232129817482790e-09, NV_C6 = -1.13596475577881948265e-11;
+
+void nvo_sincos(double x, double *sn, double *cs)
+{
+    double k = rint(x * NV_TWO_OVER_PI);
+    double r = fma(-k, NV_PIO2_HI, x);
+    r = fma(-k, NV_PIO2_LO, r);
+    double z = r * r;
+    double ps = fma(z, NV_S6, NV_S5);
+    ps = fma(z, ps, NV_S4); ps = fma(z, ps, NV_S3); ps = fma(z, ps, NV_S2); ps = fma(z, ps, NV_S1);
+    double s = fma(r * z, ps, r);
+    double pc = fma(z, NV_C6, NV_C5);
+    pc = fma(z, pc, NV_C4); pc = fma(z, pc, NV_C3); pc = fma(z, pc, NV_C2); pc = fma(z, pc, NV_C1);
+    double c = fma(z * z, pc, fma(z, -0.5, 1.0));
+    int n = (int)k & 3;
+    double a = (n & 1) ? c : s, b = (n & 1) ? s : c;
+    *sn = (n & 2) ? -a : a;
+    *cs = ((n + 1) & 2) ? -b : b;
+}
+
 /* ------------------------------------------------------------ ray marching -------- */
 /* range_libc RayMarching::calc_range restated, canonical form:
- * dx = (float)cos((double)h); sample cell = trunc(fmaf(dx, t, x0)); occupied <=> d <= 0;
+ * (dx, dy) = float(nvo_sincos(h)); sample cell = trunc(fmaf(dx, t, x0)); occupied <=> d <= 0;
  * t += max(d * 0.999f, 1.0f); out of map or t >= t_stop -> max_range.
  * hit[0..1] receives (px - x0, py - y0) as integers, or (INT16_MIN, INT16_MIN). */
 float nvo_calc_range(const float *dist, int W, int H, float x0, float y0, float heading,
                      float max_range, float t_stop, int32_t *hit, int32_t *nsteps)
 {
-    float dx = (float)cos((double)heading);
-    float dy = (float)sin((double)heading);
+    double sn, cs;
+    nvo_sincos((double)heading, &sn, &cs);
+    float dx = (float)cs, dy = (float)sn;
     float t = 0.0f;
     int32_t n = 0;
     if (hit) { hit[0] = INT16_MIN; hit[1] = INT16_MIN; }
@@ -272,14 +308,16 @@ void nvo_render_discs(float *ranges, const float *dirs, int K, const float *disc
 }
 
 /* beam directions: heading_k = (float)(lin[k] + (double)theta32) (env.py:388-390,
- * 420-424); dirs = ((float)cos, (float)sin) of that float heading. */
+ * 420-424); dirs = nvo_sincos of that float heading, rounded to float. */
 void nvo_beam_dirs(const double *lin, int K, float theta32, float *headings, float *dirs)
 {
     for (int k = 0; k < K; k++) {
         float h = (float)(lin[k] + (double)theta32);
         if (headings) headings[k] = h;
-        dirs[2 * k] = (float)cos((double)h);
-        dirs[2 * k + 1] = (float)sin((double)h);
+        double sn, cs;
+        nvo_sincos((double)h, &sn, &cs);
+        dirs[2 * k] = (float)cs;
+        dirs[2 * k + 1] = (float)sn;
     }
 }
 
