@@ -108,6 +108,44 @@ int navgym_step_batch(const navgym_step_args_t *args, void *stream);
 /* first observation of an episode, NavGymEnv.reset's tail (env.py:822-831) */
 int navgym_reset_obs_batch(const navgym_step_args_t *args, void *stream);
 
+/* ---- HER batch API: compute_rewards / compute_terminals / compute_info (env.py:464-589) on
+ * `count` stored observation rows obs[count][obs_stride] (float32, the layout of env.py:455)
+ * with goals[count][2]; any output pointer may be NULL. */
+typedef struct {
+    double dist_thresh;
+    double r_scale, r_success, r_crash, r_progress, r_forward, r_rotation, r_discomfort;
+    int32_t count, obs_stride;
+    const float *obs, *goals;
+    const float *thr, *dthr;   /* [512] */
+    float *reward;
+    uint8_t *done, *is_success, *is_crash;
+    float *distance;
+} navgym_her_args_t;
+int navgym_compute_rewards(const navgym_her_args_t *args, void *stream);
+
+/* ---- scripted pedestrians (stand-in for the reference's CNN-driven humans, env.py:617-662,
+ * whose weights are not distributed): advance every pedestrian one time step and emit the
+ * geometry the robot's lidar sees into the discs / segs buffers of navgym_step_args_t.
+ *   peds f32 [num_envs][max_ped][NAVGYM_PED_F]:
+ *     0 x, 1 y, 2 theta, 3 speed | 4 ax, 5 ay, 6 bx, 7 by (the two waypoints) | 8 target (0/1),
+ *     9..11 distance travelled in the base frame (x, y, theta; leg gait, env.py:237-255) |
+ *     12 has_legs (0/1), 13 trunk radius, 14..15 unused */
+#define NAVGYM_PED_F 16
+typedef struct {
+    int32_t num_envs, max_ped, max_disc, max_seg;
+    int32_t advance;      /* 0: only emit geometry for the current poses */
+    int32_t trunk_mode;   /* 1: one disc of radius peds[..][13] per pedestrian */
+    float dt;
+    int32_t _pad;
+    float *peds;
+    const int32_t *nped;  /* [num_envs] or NULL = max_ped everywhere */
+    float *discs;
+    int32_t *ndisc;
+    float *segs;
+    int32_t *nseg;
+} navgym_peds_args_t;
+int navgym_peds_advance(const navgym_peds_args_t *args, void *stream);
+
 /* ---- inner native boundary: range_libc --------------------------------------------- */
 /* PyOMap(bool[H,W]) + PyRayMarching(omap, max_range) (env.py:337-340): exact Euclidean
  * distance transform of occ_dev (u8, non-zero = occupied, [H][W], row = y) into dist_dev. */
@@ -154,6 +192,8 @@ int navgym_device_count(void);
 int navgym_abi_version(void);
 int navgym_sizeof_step_args(void);   /* layout check for FFI bindings */
 int navgym_sizeof_map(void);
+int navgym_sizeof_her_args(void);
+int navgym_sizeof_peds_args(void);
 /* kernels launched by this library since load (for bench.py's gpu_launches) */
 uint64_t navgym_launch_count(void);
 

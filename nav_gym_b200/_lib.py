@@ -82,6 +82,25 @@ class StepArgs(C.Structure):
     ]
 
 
+class HerArgs(C.Structure):
+    _fields_ = [('dist_thresh', C.c_double), ('r_scale', C.c_double), ('r_success', C.c_double),
+                ('r_crash', C.c_double), ('r_progress', C.c_double), ('r_forward', C.c_double),
+                ('r_rotation', C.c_double), ('r_discomfort', C.c_double),
+                ('count', C.c_int32), ('obs_stride', C.c_int32),
+                ('obs', _P), ('goals', _P), ('thr', _P), ('dthr', _P), ('reward', _P),
+                ('done', _P), ('is_success', _P), ('is_crash', _P), ('distance', _P)]
+
+
+PED_F = 16
+
+
+class PedsArgs(C.Structure):
+    _fields_ = [('num_envs', C.c_int32), ('max_ped', C.c_int32), ('max_disc', C.c_int32),
+                ('max_seg', C.c_int32), ('advance', C.c_int32), ('trunk_mode', C.c_int32),
+                ('dt', C.c_float), ('_pad', C.c_int32),
+                ('peds', _P), ('nped', _P), ('discs', _P), ('ndisc', _P), ('segs', _P), ('nseg', _P)]
+
+
 EXPORTS = [
     'navgym_step_batch', 'navgym_reset_obs_batch', 'navgym_edt_build', 'navgym_calc_range_many',
     'navgym_raymarching_create_host', 'navgym_raymarching_calc_range_many_host',
@@ -89,6 +108,7 @@ EXPORTS = [
     'navgym_render_segments_in_lidar', 'navgym_render_discs_in_lidar', 'navgym_render_in_lidar_host',
     'navgym_error_string', 'navgym_device_count', 'navgym_abi_version', 'navgym_launch_count',
     'navgym_sizeof_step_args', 'navgym_sizeof_map', 'navgym_grid_bfs',
+    'navgym_sizeof_her_args', 'navgym_sizeof_peds_args', 'navgym_compute_rewards', 'navgym_peds_advance',
 ]
 
 _lib = None
@@ -128,7 +148,11 @@ def load():
     lib.navgym_error_string.restype = C.c_char_p
     lib.navgym_error_string.argtypes = [C.c_int]
     lib.navgym_launch_count.restype = C.c_uint64
-    if lib.navgym_sizeof_step_args() != C.sizeof(StepArgs) or lib.navgym_sizeof_map() != C.sizeof(MapT):
+    lib.navgym_compute_rewards.argtypes = [C.POINTER(HerArgs), _P]
+    lib.navgym_peds_advance.argtypes = [C.POINTER(PedsArgs), _P]
+    if (lib.navgym_sizeof_step_args() != C.sizeof(StepArgs) or lib.navgym_sizeof_map() != C.sizeof(MapT)
+            or lib.navgym_sizeof_her_args() != C.sizeof(HerArgs)
+            or lib.navgym_sizeof_peds_args() != C.sizeof(PedsArgs)):
         raise RuntimeError('libnavgym_b200.so ABI mismatch with nav_gym_b200/_lib.py (rebuild)')
     _lib = lib
     return lib

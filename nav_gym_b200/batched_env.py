@@ -177,6 +177,7 @@ class BatchedNavGym(object):
         self.args = a
         self._keep = None
         self._act_dev = None
+        self.peds = None
 
     # -------------------------------------------------------------------------------------
     def set_state(self, start, goal, theta, noise_std=None):
@@ -250,11 +251,79 @@ class BatchedNavGym(object):
         torch.cuda.current_stream(self.device).synchronize()
         return obs_host, reward_host, done_host
 
+    # ---- HER batch API (env.py:491-589) on device tensors ---------------------------------
+    def compute_rewards(self, obs, goals, **reward):
+        """compute_rewards / compute_terminals / compute_info for stored observations:
+        obs float32 [N, >=519] (row layout of env.py:455), goals float32 [N, 2], both on the
+        device.  Returns dict(reward, done, is_success, is_crash, distance) of device tensors."""
+        obs = obs.to(device=self.device, dtype=torch.float32)
+        if obs.stride(-1) != 1:
+            obs = obs.contiguous()
+        goals = goals.to(device=self.device, dtype=torch.float32).contiguous()
+        n = obs.shape[0]
+        out = dict(reward=torch.empty(n, dtype=torch.float32, device=self.device),
+                   done=torch.empty(n, dtype=torch.uint8, device=self.device),
+                   is_success=torch.empty(n, dtype=torch.uint8, device=self.device),
+                   is_crash=torch.empty(n, dtype=torch.uint8, device=self.device),
+                   distance=torch.empty(n, dtype=torch.float32, device=self.device))
+        a, h = self.args, _lib.HerArgs()
+        h.dist_thresh = a.dist_thresh
+        h.r_scale, h.r_success, h.r_crash = a.r_scale, a.r_success, a.r_crash
+        h.r_progress, h.r_forward, h.r_rotation, h.r_discomfort = a.r_progress, a.r_forward, a.r_rotation, a.r_discomfort
+        for k, v in reward.items():
+            setattr(h, {'reward_scale': 'r_scale', 'reward_success_factor': 'r_success',
+                        'reward_crash_factor': 'r_crash', 'reward_progress_factor': 'r_progress',
+                        'reward_forward_factor': 'r_forward', 'reward_rotation_factor': 'r_rotation',
+                        'reward_discomfort_factor': 'r_discomfort'}[k], v)
+        h.count, h.obs_stride = n, obs.stride(0)
+        h.obs, h.goals, h.thr, h.dthr = _ptr(obs), _ptr(goals), _ptr(self.thr), _ptr(self.dthr)
+        h.reward, h.done, h.is_success = _ptr(out['reward']), _ptr(out['done']), _ptr(out['is_success'])
+        h.is_crash, h.distance = _ptr(out['is_crash']), _ptr(out['distance'])
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.navgym_compute_rewards(C.byref(h), self._stream()), 'compute_rewards')
+        return out
+
+    # ---- scripted pedestrians on the device ------------------------------------------------
+    def attach_pedestrians(self, peds, nped=None, trunk_mode=False):
+        """peds float32 [B, P, 16] (layout in include/navgym_b200.h), nped int32 [B] or None.
+        From now on step() first advances the pedestrians (reference order: humans move
+        env.py:659-662, then the robot :664) and scans against their geometry."""
+        peds = torch.as_tensor(peds, dtype=torch.float32).to(self.device).contiguous()
+        assert peds.shape[0] == self.B and peds.shape[2] == _lib.PED_F
+        P = peds.shape[1]
+        self.peds = peds
+        self.nped = None if nped is None else torch.as_tensor(nped, dtype=torch.int32).to(self.device)
+        need_disc, need_seg = (P, 0) if trunk_mode else (2 * P, 4 * P)
+        if need_disc > _lib.MAX_DISC or need_seg > _lib.MAX_SEG:
+            raise ValueError('too many pedestrians per environment')
+        self.max_disc, self.max_seg = max(need_disc, 1), max(need_seg, 1)
+        self.args.max_disc, self.args.max_seg = self.max_disc, self.max_seg
+        f32, i32 = torch.float32, torch.int32
+        self._pdiscs = torch.zeros(self.B, self.max_disc, 3, dtype=f32, device=self.device)
+        self._psegs = torch.zeros(self.B, self.max_seg, 4, dtype=f32, device=self.device)
+        self._pnd = torch.zeros(self.B, dtype=i32, device=self.device)
+        self._pns = torch.zeros(self.B, dtype=i32, device=self.device)
+        p = _lib.PedsArgs()
+        p.num_envs, p.max_ped, p.max_disc, p.max_seg = self.B, P, self.max_disc, self.max_seg
+        p.trunk_mode, p.dt = int(trunk_mode), self.args.dt
+        p.peds, p.nped = _ptr(self.peds), _ptr(self.nped)
+        p.discs, p.ndisc, p.segs, p.nseg = _ptr(self._pdiscs), _ptr(self._pnd), _ptr(self._psegs), _ptr(self._pns)
+        self._pargs = p
+        self._peds_emit(advance=False)
+
+    def _peds_emit(self, advance):
+        self._pargs.advance = int(advance)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.navgym_peds_advance(C.byref(self._pargs), self._stream()), 'peds_advance')
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def reset(self, discs=None, ndisc=None, segs=None, nseg=None, noise=None):
         """First observation of an episode from the state set by set_state (env.py:822-831)."""
+        if self.peds is not None and discs is None and segs is None:
+            self._peds_emit(advance=False)
+            discs, ndisc, segs, nseg = self._pdiscs, self._pnd, self._psegs, self._pns
         self._geom(discs, ndisc, segs, nseg, noise)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.navgym_reset_obs_batch(C.byref(self.args), self._stream()), 'reset')
@@ -263,6 +332,9 @@ class BatchedNavGym(object):
     def step(self, actions, discs=None, ndisc=None, segs=None, nseg=None, noise=None):
         """One lockstep NavGymEnv.step.  Returned tensors are owned by the env and overwritten
         by the next call (clone to keep)."""
+        if self.peds is not None and discs is None and segs is None:
+            self._peds_emit(advance=True)
+            discs, ndisc, segs, nseg = self._pdiscs, self._pnd, self._psegs, self._pns
         self._geom(discs, ndisc, segs, nseg, noise, actions)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.navgym_step_batch(C.byref(self.args), self._stream()), 'step')

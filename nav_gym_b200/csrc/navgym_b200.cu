@@ -635,6 +635,130 @@ __global__ void __launch_bounds__(WPE * 32, 1024 / (WPE * 32)) step_kernel(const
 #undef BEAM
 }
 
+// ------------------------------------------------------------------ HER batch API
+// compute_rewards / compute_terminals / compute_info on a batch of stored observations
+// (env.py:464-589: the reference's hindsight-relabelling entry points).  One warp per
+// observation row [scan(512) | prev_pose(2) pose(2) vel(2) yaw(1)], goals given separately.
+__global__ void __launch_bounds__(256) her_kernel(const navgym_her_args_t a)
+{
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (n >= a.count) return;
+    const unsigned FULL = 0xffffffffu;
+    const float *o = a.obs + (size_t)n * a.obs_stride;
+    bool c_any = false, d_any = false;
+    double mn = CUDART_INF;
+#pragma unroll 4
+    for (int i = 0; i < NB / 32; i++) {
+        const int k = lane + 32 * i;
+        const float v = o[k], thr = a.thr[k], dthr = a.dthr[k];
+        c_any |= v < thr;
+        d_any |= v < dthr;
+        const float den = __fadd_rn(__fsub_rn(dthr, thr), 1e-6f);
+        mn = fmin(mn, __ddiv_rn(__dsub_rn((double)v, (double)thr), (double)den));
+    }
+    const int crash = __any_sync(FULL, c_any);
+    const int discomf = __any_sync(FULL, d_any) && !crash;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mn = fmin(mn, __shfl_xor_sync(FULL, mn, off));
+    if (lane == 0) {
+        const double gx = (double)a.goals[2 * n], gy = (double)a.goals[2 * n + 1];
+        const double ppx = (double)o[NB], ppy = (double)o[NB + 1], px = (double)o[NB + 2], py = (double)o[NB + 3];
+        const double pv = (double)o[NB + 4], pw = (double)o[NB + 5];
+        double dxg = __dsub_rn(gx, px), dyg = __dsub_rn(gy, py);
+        double dist = sqrt(__dadd_rn(__dmul_rn(dxg, dxg), __dmul_rn(dyg, dyg)));
+        double dxp = __dsub_rn(gx, ppx), dyp = __dsub_rn(gy, ppy);
+        double pdist = sqrt(__dadd_rn(__dmul_rn(dxp, dxp), __dmul_rn(dyp, dyp)));
+        const int success = dist < a.dist_thresh;
+        double r_s = success ? __dmul_rn(__dmul_rn(1.0, a.r_success), a.r_scale) : 0.0;
+        double r_c = crash ? __dmul_rn(__dmul_rn(-1.0, a.r_crash), a.r_scale) : 0.0;
+        double r_p = __dmul_rn(__dmul_rn(__dsub_rn(pdist, dist), a.r_progress), a.r_scale);
+        double r_f = __dmul_rn(__dmul_rn(pv, a.r_forward), a.r_scale);
+        double r_r = __dmul_rn(__dmul_rn(__dmul_rn(-1.0, __dmul_rn(pw, pw)), a.r_rotation), a.r_scale);
+        double r_d = discomf ? __dmul_rn(__dmul_rn(-__dsub_rn(1.0, mn), a.r_discomfort), a.r_scale) : 0.0;
+        if (a.reward)
+            a.reward[n] = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(r_s, r_c), r_p), r_f), r_r), r_d);
+        if (a.done) a.done[n] = (uint8_t)(success || crash);
+        if (a.is_success) a.is_success[n] = (uint8_t)success;
+        if (a.is_crash) a.is_crash[n] = (uint8_t)crash;
+        if (a.distance) a.distance[n] = (float)dist;
+    }
+}
+
+// ------------------------------------------------------------------ scripted pedestrians
+// Pedestrian motion + geometry for the batched simulator (scripted stand-in
+// for the reference's CNN-driven humans whose weights are absent): each pedestrian walks
+// between two waypoints at its preferred speed with Human.set_vel's unicycle update
+// (human.py:32-41), turning at <= 1 rad/s toward the current target, and its leg-gait odometry
+// advances as in _update_dist_travelled (env.py:237-255).  Emits what the robot's lidar sees:
+// two leg discs (pymap2d CSimAgent "legs") for legged pedestrians, the 0.44 x 0.38 m box
+// footprint (human.py:5-10) as four segments otherwise (env.py:398-414), or one trunk disc
+// per pedestrian in trunk mode.  One thread per environment.
+__global__ void peds_advance_kernel(const navgym_peds_args_t a)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.num_envs) return;
+    const int P = a.nped ? min(a.nped[e], a.max_ped) : a.max_ped;
+    float *pp = a.peds + (size_t)e * a.max_ped * NAVGYM_PED_F;
+    float *discs = a.discs + (size_t)e * a.max_disc * 3;
+    float *segs = a.segs ? a.segs + (size_t)e * a.max_seg * 4 : nullptr;
+    int nd = 0, ns = 0;
+    for (int p = 0; p < P; p++) {
+        float *q = pp + p * NAVGYM_PED_F;
+        float x = q[0], y = q[1], th = q[2];
+        const float v = q[3];
+        float tgt = q[8];
+        if (a.advance) {
+            float gx = tgt > 0.5f ? q[6] : q[4], gy = tgt > 0.5f ? q[7] : q[5];
+            if ((gx - x) * (gx - x) + (gy - y) * (gy - y) < 0.25f) {  // reached: turn back
+                tgt = 1.0f - tgt;
+                gx = tgt > 0.5f ? q[6] : q[4];
+                gy = tgt > 0.5f ? q[7] : q[5];
+            }
+            float err = atan2f(gy - y, gx - x) - th;
+            err -= 6.2831853f * rintf(err * 0.15915494f);
+            const float w = fminf(fmaxf(err / a.dt, -1.0f), 1.0f);
+            const float vx = v * cosf(th), vy = v * sinf(th);  // human.py:35-36 (old heading)
+            const float thn = th + w * a.dt;
+            x += cosf(thn) * v * a.dt;
+            y += sinf(thn) * v * a.dt;
+            // leg gait odometry in the base frame (env.py:251-255)
+            const float c = cosf(thn), s_ = sinf(thn);
+            q[9] += (c * vx + s_ * vy) * a.dt;
+            q[10] += (-s_ * vx + c * vy) * a.dt;
+            q[11] += w * a.dt;
+            th = thn - 6.2831853f * floorf(thn * 0.15915494f);
+            q[0] = x; q[1] = y; q[2] = th; q[8] = tgt;
+        }
+        const float c = cosf(th), s_ = sinf(th);
+        if (a.trunk_mode) {
+            if (nd < a.max_disc) { discs[3 * nd] = x; discs[3 * nd + 1] = y; discs[3 * nd + 2] = q[13]; nd++; }
+        } else if (q[12] > 0.5f) {  // legs
+            const float front = 0.3f * cosf(q[9] * (2.0f / 0.3f) + q[11]);
+            const float side = 0.1f * cosf(q[10] * (2.0f / 0.1f) + q[11]) + 0.1f;
+            if (nd + 1 < a.max_disc) {
+                discs[3 * nd] = x + c * front - s_ * side; discs[3 * nd + 1] = y + s_ * front + c * side;
+                discs[3 * nd + 2] = 0.03f; nd++;
+                discs[3 * nd] = x - c * front + s_ * side; discs[3 * nd + 1] = y - s_ * front - c * side;
+                discs[3 * nd + 2] = 0.03f; nd++;
+            }
+        } else if (segs && ns + 3 < a.max_seg) {  // box footprint, closed
+            const float fx[4] = {0.22f, -0.22f, -0.22f, 0.22f}, fy[4] = {0.19f, 0.19f, -0.19f, -0.19f};
+            float wx[4], wy[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { wx[i] = c * fx[i] - s_ * fy[i] + x; wy[i] = s_ * fx[i] + c * fy[i] + y; }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                float *sg = segs + 4 * (ns + i);
+                sg[0] = wx[i]; sg[1] = wy[i]; sg[2] = wx[(i + 1) & 3]; sg[3] = wy[(i + 1) & 3];
+            }
+            ns += 4;
+        }
+    }
+    a.ndisc[e] = nd;
+    if (a.nseg) a.nseg[e] = ns;
+}
+
 // ------------------------------------------------------------------ EDT build kernels
 // Pass 1: per column, distance to the nearest occupied cell of that column (coalesced in x).
 __global__ void edt_columns_kernel(const uint8_t *__restrict__ occ, int H, int W, int32_t *__restrict__ g)
@@ -758,6 +882,8 @@ int navgym_debug_read_prof(unsigned long long *out, int reset)
 int navgym_abi_version(void) { return 1; }
 int navgym_sizeof_step_args(void) { return (int)sizeof(navgym_step_args_t); }
 int navgym_sizeof_map(void) { return (int)sizeof(navgym_map_t); }
+int navgym_sizeof_her_args(void) { return (int)sizeof(navgym_her_args_t); }
+int navgym_sizeof_peds_args(void) { return (int)sizeof(navgym_peds_args_t); }
 uint64_t navgym_launch_count(void) { return g_launches; }
 const char *navgym_error_string(int code) { return cudaGetErrorString((cudaError_t)code); }
 int navgym_device_count(void)
@@ -780,6 +906,23 @@ int navgym_reset_obs_batch(const navgym_step_args_t *args, void *stream)
     if (args->num_envs <= 0) return 0;
     if (args->obs_stride < OBS_DIM) return (int)cudaErrorInvalidValue;
     launch_step<true>(*args, (cudaStream_t)stream);
+    return (int)cudaGetLastError();
+}
+
+int navgym_compute_rewards(const navgym_her_args_t *args, void *stream)
+{
+    if (args->count <= 0) return 0;
+    if (args->obs_stride < OBS_DIM) return (int)cudaErrorInvalidValue;
+    her_kernel<<<(args->count + 7) / 8, 256, 0, (cudaStream_t)stream>>>(*args);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
+
+int navgym_peds_advance(const navgym_peds_args_t *args, void *stream)
+{
+    if (args->num_envs <= 0) return 0;
+    peds_advance_kernel<<<(args->num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*args);
+    g_launches++;
     return (int)cudaGetLastError();
 }
 

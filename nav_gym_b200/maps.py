@@ -142,3 +142,44 @@ def spawn_pool(map_info, n, rng=None, min_goal_dist=10., max_goal_dist=20., goal
         return np.zeros((0, 5))
     pool = np.concatenate(out)[:n]
     return pool[rng.permutation(len(pool))]
+
+
+def spawn_pedestrians(map_info, robot_xy, num_peds, rng=None, v_pref_range=(0.0, 0.6),
+                      has_legs_ratio=0.5, min_robot_dist=4.0, min_goal_dist=10.0, trunk_radius=0.3):
+    """Pedestrian state rows (layout include/navgym_b200.h, NAVGYM_PED_F floats each) for one
+    environment, following the reference's spawn law (env.py:786-806): start on a free
+    cost-map cell at least 4 m from the robot, a goal at least 10 m away that is connected to
+    it, preferred speed U[0, 0.6], legs with probability 0.5.  The two waypoints are the start
+    and the goal (the reference walks A*-waypoints towards the goal and then re-plans,
+    env.py:633-680; the scripted stand-in walks back and forth)."""
+    rng = np.random if rng is None else rng
+    cm = cost_map(map_info)
+    blocked = cm['data'] > 0
+    rows, cols = np.where(~blocked)
+    res, (ox, oy) = cm['resolution'], cm['origin']
+    out = np.zeros((num_peds, _lib.PED_F), np.float32)
+    if len(rows) == 0:
+        return out
+    xs, ys = (cols + 0.5) * res + ox, (rows + 0.5) * res + oy
+    for p in range(num_peds):
+        for _ in range(100):
+            i = rng.randint(len(rows))
+            if np.hypot(xs[i] - robot_xy[0], ys[i] - robot_xy[1]) < min_robot_dist:
+                continue
+            geo = grid_bfs(blocked, (rows[i], cols[i]))
+            d = np.hypot(xs - xs[i], ys - ys[i])
+            ok = np.where((d > min_goal_dist) & (geo[rows, cols] >= 0))[0]
+            if len(ok) == 0:
+                ok = np.where((d > 0.3 * min_goal_dist) & (geo[rows, cols] >= 0))[0]
+            if len(ok):
+                j = ok[rng.randint(len(ok))]
+                break
+        else:
+            j = i
+        th = rng.uniform(0, 2 * np.pi)
+        out[p, :4] = (xs[i], ys[i], th, rng.uniform(*v_pref_range))
+        out[p, 4:8] = (xs[i], ys[i], xs[j], ys[j])
+        out[p, 8] = 1.0
+        out[p, 12] = float(rng.random_sample() < has_legs_ratio)
+        out[p, 13] = trunk_radius
+    return out

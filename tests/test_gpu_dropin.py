@@ -1,0 +1,126 @@
+"""GPU: the drop-in surface (gym.make('NavGym-v0')), the HER batch kernel against the
+reference's recorded rewards, and the scripted-pedestrian kernel."""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('name', gu.trace_names())
+def test_her_kernel_reproduces_reference_rewards(name):
+    """Stored observations of a reference trace -> compute_rewards / terminals / info on the
+    device == what the reference's own compute_reward / compute_done / compute_info returned."""
+    from nav_gym_b200.batched_env import BatchedNavGym
+    G = gu.load(name)
+    env = BatchedNavGym(1, [gu.map_info(G)], device='cuda:0')
+    assert np.array_equal(env.scan_threshold, G['thr'])
+    obs = np.concatenate([G['scan'], G['tail'].astype(np.float32)], axis=1)
+    # on a crash the reference returns the re-scanned observation, whose reward terms were
+    # computed on the crashed one: compare the steps whose returned obs is the scored obs
+    keep = G['is_crash'] == 0
+    out = env.compute_rewards(torch.from_numpy(obs).cuda(), torch.from_numpy(G['desired'].astype(np.float32)).cuda())
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    assert np.array_equal(out['is_success'][keep], G['is_success'][keep])
+    assert np.array_equal(out['is_crash'][keep], G['is_crash'][keep])
+    assert np.array_equal(out['done'][keep], G['done'][keep])
+    assert np.allclose(out['reward'][keep], G['reward'][keep], rtol=0, atol=2e-5)
+    assert np.allclose(out['distance'][keep], G['distance'][keep], rtol=0, atol=1e-5)
+
+
+def test_gym_make_dropin_contract():
+    import nav_gym_b200  # noqa: F401  (registers NavGym-v0)
+    from nav_gym_b200 import gym_shim
+    gym = gym_shim.install()
+    np.random.seed(3)
+    env = gym.make('NavGym-v0')
+    assert env.action_space.shape == (2,) and env.observation_space['observation'].shape == (519,)
+    obs = env.reset()
+    assert set(obs) == {'observation', 'achieved_goal', 'desired_goal'}
+    assert obs['observation'].shape == (519,) and obs['observation'].dtype == np.float64
+    assert np.array_equal(obs['observation'][512:514], obs['observation'][514:516])  # prev_pose == pose
+    assert np.array_equal(obs['observation'][516:518], [0, 0])
+    d0 = np.linalg.norm(obs['achieved_goal'] - obs['desired_goal'])
+    assert env.min_goal_dist < d0 < env.max_goal_dist
+    assert 5 <= len(env.humans) <= 15
+    prev = obs
+    for t in range(25):
+        a = np.array([0.3, 0.2 * np.sin(t)])
+        obs, reward, done, info = env.step(a)
+        assert isinstance(reward, np.float64) and isinstance(done, np.bool_)
+        assert set(info) == {'is_success', 'is_crash', 'distance'}
+        assert info['is_success'].dtype == np.float32 and info['distance'].dtype == np.float64
+        o = obs['observation']
+        assert np.array_equal(o[512:514], prev['achieved_goal'])     # prev_pose
+        assert np.array_equal(o[514:516], obs['achieved_goal'])      # pose
+        if t > 0:
+            assert np.allclose(o[516:518], prev_a)                   # vel = previous action
+        assert env.steps_since_reset == t + 1
+        # the HER entry points agree with what step returned (float32 observation round trip)
+        if not info['is_crash']:
+            assert abs(env.compute_reward(a, obs) - reward) < 1e-4
+            assert env.compute_done(obs) == done
+            ci = env.compute_info(obs)
+            assert ci['is_success'] == info['is_success'] and abs(ci['distance'] - info['distance']) < 1e-5
+        prev, prev_a = obs, a
+        if done:
+            break
+    assert abs(env.robot.px - obs['achieved_goal'][0]) < 1e-12
+
+
+def test_pedestrian_kernel():
+    from nav_gym_b200 import maps, _lib
+    from nav_gym_b200.batched_env import BatchedNavGym
+    from nav_gym_b200.robot import legs_to_discs, footprint_segments, Human
+    rng = np.random.RandomState(0)
+    m = maps.create_outdoor_map(10, 0.7, rng)
+    B, P = 8, 5
+    pool = maps.spawn_pool(m, 64, rng, min_goal_dist=5, max_goal_dist=15)
+    rows = pool[:B]
+    peds = np.stack([maps.spawn_pedestrians(m, rows[e, :2], P, rng) for e in range(B)])
+    env = BatchedNavGym(B, [m], device='cuda:0')
+    env.set_state(rows[:, :2], rows[:, 2:4], rows[:, 4])
+    env.attach_pedestrians(peds)
+    env.reset()
+    nd, ns = env._pnd.cpu().numpy(), env._pns.cpu().numpy()
+    legs = peds[:, :, 12] > 0.5
+    assert np.array_equal(nd, 2 * legs.sum(1)) and np.array_equal(ns, 4 * (~legs).sum(1))
+    # geometry at the initial poses == the host helpers
+    d = env._pdiscs.cpu().numpy()
+    s = env._psegs.cpu().numpy()
+    for e in range(B):
+        want_d = [legs_to_discs(peds[e, p, :3], peds[e, p, 9:12]) for p in range(P) if legs[e, p]]
+        if want_d:
+            assert np.allclose(d[e, :nd[e]], np.concatenate(want_d), atol=1e-5)
+        want_s = [footprint_segments(*peds[e, p, :3], Human.footprint) for p in range(P) if not legs[e, p]]
+        if want_s:
+            assert np.allclose(s[e, :ns[e]], np.concatenate(want_s), atol=1e-5)
+    # motion: speed * dt per step towards the target, unicycle update of human.py:32-41
+    act = torch.zeros(B, 2, device='cuda')
+    p0 = env.peds.cpu().numpy().copy()
+    for _ in range(60):
+        env.step(act)
+    p1 = env.peds.cpu().numpy()
+    moved = np.hypot(p1[:, :, 0] - p0[:, :, 0], p1[:, :, 1] - p0[:, :, 1])
+    assert np.all(moved <= p0[:, :, 3] * 0.2 * 60 + 1e-3)
+    far = np.hypot(p0[:, :, 6] - p0[:, :, 0], p0[:, :, 7] - p0[:, :, 1]) > 9
+    d_before = np.hypot(p0[:, :, 6] - p0[:, :, 0], p0[:, :, 7] - p0[:, :, 1])
+    d_after = np.hypot(p1[:, :, 6] - p1[:, :, 0], p1[:, :, 7] - p1[:, :, 1])
+    fast = p0[:, :, 3] > 0.2
+    assert np.all(d_after[far & fast] < d_before[far & fast])   # they approach their goals
+    assert np.all(p1[:, :, 9:12] != p0[:, :, 9:12]) or not fast.any()
+    # a pedestrian parked right in front of the robot shows up in the scan
+    peds2 = peds.copy()
+    peds2[:, 0, 0] = rows[:, 0] + 1.5 * np.cos(rows[:, 4])
+    peds2[:, 0, 1] = rows[:, 1] + 1.5 * np.sin(rows[:, 4])
+    peds2[:, 0, 3] = 0
+    peds2[:, 0, 4:6] = peds2[:, 0, 0:2]
+    peds2[:, 0, 6:8] = peds2[:, 0, 0:2]
+    peds2[:, 0, 12] = 0   # box
+    env2 = BatchedNavGym(B, [m], device='cuda:0')
+    env2.set_state(rows[:, :2], rows[:, 2:4], rows[:, 4])
+    env2.attach_pedestrians(peds2)
+    obs = env2.reset().cpu().numpy()
+    assert np.all(obs[:, 256] < 1.5) and np.all(obs[:, 256] > 1.2)   # beam 256 looks forward

