@@ -26,6 +26,7 @@ extern "C" {
 #define NAVGYM_HIT_NONE (-32768)
 #define NAVGYM_MAX_DISC 64     /* per-env capacity of the kernel's staging buffers */
 #define NAVGYM_MAX_SEG 128
+#define NAVGYM_SCHED_BUCKETS 32
 
 /* rows of the structure-of-arrays float64 state block state[NAVGYM_NS][num_envs] */
 enum {
@@ -76,7 +77,8 @@ typedef struct {
     int32_t resample_map;    /* 1: auto-reset also draws a new map id */
     uint64_t seed;
     int64_t env_offset;      /* global index of env 0 (multi-GPU sharding) */
-    int64_t _reserved;
+    int32_t sched_phase;     /* which third of `sched` is current: step counter mod 3 */
+    int32_t _pad1;
     float noise_lo, noise_hi; /* scan_noise_std range resampled at auto-reset */
     /* ---- device pointers ---- */
     const navgym_map_t *maps;
@@ -101,6 +103,11 @@ typedef struct {
     uint8_t *done, *is_success, *is_crash, *truncated;
     float *distance;
     int16_t *hits;
+    /* optional longest-first launch order, i32 [3][NAVGYM_SCHED_BUCKETS] counts followed by
+     * [3][NAVGYM_SCHED_BUCKETS][num_envs] env ids; initialise third 0 with all envs in bucket 0
+     * (count = num_envs, list = 0..num_envs-1), everything else zero, and advance sched_phase by
+     * one (mod 3) after every navgym_step_batch.  NULL = block i steps env i. */
+    int32_t *sched;
 } navgym_step_args_t;
 
 /* ---- fused hot path: NavGymEnv.step (env.py:591-728) over num_envs environments ------ */

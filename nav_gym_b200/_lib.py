@@ -24,6 +24,7 @@ OBS_DIM = NB + OBS_TAIL
 HIT_NONE = -32768
 MAX_DISC = 64
 MAX_SEG = 128
+SCHED_BUCKETS = 32
 NS = 10
 S_PX, S_PY, S_TH, S_GX, S_GY, S_PPX, S_PPY, S_PYAW, S_PV, S_PW = range(NS)
 
@@ -69,7 +70,7 @@ class StepArgs(C.Structure):
         ('num_envs', C.c_int32), ('obs_stride', C.c_int32), ('auto_reset', C.c_int32),
         ('max_episode_steps', C.c_int32), ('num_maps', C.c_int32), ('resample_map', C.c_int32),
         ('seed', C.c_uint64), ('env_offset', C.c_int64),
-        ('_reserved', C.c_int64),
+        ('sched_phase', C.c_int32), ('_pad1', C.c_int32),
         ('noise_lo', C.c_float), ('noise_hi', C.c_float),
         ('maps', _P), ('edt_pool', _P), ('spawn_pool', _P), ('map_id', _P),
         ('lin', _P), ('thr', _P), ('dthr', _P),
@@ -78,7 +79,7 @@ class StepArgs(C.Structure):
         ('noise', _P), ('noise_std', _P),
         ('obs', _P), ('tail64', _P), ('reward', _P),
         ('done', _P), ('is_success', _P), ('is_crash', _P), ('truncated', _P),
-        ('distance', _P), ('hits', _P),
+        ('distance', _P), ('hits', _P), ('sched', _P),
     ]
 
 

@@ -115,7 +115,8 @@ class BatchedNavGym(object):
                  time_step=0.2, distance_threshold=0.5, min_turning_radius=0.0,
                  max_disc=0, max_seg=0, seed=0, env_offset=0, auto_reset=False,
                  max_episode_steps=0, resample_map=False, scan_noise_std_range=(0.0, 0.05),
-                 cell_rule='numpy1', early_stop=True, record_hits=False, **reward):
+                 cell_rule='numpy1', early_stop=True, record_hits=False, longest_first=True,
+                 **reward):
         self.lib = _lib.require_device()
         self.device = torch.device(device)
         self.B = B = int(num_envs)
@@ -174,6 +175,14 @@ class BatchedNavGym(object):
         a.obs, a.tail64, a.reward = _ptr(self.obs), _ptr(self.tail64), _ptr(self.reward)
         a.done, a.is_success, a.is_crash = _ptr(self.done), _ptr(self.is_success), _ptr(self.is_crash)
         a.truncated, a.distance, a.hits = _ptr(self.truncated), _ptr(self.distance), _ptr(self.hits)
+        self.sched = None
+        if longest_first:
+            nbk = _lib.SCHED_BUCKETS
+            sched = np.zeros(3 * nbk + 3 * nbk * B, np.int32)
+            sched[0] = B
+            sched[3 * nbk:3 * nbk + B] = np.arange(B, dtype=np.int32)
+            self.sched = torch.from_numpy(sched).to(dev)
+            a.sched, a.sched_phase = _ptr(self.sched), 0
         self.args = a
         self._keep = None
         self._act_dev = None
@@ -338,6 +347,8 @@ class BatchedNavGym(object):
         self._geom(discs, ndisc, segs, nseg, noise, actions)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.navgym_step_batch(C.byref(self.args), self._stream()), 'step')
+        if self.sched is not None:
+            self.args.sched_phase = (self.args.sched_phase + 1) % 3
         info = dict(is_success=self.is_success, is_crash=self.is_crash, distance=self.distance,
                     episode_step=self.steps, truncated=self.truncated)
         return self.obs, self.reward, self.done, info

@@ -166,7 +166,7 @@ __device__ __forceinline__ float beam_normal(uint64_t seed, uint32_t env, uint32
 // Optional per-phase cycle accounting (tools/phase_prof.py builds with -DNAVGYM_PROFILE).
 #ifdef NAVGYM_PROFILE
 __device__ unsigned long long g_prof[16];
-#define PROF_DECL long long _pt = clock64();
+#define PROF_DECL long long _pt = clock64(); const long long _t_begin = _pt;
 #define PROF_MARK(i) do { if (tid == 0) { long long _n = clock64(); atomicAdd(&g_prof[i], (unsigned long long)(_n - _pt)); _pt = _n; } } while (0)
 #else
 #define PROF_DECL
@@ -230,8 +230,11 @@ __device__ __forceinline__ void normal4(uint64_t seed, uint32_t env, uint32_t ep
 // gathers per lane are in flight.  The three scans a step may need (the step's scan, the
 // crash re-scan env.py:718, the auto-reset first scan) run through ONE copy of the scan code
 // inside a CTA-uniform pass loop.
+#ifndef NAVGYM_THREADS_PER_SM
+#define NAVGYM_THREADS_PER_SM 1024  // resident threads the register budget is tuned for
+#endif
 template <bool IS_RESET_KERNEL, int WPE, int MARCH_SLOTS>
-__global__ void __launch_bounds__(WPE * 32, 1024 / (WPE * 32)) step_kernel(const navgym_step_args_t a)
+__global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) step_kernel(const navgym_step_args_t a)
 {
     constexpr int BPL = NB / (32 * WPE);  // beams per lane
     constexpr int TPB = WPE * 32;
@@ -239,8 +242,33 @@ __global__ void __launch_bounds__(WPE * 32, 1024 / (WPE * 32)) step_kernel(const
     __shared__ EnvSmem sm;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int e = blockIdx.x;
     const int B = a.num_envs;
+    const long long t_begin = clock64();
+    // Which environment this CTA steps.  With a schedule buffer, CTAs take environments in
+    // descending order of the cycles they cost in the previous step (they change slowly from
+    // step to step), so the longest ones start first and the launch does not end on a lone
+    // straggler; NAVGYM_SCHED_BUCKETS cost classes, bucket 0 = most expensive.
+    int e = blockIdx.x;
+    int *sched_cnt = nullptr, *sched_list = nullptr;
+    if (!IS_RESET_KERNEL && a.sched) {
+        const int cur = a.sched_phase, nxt = (a.sched_phase + 1) % 3, clr = (a.sched_phase + 2) % 3;
+        int *cnt = a.sched;                                   // [3][NBK]
+        int *lst = a.sched + 3 * NAVGYM_SCHED_BUCKETS;        // [3][NBK][B]
+        const int c = cnt[cur * NAVGYM_SCHED_BUCKETS + (threadIdx.x & 31)];
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += v;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, (int)blockIdx.x < incl);
+        const int b = m ? __ffs(m) - 1 : 31;
+        const int excl = __shfl_sync(0xffffffffu, incl - c, b);
+        e = lst[((size_t)cur * NAVGYM_SCHED_BUCKETS + b) * B + ((int)blockIdx.x - excl)];
+        sched_cnt = cnt + nxt * NAVGYM_SCHED_BUCKETS;
+        sched_list = lst + (size_t)nxt * NAVGYM_SCHED_BUCKETS * B;
+        if (blockIdx.x == 0 && threadIdx.x < NAVGYM_SCHED_BUCKETS) cnt[clr * NAVGYM_SCHED_BUCKETS + threadIdx.x] = 0;
+    }
     const unsigned FULL = 0xffffffffu;
     double *S = a.state;
 #define ST(f) S[(size_t)(f) * B + e]
@@ -630,7 +658,19 @@ __global__ void __launch_bounds__(WPE * 32, 1024 / (WPE * 32)) step_kernel(const
             if (a.noise_std) a.noise_std[e] = sm.noise_std;
         }
     }
+    if (sched_cnt && tid == 0) {  // file this environment under its cost class for the next step
+        const long long kc = (clock64() - t_begin) >> 13;
+        const int b = NAVGYM_SCHED_BUCKETS - 1 - (int)(kc > NAVGYM_SCHED_BUCKETS - 1 ? NAVGYM_SCHED_BUCKETS - 1 : kc);
+        const int pos = atomicAdd(&sched_cnt[b], 1);
+        sched_list[(size_t)b * B + pos] = e;
+    }
     PROF_MARK(7);
+#ifdef NAVGYM_PROFILE
+    if (tid == 0 && a.truncated) {  // per-CTA duration (kilo-cycles, saturating) for tail analysis
+        long long dur = (clock64() - _t_begin) >> 10;
+        a.truncated[e] = (uint8_t)(dur > 255 ? 255 : dur);
+    }
+#endif
 #undef ST
 #undef BEAM
 }

@@ -69,3 +69,15 @@ for lanes in (32, 64, 128, 256):
     stat = s1[:300].reshape(300, 16 // wpe, wpe, 32).sum(1).max(2).max(1).mean()
     print('lanes %3d: ideal %.1f  dynamic in-order %.1f  longest-first %.1f  static (current) %.1f' % (
         lanes, s1[:300].sum(1).mean() / lanes, dyn, lpt, stat))
+
+# ---- lockstep groups of 32 adjacent beams (warp-uniform params, no per-lane refill)
+g = s1.reshape(N, 16, 32)
+print('lockstep 32 adjacent beams: mean steps/ray %.2f, mean of group max %.2f -> SIMT efficiency %.2f' % (
+    g.mean(), g.max(2).mean(), g.mean() / g.max(2).mean()))
+for cap in (8, 12, 16, 24):
+    # two-phase: lockstep up to `cap` iterations, leftovers compacted and dealt dynamically
+    main = np.minimum(g, cap); rest = np.maximum(g - cap, 0)
+    it_main = np.minimum(g.max(2), cap).mean()
+    frac_left = (rest > 0).mean(); steps_left = rest.sum() / g.sum()
+    print(' cap %2d: main iterations/group %.2f (eff %.2f), rays continuing %.1f%%, steps left %.1f%%' % (
+        cap, it_main, main.mean() / it_main, 100 * frac_left, 100 * steps_left))

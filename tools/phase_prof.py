@@ -8,9 +8,12 @@ OUT = os.path.join(ROOT, 'tools', '_prof', 'libnavgym_b200_prof.so')
 if sys.argv[1] == 'build':
     from nav_gym_b200 import _lib
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    for tag, extra in (('', []),):
+    for tag, extra in (('', []), ('_t1280', ['-DNAVGYM_THREADS_PER_SM=1280']), ('_t1536', ['-DNAVGYM_THREADS_PER_SM=1536']), ('_t2048', ['-DNAVGYM_THREADS_PER_SM=2048'])):
         out = OUT.replace('.so', tag + '.so')
-        subprocess.check_call(['nvcc'] + _lib.NVCC_FLAGS + ['-DNAVGYM_PROFILE'] + extra + ['-o', out, _lib.SRC])
+        r = subprocess.run(['nvcc'] + _lib.NVCC_FLAGS + ['-DNAVGYM_PROFILE', '-Xptxas', '-v'] + extra + ['-o', out, _lib.SRC], capture_output=True, text=True)
+        lines = r.stderr.splitlines()
+        for i, l in enumerate(lines):
+            if 'step_kernelILb0ELi2ELi1' in l: print(tag, lines[i+1].strip(), lines[i+2].strip())
         print('built', out)
 else:
     os.environ['NAVGYM_LIB'] = OUT.replace('.so', os.environ.get('NAVGYM_VARIANT', '') + '.so')
@@ -44,3 +47,5 @@ else:
     for i, nm in enumerate(names):
         print('%-22s %8.0f cycles/CTA  %5.1f%%' % (nm, buf[i] / (n * B), 100.0 * buf[i] / tot))
     print('total %.0f cycles/CTA' % (tot / (n * B)))
+    d = env.truncated.cpu().numpy().astype(float); dn = env.done.cpu().numpy() > 0
+    print('CTA duration kcycles: mean %.1f p50 %.0f p90 %.0f p99 %.0f max %.0f | done envs (%d): mean %.1f | not done: mean %.1f max %.0f' % (d.mean(), np.percentile(d,50), np.percentile(d,90), np.percentile(d,99), d.max(), dn.sum(), d[dn].mean() if dn.any() else 0, d[~dn].mean(), d[~dn].max()))
