@@ -79,6 +79,8 @@ typedef struct {
     int64_t env_offset;      /* global index of env 0 (multi-GPU sharding) */
     int32_t sched_phase;     /* which third of `sched` is current: step counter mod 3 */
     int32_t _pad1;
+    int32_t env_begin;       /* this launch steps environments [env_begin, env_begin + env_count) */
+    int32_t env_count;       /* 0 = through num_envs; num_envs stays the SoA stride of all buffers */
     float noise_lo, noise_hi; /* scan_noise_std range resampled at auto-reset */
     /* ---- device pointers ---- */
     const navgym_map_t *maps;
@@ -112,6 +114,20 @@ typedef struct {
 
 /* ---- fused hot path: NavGymEnv.step (env.py:591-728) over num_envs environments ------ */
 int navgym_step_batch(const navgym_step_args_t *args, void *stream);
+/* The same step for a caller whose buffers live on the HOST (the reference's own calling
+ * convention: numpy in, numpy out).  actions_host f32 [num_envs][2], obs_host f32
+ * [num_envs][obs_stride], reward_host f32 [num_envs], done_host u8 [num_envs] must be pinned
+ * (cudaHostAlloc / cudaHostRegister).  The batch is stepped as `chunks` launches over consecutive
+ * environment ranges on prioritised streams, each followed by the device-to-host copy of its
+ * rows, so the copies of early chunks overlap the raycast of later ones; args->actions, obs,
+ * reward, done are the device staging buffers.  Ordered after prior work on `stream`; returns
+ * when every result has landed on the host. */
+typedef struct navgym_host_pipe navgym_host_pipe_t;
+navgym_host_pipe_t *navgym_host_pipe_create(int chunks, int num_envs, int longest_first);
+void navgym_host_pipe_destroy(navgym_host_pipe_t *pipe);
+int navgym_step_batch_host(navgym_host_pipe_t *pipe, const navgym_step_args_t *args, void *stream,
+                           const float *actions_host, float *obs_host, float *reward_host,
+                           uint8_t *done_host);
 /* first observation of an episode, NavGymEnv.reset's tail (env.py:822-831) */
 int navgym_reset_obs_batch(const navgym_step_args_t *args, void *stream);
 

@@ -71,6 +71,7 @@ class StepArgs(C.Structure):
         ('max_episode_steps', C.c_int32), ('num_maps', C.c_int32), ('resample_map', C.c_int32),
         ('seed', C.c_uint64), ('env_offset', C.c_int64),
         ('sched_phase', C.c_int32), ('_pad1', C.c_int32),
+        ('env_begin', C.c_int32), ('env_count', C.c_int32),
         ('noise_lo', C.c_float), ('noise_hi', C.c_float),
         ('maps', _P), ('edt_pool', _P), ('spawn_pool', _P), ('map_id', _P),
         ('lin', _P), ('thr', _P), ('dthr', _P),
@@ -103,7 +104,8 @@ class PedsArgs(C.Structure):
 
 
 EXPORTS = [
-    'navgym_step_batch', 'navgym_reset_obs_batch', 'navgym_edt_build', 'navgym_calc_range_many',
+    'navgym_step_batch', 'navgym_reset_obs_batch', 'navgym_host_pipe_create', 'navgym_host_pipe_destroy',
+    'navgym_step_batch_host', 'navgym_edt_build', 'navgym_calc_range_many',
     'navgym_raymarching_create_host', 'navgym_raymarching_calc_range_many_host',
     'navgym_raymarching_edt_dev', 'navgym_raymarching_edt_host', 'navgym_raymarching_destroy',
     'navgym_render_segments_in_lidar', 'navgym_render_discs_in_lidar', 'navgym_render_in_lidar_host',
@@ -127,6 +129,11 @@ def load():
     lib = C.CDLL(SO)
     lib.navgym_step_batch.argtypes = [C.POINTER(StepArgs), _P]
     lib.navgym_reset_obs_batch.argtypes = [C.POINTER(StepArgs), _P]
+    lib.navgym_host_pipe_create.restype = _P
+    lib.navgym_host_pipe_create.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.navgym_host_pipe_destroy.restype = None
+    lib.navgym_host_pipe_destroy.argtypes = [_P]
+    lib.navgym_step_batch_host.argtypes = [_P, C.POINTER(StepArgs), _P, _P, _P, _P, _P]
     lib.navgym_edt_build.argtypes = [_P, C.c_int, C.c_int, _P, _P, _P]
     lib.navgym_calc_range_many.argtypes = [_P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_float,
                                            C.c_float, _P, _P]

@@ -177,15 +177,12 @@ class BatchedNavGym(object):
         a.truncated, a.distance, a.hits = _ptr(self.truncated), _ptr(self.distance), _ptr(self.hits)
         self.sched = None
         if longest_first:
-            nbk = _lib.SCHED_BUCKETS
-            sched = np.zeros(3 * nbk + 3 * nbk * B, np.int32)
-            sched[0] = B
-            sched[3 * nbk:3 * nbk + B] = np.arange(B, dtype=np.int32)
-            self.sched = torch.from_numpy(sched).to(dev)
+            self.sched = self._make_sched(np.arange(B, dtype=np.int32))
             a.sched, a.sched_phase = _ptr(self.sched), 0
         self.args = a
         self._keep = None
         self._act_dev = None
+        self._pipe = None
         self.peds = None
 
     # -------------------------------------------------------------------------------------
@@ -246,19 +243,52 @@ class BatchedNavGym(object):
                        noise_std=rng.uniform(lo, hi, self.B).astype(np.float32))
         return self.reset()
 
-    def step_host(self, actions_host, obs_host, reward_host, done_host):
+    def _make_sched(self, envs):
+        """longest-first schedule buffer (include/navgym_b200.h) for the given env ids"""
+        nbk = _lib.SCHED_BUCKETS
+        sched = np.zeros(3 * nbk + 3 * nbk * self.B, np.int32)
+        sched[0] = len(envs)
+        sched[3 * nbk:3 * nbk + len(envs)] = envs
+        return torch.from_numpy(sched).to(self.device)
+
+    def step_host(self, actions_host, obs_host, reward_host, done_host, chunks=2):
         """The same step for callers that live on the host (the reference's calling
-        convention): pinned host actions in, pinned host obs / reward / done out; the copies
-        ride the env's stream and the call returns when the results have landed."""
-        if self._act_dev is None:
+        convention): pinned host actions in, pinned host obs / reward / done out, through the
+        C ABI's navgym_step_batch_host: `chunks` launches over consecutive env ranges on
+        prioritised streams, each followed by the D2H copy of its rows, so the copies of early
+        chunks overlap the raycast of later ones (PCIe is the end-to-end bound: 2.1 KB per
+        env-step).  Returns when all results have landed."""
+        for t in (actions_host, obs_host, reward_host, done_host):
+            if not t.is_pinned() or not t.is_contiguous():
+                raise ValueError('step_host needs contiguous pinned host tensors')
+        assert obs_host.dtype == torch.float32 and tuple(obs_host.shape) == (self.B, OBS_DIM)
+        assert reward_host.dtype == torch.float32 and done_host.dtype == torch.uint8
+        assert actions_host.dtype == torch.float32 and actions_host.numel() == 2 * self.B
+        if self.peds is not None:
+            chunks = 1
+            self._peds_emit(advance=True)
+            self._geom(self._pdiscs, self._pnd, self._psegs, self._pns, None)
+        else:
+            self._geom(None, None, None, None, None)
+        if self._pipe is None or self._pipe[1] != chunks:
+            if self._pipe is not None:
+                self.lib.navgym_host_pipe_destroy(self._pipe[0])
+            h = self.lib.navgym_host_pipe_create(chunks, self.B, int(self.sched is not None))
+            if not h:
+                raise RuntimeError('navgym_host_pipe_create failed')
+            self._pipe = (C.c_void_p(h), chunks)
             self._act_dev = torch.empty(self.B, 2, dtype=torch.float32, device=self.device)
-        self._act_dev.copy_(actions_host, non_blocking=True)
-        self.step(self._act_dev)
-        obs_host.copy_(self.obs, non_blocking=True)
-        reward_host.copy_(self.reward, non_blocking=True)
-        done_host.copy_(self.done, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+        self.args.actions = _ptr(self._act_dev)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.navgym_step_batch_host(
+                self._pipe[0], C.byref(self.args), self._stream(), _ptr(actions_host), _ptr(obs_host),
+                _ptr(reward_host), _ptr(done_host)), 'step_host')
         return obs_host, reward_host, done_host
+
+    def __del__(self):
+        p, self._pipe = getattr(self, '_pipe', None), None
+        if p is not None:
+            self.lib.navgym_host_pipe_destroy(p[0])
 
     # ---- HER batch API (env.py:491-589) on device tensors ---------------------------------
     def compute_rewards(self, obs, goals, **reward):

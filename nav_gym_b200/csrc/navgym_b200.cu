@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
     // descending order of the cycles they cost in the previous step (they change slowly from
     // step to step), so the longest ones start first and the launch does not end on a lone
     // straggler; NAVGYM_SCHED_BUCKETS cost classes, bucket 0 = most expensive.
-    int e = blockIdx.x;
+    int e = a.env_begin + blockIdx.x;
     int *sched_cnt = nullptr, *sched_list = nullptr;
     if (!IS_RESET_KERNEL && a.sched) {
         const int cur = a.sched_phase, nxt = (a.sched_phase + 1) % 3, clr = (a.sched_phase + 2) % 3;
@@ -883,7 +883,8 @@ static int env_int(const char *name, int dflt)
 template <bool RESET, int WPE, int SLOTS>
 static void launch_one(const navgym_step_args_t &a, cudaStream_t st)
 {
-    step_kernel<RESET, WPE, SLOTS><<<a.num_envs, WPE * 32, 0, st>>>(a);
+    const int count = a.env_count > 0 ? a.env_count : a.num_envs - a.env_begin;
+    step_kernel<RESET, WPE, SLOTS><<<count, WPE * 32, 0, st>>>(a);
 }
 
 template <bool RESET>
@@ -936,9 +937,95 @@ int navgym_device_count(void)
 int navgym_step_batch(const navgym_step_args_t *args, void *stream)
 {
     if (args->num_envs <= 0) return 0;
-    if (args->obs_stride < OBS_DIM) return (int)cudaErrorInvalidValue;
+    if (args->obs_stride < OBS_DIM || args->env_begin < 0 || args->env_begin + args->env_count > args->num_envs)
+        return (int)cudaErrorInvalidValue;
     launch_step<false>(*args, (cudaStream_t)stream);
     return (int)cudaGetLastError();
+}
+
+// ---- host-buffer step: chunked launches on prioritised streams, D2H of early chunks
+// overlapping the raycast of later ones -----------------------------------------------------
+#define NAVGYM_MAX_CHUNKS 8
+struct navgym_host_pipe {
+    int chunks, num_envs;
+    cudaStream_t streams[NAVGYM_MAX_CHUNKS];
+    cudaEvent_t ready;
+    int32_t *sched[NAVGYM_MAX_CHUNKS];
+    int phase[NAVGYM_MAX_CHUNKS];
+    int b0[NAVGYM_MAX_CHUNKS + 1];
+};
+
+navgym_host_pipe_t *navgym_host_pipe_create(int chunks, int num_envs, int longest_first)
+{
+    if (chunks < 1 || chunks > NAVGYM_MAX_CHUNKS || num_envs < 1) return nullptr;
+    navgym_host_pipe_t *p = new navgym_host_pipe_t();
+    p->chunks = chunks;
+    p->num_envs = num_envs;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi is the numerically lowest = highest priority
+    for (int c = 0; c <= chunks; c++) p->b0[c] = (int)((long long)num_envs * c / chunks);
+    for (int c = 0; c < chunks; c++) {
+        int prio = hi + c;
+        if (prio > lo) prio = lo;
+        if (cudaStreamCreateWithPriority(&p->streams[c], cudaStreamNonBlocking, prio) != cudaSuccess) { delete p; return nullptr; }
+        p->sched[c] = nullptr;
+        p->phase[c] = 0;
+        if (longest_first) {
+            const size_t n = 3 * NAVGYM_SCHED_BUCKETS + (size_t)3 * NAVGYM_SCHED_BUCKETS * num_envs;
+            int32_t *h = new int32_t[n]();
+            const int cnt = p->b0[c + 1] - p->b0[c];
+            h[0] = cnt;
+            for (int i = 0; i < cnt; i++) h[3 * NAVGYM_SCHED_BUCKETS + i] = p->b0[c] + i;
+            cudaError_t err = cudaMalloc(&p->sched[c], n * sizeof(int32_t));
+            if (!err) err = cudaMemcpy(p->sched[c], h, n * sizeof(int32_t), cudaMemcpyHostToDevice);
+            delete[] h;
+            if (err) { delete p; return nullptr; }
+        }
+    }
+    cudaEventCreateWithFlags(&p->ready, cudaEventDisableTiming);
+    return p;
+}
+
+void navgym_host_pipe_destroy(navgym_host_pipe_t *p)
+{
+    if (!p) return;
+    for (int c = 0; c < p->chunks; c++) {
+        cudaStreamDestroy(p->streams[c]);
+        if (p->sched[c]) cudaFree(p->sched[c]);
+    }
+    cudaEventDestroy(p->ready);
+    delete p;
+}
+
+int navgym_step_batch_host(navgym_host_pipe_t *p, const navgym_step_args_t *args, void *stream,
+                           const float *actions_host, float *obs_host, float *reward_host,
+                           uint8_t *done_host)
+{
+    if (!p || args->num_envs != p->num_envs || !args->actions) return (int)cudaErrorInvalidValue;
+    cudaStream_t in = (cudaStream_t)stream;
+    const size_t B = (size_t)args->num_envs;
+    CK(cudaMemcpyAsync((void *)args->actions, actions_host, B * 2 * sizeof(float), cudaMemcpyHostToDevice, in));
+    CK(cudaEventRecord(p->ready, in));
+    for (int c = 0; c < p->chunks; c++) {
+        cudaStream_t st = p->streams[c];
+        navgym_step_args_t a = *args;
+        a.env_begin = p->b0[c];
+        a.env_count = p->b0[c + 1] - p->b0[c];
+        if (a.env_count <= 0) continue;
+        a.sched = p->sched[c];
+        a.sched_phase = p->phase[c];
+        CK(cudaStreamWaitEvent(st, p->ready, 0));
+        int err = navgym_step_batch(&a, st);
+        if (err) return err;
+        if (p->sched[c]) p->phase[c] = (p->phase[c] + 1) % 3;
+        const size_t b0 = (size_t)a.env_begin, n = (size_t)a.env_count;
+        CK(cudaMemcpyAsync(obs_host + b0 * args->obs_stride, args->obs + b0 * args->obs_stride,
+                           n * args->obs_stride * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(reward_host + b0, args->reward + b0, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(done_host + b0, args->done + b0, n, cudaMemcpyDeviceToHost, st));
+    }
+    for (int c = 0; c < p->chunks; c++) CK(cudaStreamSynchronize(p->streams[c]));
+    return 0;
 }
 
 int navgym_reset_obs_batch(const navgym_step_args_t *args, void *stream)
