@@ -213,11 +213,15 @@ def main():
             torch.cuda.synchronize(dev)
 
     # ---- device-resident leg ---------------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
     for i in range(W):
         env.step(bank[i % n_bank])
+    if sampler is not None:  # nvidia-smi needs a moment to deliver its first sample
+        t_wait = time.time()
+        while not sampler.rows and time.time() - t_wait < 3.0:
+            time.sleep(0.05)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     launches0 = lib.navgym_launch_count()
     t0 = time.time()
     for i in range(K):
@@ -235,28 +239,51 @@ def main():
     crash_frac = float(env.is_crash.float().mean().item())
     done_frac = float(env.done.float().mean().item())
 
-    # ---- end-to-end leg: host buffers, copies inside the timed region -------------------
+    # ---- end-to-end legs: HOST buffers, copies inside the timed region ----------------------
+    # (a) synchronous call: navgym_step_batch_host = H2D actions -> step -> D2H obs/reward/done
+    # (b) two env groups in flight (submit/wait): each group's next actions are only handed in
+    #     after its previous observations have landed on the host; while the host holds group
+    #     A's results, group B is stepping, so PCIe hides behind the raycast.
     act_h = torch.empty(n_bank, B, 2, dtype=torch.float32).pin_memory()
     act_h.copy_(bank.cpu())
     obs_h = torch.empty(B, NB + 7, dtype=torch.float32).pin_memory()
     rew_h = torch.empty(B, dtype=torch.float32).pin_memory()
     done_h = torch.empty(B, dtype=torch.uint8).pin_memory()
-    Ke = min(K, 100)
+    Ke = min(K, 200)
     for i in range(3):
         env.step_host(act_h[i % n_bank], obs_h, rew_h, done_h)
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    t_s = time.perf_counter()
     for i in range(Ke):
         env.step_host(act_h[i % n_bank], obs_h, rew_h, done_h)
-    e1.record()
     barrier()
-    e2e_ms = e0.elapsed_time(e1)
+    e2e_sync_ms = (time.perf_counter() - t_s) * 1e3
 
-    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+    n_groups = int(os.environ.get('NAVGYM_HOST_GROUPS', '4'))
+    bounds = env.host_groups(n_groups)
+    cur = torch.empty(B, 2, dtype=torch.float32).pin_memory()
+
+    def pipelined(n):
+        cur.copy_(act_h[0])
+        for g in range(n_groups):
+            env.submit_host(g, cur, obs_h, rew_h, done_h)
+        for i in range(n):
+            for g, (b0, b1) in enumerate(bounds):
+                env.wait_host(g)                      # group g's obs / reward / done are on the host
+                if i + 1 < n:
+                    cur[b0:b1].copy_(act_h[(i + 1) % n_bank, b0:b1])   # "policy": next actions
+                    env.submit_host(g, cur, obs_h, rew_h, done_h)
+    pipelined(3)
+    barrier()
+    t_s = time.perf_counter()
+    pipelined(Ke)
+    barrier()
+    e2e_ms = (time.perf_counter() - t_s) * 1e3
+
+    t = torch.tensor([total_ms, e2e_ms, e2e_sync_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = float(t[0]), float(t[1])
+    total_ms, e2e_ms, e2e_sync_ms = float(t[0]), float(t[1]), float(t[2])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -283,7 +310,13 @@ def main():
                      "note": "latency/issue-bound gather kernel: see DESIGN.md roofline section"},
         "e2e": {"value": world * B * Ke / (e2e_ms * 1e-3), "unit": "env-steps/s",
                 "h2d_bytes_per_step": B * 2 * 4, "d2h_bytes_per_step": B * ((NB + 7) * 4 + 4 + 1),
-                "steps": Ke},
+                "steps": Ke, "timing": "host wall clock, max over ranks",
+                "api": "BatchedNavGym.submit_host/wait_host (C ABI navgym_step_batch_host_submit/"
+                       "_wait): pinned host actions in, pinned host obs/reward/done out, two env "
+                       "groups in flight; a group's next actions are submitted only after its "
+                       "previous results landed",
+                "sync_value": world * B * Ke / (e2e_sync_ms * 1e-3),
+                "sync_api": "BatchedNavGym.step_host (navgym_step_batch_host), one blocking call per step"},
         "gpu_launches": launches,
         "clocks": clocks,
     }
@@ -296,7 +329,7 @@ def main():
 
 # dram__bytes_read.sum + dram__bytes_write.sum of step_kernel<false> per launch, from the
 # `ncu --set full` capture summarised in profiles/ (None until measured).
-TRAFFIC_BYTES_PER_LAUNCH = None
+TRAFFIC_BYTES_PER_LAUNCH = 4284672  # profiles/r1_step_kernel_ncu_full_summary.txt
 
 if __name__ == '__main__':
     main()

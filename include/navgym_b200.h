@@ -128,6 +128,17 @@ void navgym_host_pipe_destroy(navgym_host_pipe_t *pipe);
 int navgym_step_batch_host(navgym_host_pipe_t *pipe, const navgym_step_args_t *args, void *stream,
                            const float *actions_host, float *obs_host, float *reward_host,
                            uint8_t *done_host);
+/* Asynchronous form for hosts that keep several groups of environments in flight (group g =
+ * the pipe's g-th env range; EnvPool-style): submit enqueues H2D(actions of the group) -> step
+ * -> D2H(its rows) on the group's stream and returns at once; wait blocks until that group's
+ * results are on the host.  While the host consumes group A's observations group B is stepping,
+ * so the PCIe transfer of one group hides behind the raycast of the other.  The caller must not
+ * submit a group again before waiting for it, and must have synchronised prior work that
+ * touches the state (reset) before the first submit. */
+int navgym_step_batch_host_submit(navgym_host_pipe_t *pipe, const navgym_step_args_t *args, int group,
+                                  const float *actions_host, float *obs_host, float *reward_host,
+                                  uint8_t *done_host);
+int navgym_step_batch_host_wait(navgym_host_pipe_t *pipe, int group);
 /* first observation of an episode, NavGymEnv.reset's tail (env.py:822-831) */
 int navgym_reset_obs_batch(const navgym_step_args_t *args, void *stream);
 

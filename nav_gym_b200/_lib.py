@@ -105,7 +105,7 @@ class PedsArgs(C.Structure):
 
 EXPORTS = [
     'navgym_step_batch', 'navgym_reset_obs_batch', 'navgym_host_pipe_create', 'navgym_host_pipe_destroy',
-    'navgym_step_batch_host', 'navgym_edt_build', 'navgym_calc_range_many',
+    'navgym_step_batch_host', 'navgym_step_batch_host_submit', 'navgym_step_batch_host_wait', 'navgym_edt_build', 'navgym_calc_range_many',
     'navgym_raymarching_create_host', 'navgym_raymarching_calc_range_many_host',
     'navgym_raymarching_edt_dev', 'navgym_raymarching_edt_host', 'navgym_raymarching_destroy',
     'navgym_render_segments_in_lidar', 'navgym_render_discs_in_lidar', 'navgym_render_in_lidar_host',
@@ -134,6 +134,8 @@ def load():
     lib.navgym_host_pipe_destroy.restype = None
     lib.navgym_host_pipe_destroy.argtypes = [_P]
     lib.navgym_step_batch_host.argtypes = [_P, C.POINTER(StepArgs), _P, _P, _P, _P, _P]
+    lib.navgym_step_batch_host_submit.argtypes = [_P, C.POINTER(StepArgs), C.c_int, _P, _P, _P, _P]
+    lib.navgym_step_batch_host_wait.argtypes = [_P, C.c_int]
     lib.navgym_edt_build.argtypes = [_P, C.c_int, C.c_int, _P, _P, _P]
     lib.navgym_calc_range_many.argtypes = [_P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_float,
                                            C.c_float, _P, _P]

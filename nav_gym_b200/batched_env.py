@@ -285,6 +285,36 @@ class BatchedNavGym(object):
                 _ptr(reward_host), _ptr(done_host)), 'step_host')
         return obs_host, reward_host, done_host
 
+    # ---- asynchronous host API: several env groups in flight (EnvPool style) ----------------
+    def host_groups(self, groups=2):
+        """Split the batch into `groups` consecutive env ranges for submit_host / wait_host and
+        return their (begin, end) bounds."""
+        if self.peds is not None:
+            raise NotImplementedError('async host groups with device pedestrians')
+        if self._pipe is not None:
+            self.lib.navgym_host_pipe_destroy(self._pipe[0])
+        h = self.lib.navgym_host_pipe_create(groups, self.B, int(self.sched is not None))
+        if not h:
+            raise RuntimeError('navgym_host_pipe_create failed')
+        self._pipe = (C.c_void_p(h), groups)
+        self._act_dev = torch.empty(self.B, 2, dtype=torch.float32, device=self.device)
+        self.args.actions = _ptr(self._act_dev)
+        self._geom(None, None, None, None, None)
+        torch.cuda.synchronize(self.device)
+        return [(self.B * g // groups, self.B * (g + 1) // groups) for g in range(groups)]
+
+    def submit_host(self, group, actions_host, obs_host, reward_host, done_host):
+        """Enqueue one step of env group `group`: its rows of the pinned [B, ...] host tensors
+        are read / written; returns immediately."""
+        self.args.actions = _ptr(self._act_dev)
+        _lib.check(self.lib.navgym_step_batch_host_submit(
+            self._pipe[0], C.byref(self.args), int(group), _ptr(actions_host), _ptr(obs_host),
+            _ptr(reward_host), _ptr(done_host)), 'step_host_submit')
+
+    def wait_host(self, group):
+        """Block until the results of the last submit_host(group) are on the host."""
+        _lib.check(self.lib.navgym_step_batch_host_wait(self._pipe[0], int(group)), 'step_host_wait')
+
     def __del__(self):
         p, self._pipe = getattr(self, '_pipe', None), None
         if p is not None:

@@ -1028,6 +1028,42 @@ int navgym_step_batch_host(navgym_host_pipe_t *p, const navgym_step_args_t *args
     return 0;
 }
 
+// Asynchronous variant for callers that keep several groups of environments in flight
+// (group g = the pipe's g-th env range): submit enqueues H2D(actions) -> step -> D2H(results)
+// for one group on that group's stream and returns at once; wait blocks until that group's
+// results have landed.  While the host consumes group A's observations, group B is stepping.
+int navgym_step_batch_host_submit(navgym_host_pipe_t *p, const navgym_step_args_t *args, int group,
+                                  const float *actions_host, float *obs_host, float *reward_host,
+                                  uint8_t *done_host)
+{
+    if (!p || group < 0 || group >= p->chunks || args->num_envs != p->num_envs || !args->actions)
+        return (int)cudaErrorInvalidValue;
+    cudaStream_t st = p->streams[group];
+    navgym_step_args_t a = *args;
+    a.env_begin = p->b0[group];
+    a.env_count = p->b0[group + 1] - p->b0[group];
+    if (a.env_count <= 0) return 0;
+    a.sched = p->sched[group];
+    a.sched_phase = p->phase[group];
+    const size_t b0 = (size_t)a.env_begin, n = (size_t)a.env_count;
+    CK(cudaMemcpyAsync((void *)(args->actions + 2 * b0), actions_host + 2 * b0, n * 2 * sizeof(float),
+                       cudaMemcpyHostToDevice, st));
+    int err = navgym_step_batch(&a, st);
+    if (err) return err;
+    if (p->sched[group]) p->phase[group] = (p->phase[group] + 1) % 3;
+    CK(cudaMemcpyAsync(obs_host + b0 * args->obs_stride, args->obs + b0 * args->obs_stride,
+                       n * args->obs_stride * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(reward_host + b0, args->reward + b0, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(done_host + b0, args->done + b0, n, cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+int navgym_step_batch_host_wait(navgym_host_pipe_t *p, int group)
+{
+    if (!p || group < 0 || group >= p->chunks) return (int)cudaErrorInvalidValue;
+    return (int)cudaStreamSynchronize(p->streams[group]);
+}
+
 int navgym_reset_obs_batch(const navgym_step_args_t *args, void *stream)
 {
     if (args->num_envs <= 0) return 0;

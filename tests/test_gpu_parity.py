@@ -171,3 +171,40 @@ def test_step_host_pipeline_matches_device_step():
         n_done += int(d.sum())
     assert n_done > 0
     assert torch.equal(envs[0].state, envs[1].state) and torch.equal(envs[0].episodes, envs[1].episodes)
+
+
+def test_async_host_groups_match_device_step():
+    """Two env groups kept in flight through submit_host / wait_host give, group by group,
+    exactly the device-resident step's results."""
+    from nav_gym_b200 import maps
+    from nav_gym_b200.batched_env import BatchedNavGym, MapPool, filter_spawn_pool
+    rng = np.random.RandomState(6)
+    m = maps.create_outdoor_map(10, 0.7, rng)
+    pool = filter_spawn_pool(m, maps.spawn_pool(m, 2048, rng, min_goal_dist=4, max_goal_dist=15))
+    mp = MapPool([m], 'cuda:0', spawn_pools=[pool])
+    B = 777
+    envs = [BatchedNavGym(B, mp, seed=3, auto_reset=True) for _ in range(2)]
+    for e in envs:
+        e.reset_from_spawn_pool(np.random.RandomState(7))
+    bounds = envs[1].host_groups(2)
+    act_h = torch.empty(B, 2).pin_memory()
+    obs_h = torch.empty(B, 519).pin_memory()
+    rew_h = torch.empty(B).pin_memory()
+    done_h = torch.empty(B, dtype=torch.uint8).pin_memory()
+    T = 12
+    acts = torch.from_numpy(rng.uniform([0.2, -0.64], [0.5, 0.64], (T, B, 2)).astype(np.float32))
+    want = []
+    for t in range(T):
+        o, r, d, _ = envs[0].step(acts[t].cuda())
+        want.append((o.cpu().clone(), r.cpu().clone(), d.cpu().clone()))
+    act_h.copy_(acts[0])
+    for g in range(2):
+        envs[1].submit_host(g, act_h, obs_h, rew_h, done_h)
+    for t in range(T):
+        for g, (b0, b1) in enumerate(bounds):
+            envs[1].wait_host(g)
+            assert torch.equal(obs_h[b0:b1], want[t][0][b0:b1]), (t, g)
+            assert torch.equal(rew_h[b0:b1], want[t][1][b0:b1]) and torch.equal(done_h[b0:b1], want[t][2][b0:b1])
+            if t + 1 < T:
+                act_h[b0:b1].copy_(acts[t + 1][b0:b1])
+                envs[1].submit_host(g, act_h, obs_h, rew_h, done_h)
