@@ -105,6 +105,7 @@ def cpu_reference_run(steps, warmup, B_cpu=512, seed=0):
     all host cores; the reference itself is Python + absent native deps and cannot run here).
     Bounded sample: B_cpu envs of the same world and action law."""
     from oracle import oracle as orc
+    orc.use_all_cores()
     m, pool = build_world(seed, pool_n=8192)
     rng = np.random.RandomState(seed + 1)
     rows = pool[rng.randint(len(pool), size=B_cpu)]
@@ -163,6 +164,12 @@ def main():
     if a.impl == 'reference':
         if rank != 0:
             return
+        # launchers such as torchrun export OMP_NUM_THREADS=1; the CPU arm uses every host core
+        # (set before libgomp is first loaded: it reads its environment once)
+        ncpu = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+        os.environ['OMP_NUM_THREADS'] = str(ncpu)
+        os.environ['OMP_PROC_BIND'] = 'false'
+        os.environ['OMP_WAIT_POLICY'] = 'active' 
         r = cpu_reference_run(a.steps, a.warmup)
         line = {"impl": "reference", "metric": METRIC, "value": r['value'], "unit": "env-steps/s",
                 "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,

@@ -530,6 +530,15 @@ void nvo_reset_obs_batch(const nvo_params_t *P, int B, const nvo_map_t *maps, co
     }
 }
 
+void nvo_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int nvo_num_threads(void)
 {
 #ifdef _OPENMP

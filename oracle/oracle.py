@@ -288,3 +288,11 @@ class OracleBatch(object):
 
 def num_threads():
     return lib().nvo_num_threads()
+
+
+def use_all_cores():
+    """Run the OpenMP loops on every host core (launchers such as torchrun export
+    OMP_NUM_THREADS=1, which would otherwise throttle the CPU baseline)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    lib().nvo_set_num_threads(int(n))
+    return num_threads()
