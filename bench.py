@@ -161,15 +161,16 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
 
-    if a.impl == 'reference':
-        if rank != 0:
-            return
-        # launchers such as torchrun export OMP_NUM_THREADS=1; the CPU arm uses every host core
+    if a.impl == 'reference' or world == 1:
+        # launchers such as torchrun export OMP_NUM_THREADS=1; the CPU legs use every host core
         # (set before libgomp is first loaded: it reads its environment once)
         ncpu = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
         os.environ['OMP_NUM_THREADS'] = str(ncpu)
         os.environ['OMP_PROC_BIND'] = 'false'
-        os.environ['OMP_WAIT_POLICY'] = 'active' 
+        os.environ['OMP_WAIT_POLICY'] = 'active'
+    if a.impl == 'reference':
+        if rank != 0:
+            return
         r = cpu_reference_run(a.steps, a.warmup)
         line = {"impl": "reference", "metric": METRIC, "value": r['value'], "unit": "env-steps/s",
                 "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
