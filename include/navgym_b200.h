@@ -54,7 +54,8 @@ typedef struct {
  *   segs    f32 [num_envs][max_seg][4] (ax,ay,bx,by)  nseg i32 [num_envs]
  *   noise   f32 [num_envs][2][512] additive, slot 0 = the step's scan, slot 1 = the crash
  *           re-scan (parity traces); NULL -> Philox N(0, noise_std[env]) (production)
- *   obs     f32 [num_envs][obs_stride], first 512+7 columns written per row
+ *   obs     f32 [num_envs][obs_stride], first S*512+7 columns written per row (S = num_scan_stack;
+ *           the S-1 older scans are carried over from the row's previous contents)
  *   tail64  f64 [num_envs][7]   (the 7 trailing observation fields in float64, env.py:455)
  *   hits    i16 [num_envs][512][2] hit cell minus origin cell of the step's first scan, or
  *           NAVGYM_HIT_NONE; NULL = not recorded
@@ -78,7 +79,7 @@ typedef struct {
     uint64_t seed;
     int64_t env_offset;      /* global index of env 0 (multi-GPU sharding) */
     int32_t sched_phase;     /* which third of `sched` is current: step counter mod 3 */
-    int32_t _pad1;
+    int32_t num_scan_stack;  /* S of env.py:257-279 (0 or 1 = no stacking): obs row = S*512 + 7 */
     int32_t env_begin;       /* this launch steps environments [env_begin, env_begin + env_count) */
     int32_t env_count;       /* 0 = through num_envs; num_envs stays the SoA stride of all buffers */
     float noise_lo, noise_hi; /* scan_noise_std range resampled at auto-reset */
@@ -149,6 +150,7 @@ typedef struct {
     double dist_thresh;
     double r_scale, r_success, r_crash, r_progress, r_forward, r_rotation, r_discomfort;
     int32_t count, obs_stride;
+    int32_t num_scan_stack, _pad;
     const float *obs, *goals;
     const float *thr, *dthr;   /* [512] */
     float *reward;

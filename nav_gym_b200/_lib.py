@@ -70,7 +70,7 @@ class StepArgs(C.Structure):
         ('num_envs', C.c_int32), ('obs_stride', C.c_int32), ('auto_reset', C.c_int32),
         ('max_episode_steps', C.c_int32), ('num_maps', C.c_int32), ('resample_map', C.c_int32),
         ('seed', C.c_uint64), ('env_offset', C.c_int64),
-        ('sched_phase', C.c_int32), ('_pad1', C.c_int32),
+        ('sched_phase', C.c_int32), ('num_scan_stack', C.c_int32),
         ('env_begin', C.c_int32), ('env_count', C.c_int32),
         ('noise_lo', C.c_float), ('noise_hi', C.c_float),
         ('maps', _P), ('edt_pool', _P), ('spawn_pool', _P), ('map_id', _P),
@@ -89,6 +89,7 @@ class HerArgs(C.Structure):
                 ('r_crash', C.c_double), ('r_progress', C.c_double), ('r_forward', C.c_double),
                 ('r_rotation', C.c_double), ('r_discomfort', C.c_double),
                 ('count', C.c_int32), ('obs_stride', C.c_int32),
+                ('num_scan_stack', C.c_int32), ('_pad', C.c_int32),
                 ('obs', _P), ('goals', _P), ('thr', _P), ('dthr', _P), ('reward', _P),
                 ('done', _P), ('is_success', _P), ('is_crash', _P), ('distance', _P)]
 

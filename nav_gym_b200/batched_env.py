@@ -116,7 +116,7 @@ class BatchedNavGym(object):
                  max_disc=0, max_seg=0, seed=0, env_offset=0, auto_reset=False,
                  max_episode_steps=0, resample_map=False, scan_noise_std_range=(0.0, 0.05),
                  cell_rule='numpy1', early_stop=True, record_hits=False, longest_first=True,
-                 **reward):
+                 num_scan_stack=1, **reward):
         self.lib = _lib.require_device()
         self.device = torch.device(device)
         self.B = B = int(num_envs)
@@ -134,7 +134,9 @@ class BatchedNavGym(object):
         mid = np.zeros(B, np.int32) if map_id is None else np.asarray(map_id, np.int32)
         self.map_id = torch.from_numpy(mid).to(dev)
         self.noise_std = torch.zeros(B, dtype=f32, device=dev)
-        self.obs = torch.zeros(B, OBS_DIM, dtype=f32, device=dev)
+        self.num_scan_stack = S = max(int(num_scan_stack), 1)
+        self.obs_dim = S * NB + 7
+        self.obs = torch.zeros(B, self.obs_dim, dtype=f32, device=dev)
         self.tail64 = torch.zeros(B, 7, dtype=f64, device=dev)
         self.reward = torch.zeros(B, dtype=f32, device=dev)
         self.done = torch.zeros(B, dtype=u8, device=dev)
@@ -162,7 +164,7 @@ class BatchedNavGym(object):
         a.range_max, a.t_stop = KetiRobot.range_max, t_stop
         a.cell_rule = {'numpy1': 0, 'numpy2': 1}[cell_rule]
         a.max_disc, a.max_seg = self.max_disc, self.max_seg
-        a.num_envs, a.obs_stride = B, OBS_DIM
+        a.num_envs, a.obs_stride, a.num_scan_stack = B, self.obs_dim, S
         a.auto_reset, a.max_episode_steps = int(auto_reset), int(max_episode_steps)
         a.num_maps, a.resample_map = self.pool.num_maps, int(resample_map)
         a.seed, a.env_offset = int(seed), int(env_offset)
@@ -261,7 +263,7 @@ class BatchedNavGym(object):
         for t in (actions_host, obs_host, reward_host, done_host):
             if not t.is_pinned() or not t.is_contiguous():
                 raise ValueError('step_host needs contiguous pinned host tensors')
-        assert obs_host.dtype == torch.float32 and tuple(obs_host.shape) == (self.B, OBS_DIM)
+        assert obs_host.dtype == torch.float32 and tuple(obs_host.shape) == (self.B, self.obs_dim)
         assert reward_host.dtype == torch.float32 and done_host.dtype == torch.uint8
         assert actions_host.dtype == torch.float32 and actions_host.numel() == 2 * self.B
         if self.peds is not None:
@@ -344,7 +346,7 @@ class BatchedNavGym(object):
                         'reward_crash_factor': 'r_crash', 'reward_progress_factor': 'r_progress',
                         'reward_forward_factor': 'r_forward', 'reward_rotation_factor': 'r_rotation',
                         'reward_discomfort_factor': 'r_discomfort'}[k], v)
-        h.count, h.obs_stride = n, obs.stride(0)
+        h.count, h.obs_stride, h.num_scan_stack = n, obs.stride(0), self.num_scan_stack
         h.obs, h.goals, h.thr, h.dthr = _ptr(obs), _ptr(goals), _ptr(self.thr), _ptr(self.dthr)
         h.reward, h.done, h.is_success = _ptr(out['reward']), _ptr(out['done']), _ptr(out['is_success'])
         h.is_crash, h.distance = _ptr(out['is_crash']), _ptr(out['distance'])

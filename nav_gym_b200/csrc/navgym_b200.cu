@@ -505,6 +505,7 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
             const int nslot = pass == PASS_RESCAN ? 1 : 0;
             const float noise_std = sm.noise_std;
             const int steps = sm.steps, episode = sm.episode;
+            const int SS = a.num_scan_stack > 1 ? a.num_scan_stack : 1;
             constexpr int G = BPL >= 4 ? 4 : BPL;
 #pragma unroll 1
             for (int g = 0; g < BPL / G; g++) {
@@ -521,7 +522,19 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
                         else if (noise_std > 0.0f) v = __fadd_rn(v, noise_std * z[j]);
                     }
                     sm.scan[k] = __float_as_int(v);
-                    orow[k] = v;
+                    if (SS == 1) {
+                        orow[k] = v;
+                    } else {
+                        // _stack_scan (env.py:257-279): [pads = current scan | previous scans,
+                        // oldest first | current scan]; the previous observation row still holds
+                        // them one slot to the right
+                        const int hist = pass == PASS_RESET ? 0 : min(steps, SS - 1);
+                        for (int j = 0; j < SS - 1; j++) {
+                            if (j < SS - 1 - hist) orow[j * NB + k] = v;
+                            else if (pass == PASS_STEP) orow[j * NB + k] = orow[(j + 1) * NB + k];
+                        }
+                        orow[(SS - 1) * NB + k] = v;
+                    }
                     c_any |= v < a.thr[k];
                     d_any |= v < a.dthr[k];
                 }
@@ -634,7 +647,7 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
         case 6: tv = yaw; break;
         }
         if (lane < 7) {
-            orow[NB + lane] = (float)tv;
+            orow[(a.num_scan_stack > 1 ? a.num_scan_stack : 1) * NB + lane] = (float)tv;
             if (a.tail64) a.tail64[(size_t)e * 7 + lane] = tv;
         }
         double nv = 0.0;
@@ -685,7 +698,8 @@ __global__ void __launch_bounds__(256) her_kernel(const navgym_her_args_t a)
     const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (n >= a.count) return;
     const unsigned FULL = 0xffffffffu;
-    const float *o = a.obs + (size_t)n * a.obs_stride;
+    const int SS = a.num_scan_stack > 1 ? a.num_scan_stack : 1;
+    const float *o = a.obs + (size_t)n * a.obs_stride + (size_t)(SS - 1) * NB;  // the newest scan
     bool c_any = false, d_any = false;
     double mn = CUDART_INF;
 #pragma unroll 4
@@ -937,7 +951,7 @@ int navgym_device_count(void)
 int navgym_step_batch(const navgym_step_args_t *args, void *stream)
 {
     if (args->num_envs <= 0) return 0;
-    if (args->obs_stride < OBS_DIM || args->env_begin < 0 || args->env_begin + args->env_count > args->num_envs)
+    if (args->obs_stride < (args->num_scan_stack > 1 ? args->num_scan_stack : 1) * NB + NAVGYM_OBS_TAIL || args->env_begin < 0 || args->env_begin + args->env_count > args->num_envs)
         return (int)cudaErrorInvalidValue;
     launch_step<false>(*args, (cudaStream_t)stream);
     return (int)cudaGetLastError();
@@ -1067,7 +1081,8 @@ int navgym_step_batch_host_wait(navgym_host_pipe_t *p, int group)
 int navgym_reset_obs_batch(const navgym_step_args_t *args, void *stream)
 {
     if (args->num_envs <= 0) return 0;
-    if (args->obs_stride < OBS_DIM) return (int)cudaErrorInvalidValue;
+    if (args->obs_stride < (args->num_scan_stack > 1 ? args->num_scan_stack : 1) * NB + NAVGYM_OBS_TAIL)
+        return (int)cudaErrorInvalidValue;
     launch_step<true>(*args, (cudaStream_t)stream);
     return (int)cudaGetLastError();
 }
@@ -1075,7 +1090,8 @@ int navgym_reset_obs_batch(const navgym_step_args_t *args, void *stream)
 int navgym_compute_rewards(const navgym_her_args_t *args, void *stream)
 {
     if (args->count <= 0) return 0;
-    if (args->obs_stride < OBS_DIM) return (int)cudaErrorInvalidValue;
+    if (args->obs_stride < (args->num_scan_stack > 1 ? args->num_scan_stack : 1) * NB + NAVGYM_OBS_TAIL)
+        return (int)cudaErrorInvalidValue;
     her_kernel<<<(args->count + 7) / 8, 256, 0, (cudaStream_t)stream>>>(*args);
     g_launches++;
     return (int)cudaGetLastError();

@@ -113,8 +113,6 @@ class NavGymEnv(gym.Env, EzPickle):
                           reward_discomfort_factor, env_param_range, device=device)
         if robot_type != 'keti':
             raise NotImplementedError
-        if num_scan_stack != 1:
-            raise NotImplementedError('num_scan_stack > 1 (env.py:257-279) is not built yet')
         self.robot_type, self.time_step = robot_type, time_step
         self.min_turning_radius, self.distance_threshold = min_turning_radius, distance_threshold
         self.num_scan_stack = num_scan_stack
@@ -206,7 +204,8 @@ class NavGymEnv(gym.Env, EzPickle):
         self._sim = BatchedNavGym(1, mp, device=self.device, time_step=self.time_step,
                                   distance_threshold=self.distance_threshold,
                                   min_turning_radius=self.min_turning_radius, early_stop=True,
-                                  seed=int(np.random.randint(2 ** 31)), **self._reward_kwargs())
+                                  seed=int(np.random.randint(2 ** 31)),
+                                  num_scan_stack=self.num_scan_stack, **self._reward_kwargs())
         self._sim.set_state([[sx, sy]], [[gx, gy]], [th],
                             noise_std=[self.env_param['scan_noise_std']])
         if n_h:
@@ -219,7 +218,7 @@ class NavGymEnv(gym.Env, EzPickle):
 
     def _obs(self):
         sim = self._sim
-        scan = sim.obs[0, :KetiRobot.n_angles].double().cpu().numpy()
+        scan = sim.obs[0, :self.num_scan_stack * KetiRobot.n_angles].double().cpu().numpy()
         tail = sim.tail64[0].cpu().numpy()
         st = sim.state[:, 0].cpu().numpy()
         self.robot.px, self.robot.py, self.robot.theta = float(st[0]), float(st[1]), float(st[2])

@@ -32,6 +32,8 @@ TRACES = [
     ('outdoor_n12_seek', 14, 0.0, [12, 12], 'seek', 400),
     ('indoor_n5_seek', 15, 1.0, [5, 5], 'seek', 400),
     ('outdoor_n15_random', 16, 0.0, [15, 15], 'random', 150),
+    # num_scan_stack = 3 (env.py:257-279): [pads | previous scans | current scan]
+    ('indoor_n3_stack3', 17, 1.0, [3, 3], 'random', 150, 3),
 ]
 
 
@@ -64,7 +66,7 @@ def _pack(recs, key, width):
     return out, cnt
 
 
-def run_trace(name, seed, indoor_ratio, nh, mode, max_steps):
+def run_trace(name, seed, indoor_ratio, nh, mode, max_steps, stack=1):
     np.random.seed(seed)
     import torch
     torch.manual_seed(seed)
@@ -72,7 +74,8 @@ def run_trace(name, seed, indoor_ratio, nh, mode, max_steps):
     epr = dict(num_humans=(nh, 'int'), corridor_width=([3, 4], 'int'), iterations=([80, 150], 'int'),
                obstacle_number=([10, 10], 'int'), obstacle_width=([0.3, 1.0], 'float'),
                scan_noise_std=([0., 0.05], 'float'))
-    env = rh.make_env(indoor_ratio=indoor_ratio, env_param_range=epr)
+    env = rh.make_env(indoor_ratio=indoor_ratio, env_param_range=epr, num_scan_stack=stack)
+    NS = NB * stack
     rh.REC.clear()
     obs0 = env.reset()
     first, _ = _robot_scans(False)
@@ -83,6 +86,7 @@ def run_trace(name, seed, indoor_ratio, nh, mode, max_steps):
         noise_std=np.float64(env.env_param['scan_noise_std']),
         start=np.array([env.robot.px, env.robot.py, env.robot.theta], np.float64),
         goal=np.array([env.robot.gx, env.robot.gy], np.float64),
+        num_scan_stack=np.int32(stack),
         obs0=obs0['observation'].astype(np.float64), hits0=first['hits'].astype(np.int16),
         cell0=first['ins'][0, :2].astype(np.int32),
         discs0=first['discs'], segs0=first['segs'],
@@ -99,21 +103,24 @@ def run_trace(name, seed, indoor_ratio, nh, mode, max_steps):
         recs2.append(s2 if s2 is not None else dict(discs=np.zeros((0, 3)), segs=np.zeros((0, 4)),
                                                     noise=None))
         rows.append(dict(
-            action=a, scan=obs['observation'][:NB].astype(np.float32), tail=obs['observation'][NB:],
+            action=a, scan=obs['observation'][NS - NB:NS].astype(np.float32), tail=obs['observation'][NS:],
+            scan_stack=obs['observation'][:NS].astype(np.float32),
             achieved=obs['achieved_goal'], desired=obs['desired_goal'], reward=float(reward),
             done=bool(done), is_success=float(info['is_success']), is_crash=float(info['is_crash']),
             distance=float(info['distance']), hits=s1['hits'].astype(np.int16),
             cell=s1['ins'][0, :2].astype(np.int32),
             state=np.array([env.robot.px, env.robot.py, env.robot.theta]),
             steps=env.steps_since_reset))
-        assert np.array_equal(obs['observation'][:NB].astype(np.float32).astype(np.float64),
-                              obs['observation'][:NB])
+        assert np.array_equal(obs['observation'][:NS].astype(np.float32).astype(np.float64),
+                              obs['observation'][:NS])
         if done:
             break
     T = len(rows)
     G['actions'] = np.array([r['action'] for r in rows], np.float64)
     G['scan'] = np.array([r['scan'] for r in rows], np.float32)
     G['tail'] = np.array([r['tail'] for r in rows], np.float64)
+    if stack > 1:
+        G['scan_stack'] = np.array([r['scan_stack'] for r in rows], np.float32)
     G['achieved'] = np.array([r['achieved'] for r in rows], np.float64)
     G['desired'] = np.array([r['desired'] for r in rows], np.float64)
     G['reward'] = np.array([r['reward'] for r in rows], np.float64)

@@ -359,6 +359,7 @@ typedef struct {
     float t_stop;               /* cells; reference marches to W*H (env.py:337) */
     int32_t cell_rule;
     int32_t max_disc, max_seg;
+    int32_t num_scan_stack;     /* S of env.py:257-279; obs row = S*512 + 7 */
 } nvo_params_t;
 
 static void scan_once(const nvo_params_t *P, const nvo_map_t *m, const float *edt,
@@ -392,6 +393,28 @@ static void scan_once(const nvo_params_t *P, const nvo_map_t *m, const float *ed
     }
 }
 
+/* _stack_scan (env.py:257-279): [current scan x (S-1-n) | the n previous scans, oldest first |
+ * current scan]; hist holds the scans of the last n <= S-1 returned observations. */
+static void stack_row(float *o, const float *scan, int S, const float *hist, int n)
+{
+    int idx = 0;
+    for (int p = 0; p < S - 1 - n; p++) memcpy(o + (size_t)NVO_NB * idx++, scan, sizeof(float) * NVO_NB);
+    for (int h = 0; h < n; h++) memcpy(o + (size_t)NVO_NB * idx++, hist + (size_t)h * NVO_NB, sizeof(float) * NVO_NB);
+    memcpy(o + (size_t)NVO_NB * (S - 1), scan, sizeof(float) * NVO_NB);
+}
+
+/* prev_obs_queue.append(obs), a deque(maxlen = S-1) (env.py:727, 738) */
+static void push_hist(float *hist, int32_t *n, int S, const float *scan)
+{
+    if (S <= 1) return;
+    if (*n == S - 1) {
+        memmove(hist, hist + NVO_NB, sizeof(float) * NVO_NB * (size_t)(S - 2));
+        *n -= 1;
+    }
+    memcpy(hist + (size_t)NVO_NB * *n, scan, sizeof(float) * NVO_NB);
+    *n += 1;
+}
+
 /* One lockstep NavGymEnv.step over B environments.
  *  actions f32[B,2]; discs f32[B,max_disc,3], ndisc i32[B]; segs f32[B,max_seg,4], nseg;
  *  noise f32[B,2,512] or NULL (slot 0: the step's scan, slot 1: the crash re-scan);
@@ -403,8 +426,9 @@ void nvo_step_batch(const nvo_params_t *P, int B, const nvo_map_t *maps, const f
                     const float *discs, const int32_t *ndisc, const float *segs,
                     const int32_t *nseg, const float *noise, float *obs, double *tail64,
                     double *reward, uint8_t *done, uint8_t *is_success, uint8_t *is_crash,
-                    double *distance, int16_t *hits)
+                    double *distance, int16_t *hits, float *hist, int32_t *nhist)
 {
+    const int SS = P->num_scan_stack > 1 ? P->num_scan_stack : 1;
 #pragma omp parallel for schedule(dynamic, 16)
     for (int e = 0; e < B; e++) {
         double *S = state;
@@ -483,11 +507,13 @@ void nvo_step_batch(const nvo_params_t *P, int B, const nvo_map_t *maps, const f
             yaw = atan2(sin(thn), cos(thn));
             opx = px; opy = py;
         }
-        float *o = obs + (size_t)e * (NVO_NB + 7);
-        memcpy(o, scan, sizeof(scan));
+        float *o = obs + (size_t)e * (SS * NVO_NB + 7);
+        float *he = hist ? hist + (size_t)e * (SS - 1) * NVO_NB : 0;
+        stack_row(o, scan, SS, he, nhist ? nhist[e] : 0);
+        if (nhist) push_hist(he, &nhist[e], SS, scan);
         double *t7 = tail64 + (size_t)e * 7;
         t7[0] = ppx; t7[1] = ppy; t7[2] = opx; t7[3] = opy; t7[4] = pv; t7[5] = pw; t7[6] = yaw;
-        for (int i = 0; i < 7; i++) o[NVO_NB + i] = (float)t7[i];
+        for (int i = 0; i < 7; i++) o[SS * NVO_NB + i] = (float)t7[i];
         /* env.py:725-727 */
         ST(S_PV) = (double)actions[2 * e];
         ST(S_PW) = (double)actions[2 * e + 1];
@@ -503,8 +529,9 @@ void nvo_reset_obs_batch(const nvo_params_t *P, int B, const nvo_map_t *maps, co
                          const int32_t *map_id, const double *lin, double *state,
                          int32_t *steps, const float *discs, const int32_t *ndisc,
                          const float *segs, const int32_t *nseg, const float *noise,
-                         float *obs, double *tail64, int16_t *hits)
+                         float *obs, double *tail64, int16_t *hits, float *hist, int32_t *nhist)
 {
+    const int SS = P->num_scan_stack > 1 ? P->num_scan_stack : 1;
 #pragma omp parallel for schedule(dynamic, 16)
     for (int e = 0; e < B; e++) {
         double *S = state;
@@ -520,11 +547,14 @@ void nvo_reset_obs_batch(const nvo_params_t *P, int B, const nvo_map_t *maps, co
                   noise ? noise + (size_t)e * 2 * NVO_NB : 0, scan,
                   hits ? hits + (size_t)e * 2 * NVO_NB : 0);
         double yaw = atan2(sin(th), cos(th));
-        float *o = obs + (size_t)e * (NVO_NB + 7);
-        memcpy(o, scan, sizeof(scan));
+        float *o = obs + (size_t)e * (SS * NVO_NB + 7);
+        float *he = hist ? hist + (size_t)e * (SS - 1) * NVO_NB : 0;
+        if (nhist) nhist[e] = 0;
+        stack_row(o, scan, SS, he, 0);
+        if (nhist) push_hist(he, &nhist[e], SS, scan);
         double *t7 = tail64 + (size_t)e * 7;
         t7[0] = px; t7[1] = py; t7[2] = px; t7[3] = py; t7[4] = 0; t7[5] = 0; t7[6] = yaw;
-        for (int i = 0; i < 7; i++) o[NVO_NB + i] = (float)t7[i];
+        for (int i = 0; i < 7; i++) o[SS * NVO_NB + i] = (float)t7[i];
         ST(S_PV) = 0; ST(S_PW) = 0; ST(S_PPX) = px; ST(S_PPY) = py; ST(S_PYAW) = yaw;
 #undef ST
     }

@@ -37,7 +37,8 @@ class ParamsT(C.Structure):
                 ('r_scale', C.c_double), ('r_success', C.c_double), ('r_crash', C.c_double),
                 ('r_progress', C.c_double), ('r_forward', C.c_double), ('r_rotation', C.c_double),
                 ('r_discomfort', C.c_double), ('range_max', C.c_float), ('t_stop', C.c_float),
-                ('cell_rule', C.c_int32), ('max_disc', C.c_int32), ('max_seg', C.c_int32)]
+                ('cell_rule', C.c_int32), ('max_disc', C.c_int32), ('max_seg', C.c_int32),
+                ('num_scan_stack', C.c_int32)]
 
 
 _lib = None
@@ -196,7 +197,7 @@ def legs_to_discs(pose, dist_travelled):
 def default_params(**kw):
     p = dict(dt=0.2, dist_thresh=0.5, min_turn_radius=0.0, r_scale=15.0, r_success=1.0,
              r_crash=1.0, r_progress=0.001, r_forward=0.0, r_rotation=0.005, r_discomfort=0.01,
-             range_max=RANGE_MAX, t_stop=1e12, cell_rule=0, max_disc=0, max_seg=0)
+             range_max=RANGE_MAX, t_stop=1e12, cell_rule=0, max_disc=0, max_seg=0, num_scan_stack=1)
     p.update(kw)
     return p
 
@@ -229,7 +230,10 @@ class OracleBatch(object):
         self.state[S_TH] = theta
         self.state[S_GX], self.state[S_GY] = np.asarray(goal, np.float64).T
         self.steps = np.zeros(B, np.int32)
-        self.obs = np.zeros((B, OBS_DIM), np.float32)
+        S = self.S = max(int(self.params['num_scan_stack']), 1)
+        self.obs = np.zeros((B, S * NB + 7), np.float32)
+        self.hist = np.zeros((B, max(S - 1, 1), NB), np.float32)
+        self.nhist = np.zeros(B, np.int32)
         self.tail64 = np.zeros((B, 7), np.float64)
         self.reward = np.zeros(B, np.float64)
         self.done = np.zeros(B, np.uint8)
@@ -243,7 +247,7 @@ class OracleBatch(object):
         return ParamsT(p['dt'], p['dist_thresh'], p['min_turn_radius'], p['r_scale'], p['r_success'],
                        p['r_crash'], p['r_progress'], p['r_forward'], p['r_rotation'],
                        p['r_discomfort'], p['range_max'], p['t_stop'], p['cell_rule'],
-                       p['max_disc'], p['max_seg'])
+                       p['max_disc'], p['max_seg'], p['num_scan_stack'])
 
     def _geom(self, discs, ndisc, segs, nseg):
         md, ms = self.params['max_disc'], self.params['max_seg']
@@ -264,7 +268,8 @@ class OracleBatch(object):
                                   _p(self.map_id), _p(self.lin), _p(self.state), _p(self.steps),
                                   _p(discs), _p(ndisc), _p(segs), _p(nseg), _p(noise),
                                   _p(self.obs), _p(self.tail64),
-                                  _p(self.hits) if want_hits else None)
+                                  _p(self.hits) if want_hits else None,
+                                  _p(self.hist) if self.S > 1 else None, _p(self.nhist) if self.S > 1 else None)
         return self.obs
 
     def step(self, actions, discs=None, ndisc=None, segs=None, nseg=None, noise=None,
@@ -279,7 +284,8 @@ class OracleBatch(object):
                              _p(self.steps), _p(actions), _p(discs), _p(ndisc), _p(segs), _p(nseg),
                              _p(noise), _p(self.obs), _p(self.tail64), _p(self.reward),
                              _p(self.done), _p(self.is_success), _p(self.is_crash),
-                             _p(self.distance), _p(self.hits) if want_hits else None)
+                             _p(self.distance), _p(self.hits) if want_hits else None,
+                             _p(self.hist) if self.S > 1 else None, _p(self.nhist) if self.S > 1 else None)
         return self.obs, self.reward, self.done
 
     def set_threads(self, n):

@@ -42,14 +42,16 @@ def replay(G, stepper, pose_tol=1e-9, reward_tol=1e-9, check_hits=True):
     done, is_success, is_crash, distance, hits, state (rows px,py,th first), steps.
     Integer/flag outputs and the float32 scan are compared bit-exactly."""
     md, ms = geom_dims(G)
+    S = int(G['num_scan_stack']) if 'num_scan_stack' in G else 1
+    NS = S * NB
     d0, nd0 = pad(G['discs0'], md, 3)
     s0, ns0 = pad(G['segs0'], ms, 4)
     n0 = np.zeros((1, 2, NB), np.float32)
     n0[0, 0] = G['noise0']
     stepper.reset_obs(d0, nd0, s0, ns0, n0)
     obs = np.asarray(stepper.obs)[0]
-    assert np.array_equal(obs[:NB], G['obs0'][:NB].astype(np.float32)), 'first scan'
-    assert np.allclose(np.asarray(stepper.tail64)[0], G['obs0'][NB:], rtol=0, atol=pose_tol)
+    assert np.array_equal(obs[:NS], G['obs0'][:NS].astype(np.float32)), 'first scan (stack)'
+    assert np.allclose(np.asarray(stepper.tail64)[0], G['obs0'][NS:], rtol=0, atol=pose_tol)
     if check_hits:
         assert np.array_equal(_mask_hits(np.asarray(stepper.hits)[0], stepper), _mask_hits(G['hits0'], stepper))
     T = len(G['actions'])
@@ -59,9 +61,11 @@ def replay(G, stepper, pose_tol=1e-9, reward_tol=1e-9, check_hits=True):
         stepper.step(G['actions'][t][None].astype(np.float32), dd, nd, ss, ns, G['noise'][t][None])
         obs = np.asarray(stepper.obs)[0]
         tag = 'step %d' % t
-        assert np.array_equal(obs[:NB], G['scan'][t]), tag + ' scan'
+        assert np.array_equal(obs[NS - NB:NS], G['scan'][t]), tag + ' scan'
+        if S > 1:
+            assert np.array_equal(obs[:NS], G['scan_stack'][t]), tag + ' scan stack'
         assert np.allclose(np.asarray(stepper.tail64)[0], G['tail'][t], rtol=0, atol=pose_tol), tag
-        assert np.allclose(obs[NB:], G['tail'][t].astype(np.float32), rtol=1e-6, atol=1e-6), tag
+        assert np.allclose(obs[NS:], G['tail'][t].astype(np.float32), rtol=1e-6, atol=1e-6), tag
         assert abs(float(np.asarray(stepper.reward)[0]) - G['reward'][t]) <= reward_tol, tag + ' reward'
         assert int(np.asarray(stepper.done)[0]) == int(G['done'][t]), tag + ' done'
         assert int(np.asarray(stepper.is_success)[0]) == int(G['is_success'][t]), tag

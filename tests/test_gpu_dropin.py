@@ -15,9 +15,10 @@ def test_her_kernel_reproduces_reference_rewards(name):
     device == what the reference's own compute_reward / compute_done / compute_info returned."""
     from nav_gym_b200.batched_env import BatchedNavGym
     G = gu.load(name)
-    env = BatchedNavGym(1, [gu.map_info(G)], device='cuda:0')
+    S = int(G['num_scan_stack']) if 'num_scan_stack' in G else 1
+    env = BatchedNavGym(1, [gu.map_info(G)], device='cuda:0', num_scan_stack=S)
     assert np.array_equal(env.scan_threshold, G['thr'])
-    obs = np.concatenate([G['scan'], G['tail'].astype(np.float32)], axis=1)
+    obs = np.concatenate([G['scan_stack'] if S > 1 else G['scan'], G['tail'].astype(np.float32)], axis=1)
     # on a crash the reference returns the re-scanned observation, whose reward terms were
     # computed on the crashed one: compare the steps whose returned obs is the scored obs
     keep = G['is_crash'] == 0
@@ -124,3 +125,25 @@ def test_pedestrian_kernel():
     env2.attach_pedestrians(peds2)
     obs = env2.reset().cpu().numpy()
     assert np.all(obs[:, 256] < 1.5) and np.all(obs[:, 256] > 1.2)   # beam 256 looks forward
+
+
+def test_gym_make_scan_stack():
+    """num_scan_stack = 3 through the drop-in: observation = [3 x 512 scans | 7], newest last,
+    missing history padded with the current scan (env.py:257-279)."""
+    import nav_gym_b200  # noqa: F401
+    from nav_gym_b200 import gym_shim
+    gym = gym_shim.install()
+    np.random.seed(5)
+    env = gym.make('NavGym-v0', num_scan_stack=3)
+    assert env.observation_space['observation'].shape == (3 * 512 + 7,)
+    o0 = env.reset()['observation']
+    assert o0.shape == (1543,)
+    s0 = o0[1024:1536]
+    assert np.array_equal(o0[:512], s0) and np.array_equal(o0[512:1024], s0)
+    o1 = env.step(np.array([0.3, 0.1]))[0]['observation']
+    s1 = o1[1024:1536]
+    assert np.array_equal(o1[:512], s1) and np.array_equal(o1[512:1024], s0)
+    o2, r, d, info = env.step(np.array([0.3, -0.1]))
+    o2 = o2['observation']
+    if not info['is_crash']:
+        assert np.array_equal(o2[:512], s0) and np.array_equal(o2[512:1024], s1)
