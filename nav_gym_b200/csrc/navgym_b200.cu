@@ -181,7 +181,9 @@ struct EnvSmem {
     // loop runs with a small register footprint
     double px, py, th, gx, gy, ppx, ppy, pyaw, pv, pw, act_v, act_w;
     int map, steps, episode, next_pass;
-    int next_beam;         // next undealt beam of the scan in flight
+    int next_beam;         // next undealt entry of the survivor list
+    int n_alive;           // beams still marching after the head phase
+    short alive[NB];       // their indices
     float noise_std;
     // per-pass scan setup
     float lx, ly, lt, res32, max_range, t_stop;
@@ -230,6 +232,9 @@ __device__ __forceinline__ void normal4(uint64_t seed, uint32_t env, uint32_t ep
 // gathers per lane are in flight.  The three scans a step may need (the step's scan, the
 // crash re-scan env.py:718, the auto-reset first scan) run through ONE copy of the scan code
 // inside a CTA-uniform pass loop.
+#ifndef NAVGYM_HEAD_STEPS
+#define NAVGYM_HEAD_STEPS 4  // samples every beam marches in the lockstep head phase
+#endif
 #ifndef NAVGYM_THREADS_PER_SM
 #define NAVGYM_THREADS_PER_SM 1024  // resident threads the register budget is tuned for
 #endif
@@ -349,26 +354,23 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
             sm.max_range = (float)((double)m.W * (double)m.H);
             sm.t_stop = fminf(fminf(a.t_stop, sm.max_range), 8.0e6f);
             sm.next_beam = TPB * MARCH_SLOTS;
+            sm.n_alive = 0;
         }
         if (WPE > 1) __syncthreads(); else __syncwarp();
         const float lx = sm.lx, ly = sm.ly, lt = sm.lt;
         PROF_MARK(1);
-        // ---- beam directions (env.py:388-390, 420-424)
-#pragma unroll 2
-        for (int i = 0; i < BPL; i++) {
-            const int k = BEAM(i);
-            const float h = (float)__dadd_rn(a.lin[k], (double)lt);
-            double sd, cd;
-            dir_sincos((double)h, sd, cd);
-            sm.dir[k] = make_float2((float)cd, (float)sd);
-        }
-        if (WPE > 1) __syncthreads(); else __syncwarp();  // any lane may be dealt any beam
-        PROF_MARK(2);
-        // ---- occupancy-grid march (env.py:425-426), MARCH_SLOTS beams in flight per lane.
-        // The loop only finds each beam's hit cell (packed into sm.scan); ranges are computed
-        // afterwards with all lanes active.  Every beam of a scan starts on the origin cell,
-        // so that first sample (t = 0) is taken once per environment: either the origin is
-        // occupied (all beams end there) or all beams advance by the same first step.
+        // ---- occupancy-grid march (env.py:425-426).
+        // Every beam of a scan starts on the origin cell, so that first sample (t = 0) is taken
+        // once per environment: either the origin is occupied (all beams end there) or all
+        // beams advance by the same first step.  The march then runs in two phases:
+        //  head: every thread marches its own beams NAVGYM_HEAD_STEPS samples, HB beams at a
+        //        time in lockstep — almost every beam is still alive that early, and the HB
+        //        independent EDT gathers per thread hide the L2 latency by ILP;
+        //  tail: the surviving beams are compacted into a list and dealt out dynamically (a
+        //        lane takes the next survivor whenever its beam ends), so lanes stay busy on
+        //        the long-tailed remainder instead of idling until the slowest beam ends.
+        // The loops only find each beam's hit cell (packed into sm.scan); ranges are computed
+        // afterwards with all lanes active.
         {
             const int W = sm.W, H = sm.H, ci = sm.ci, cj = sm.cj;
             const float x0 = (float)ci, y0 = (float)cj;
@@ -377,62 +379,115 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
             asm volatile("" : "+l"(dist));  // keep base + offset folded into one register pair
             const float d0 = __ldg(dist + cj * W + ci);   // origin cell is clipped into the map
             const float t1 = fmaxf(__fmul_rn(d0, 0.999f), 1.0f);  // == 0.0f + first step
-            const bool origin_hit = d0 <= 0.0f, first_live = t1 < t_stop;
-            // Beams are dealt out dynamically: slot s of thread tid starts on beam s * TPB + tid
-            // and, whenever its beam ends, takes the next undealt beam of the environment from
-            // a shared counter.  Beams go out in increasing order, so at any moment the CTA
-            // works on a narrow window of neighbouring beams (shared sectors) while every lane
-            // stays busy until the scan runs out of beams.
-            int kb[MARCH_SLOTS];  // the slot's current beam, -1 = none left
-            float t[MARCH_SLOTS], dx[MARCH_SLOTS], dy[MARCH_SLOTS];
+            const bool degenerate = (d0 <= 0.0f) | !(t1 < t_stop);
+            constexpr int HB = BPL >= 4 ? 4 : BPL;   // beams in flight per thread in the head phase
+#pragma unroll 1
+            for (int r = 0; r < BPL / HB; r++) {
+                float th_[HB], dxh[HB], dyh[HB];
+                // beam directions (env.py:388-390, 420-424)
 #pragma unroll
-            for (int s = 0; s < MARCH_SLOTS; s++) {
-                kb[s] = s * TPB + tid;
-                t[s] = t1;
-                const float2 dd = sm.dir[kb[s]];
-                dx[s] = dd.x;
-                dy[s] = dd.y;
+                for (int j = 0; j < HB; j++) {
+                    const int k = BEAM(r * HB + j);
+                    const float h = (float)__dadd_rn(a.lin[k], (double)lt);
+                    double sd, cd;
+                    dir_sincos((double)h, sd, cd);
+                    dxh[j] = (float)cd;
+                    dyh[j] = (float)sd;
+                    sm.dir[k] = make_float2(dxh[j], dyh[j]);
+                    th_[j] = t1;
+                    if (degenerate) { sm.scan[k] = d0 <= 0.0f ? (cj << 16 | ci) : -1; th_[j] = -1.0f; }
+                }
+#pragma unroll 1
+                for (int st = 0; st < NAVGYM_HEAD_STEPS; st++) {
+                    float dv[HB];
+                    int cx[HB], cy[HB];
+                    bool inb[HB];
+#pragma unroll
+                    for (int j = 0; j < HB; j++) {
+                        cx[j] = __float2int_rz(__fmaf_rn(dxh[j], th_[j], x0));
+                        cy[j] = __float2int_rz(__fmaf_rn(dyh[j], th_[j], y0));
+                        inb[j] = ((unsigned)cx[j] < (unsigned)W) & ((unsigned)cy[j] < (unsigned)H);
+                        const unsigned idx = (inb[j] & (th_[j] >= 0.0f)) ? (unsigned)(cy[j] * W + cx[j]) : 0u;
+                        dv[j] = __ldg(dist + idx);
+                    }
+#pragma unroll
+                    for (int j = 0; j < HB; j++) {
+                        const bool alive = th_[j] >= 0.0f;
+                        const bool hit = inb[j] & (dv[j] <= 0.0f);
+                        const float tn = __fadd_rn(th_[j], fmaxf(__fmul_rn(dv[j], 0.999f), 1.0f));
+                        const bool fin = !inb[j] | hit | !(tn < t_stop);
+                        if (alive & fin) sm.scan[BEAM(r * HB + j)] = hit ? (cy[j] << 16 | cx[j]) : -1;
+                        th_[j] = (alive & !fin) ? tn : -1.0f;
+                    }
+                }
+                // survivors: park t in the scan slot and append the beam to the compact list
+#pragma unroll
+                for (int j = 0; j < HB; j++) {
+                    const int k = BEAM(r * HB + j);
+                    const bool alive = th_[j] >= 0.0f;
+                    if (alive) sm.scan[k] = __float_as_int(th_[j]);
+                    const unsigned mk = __ballot_sync(FULL, alive);
+                    int base = 0;
+                    if (lane == 0 && mk) base = atomicAdd(&sm.n_alive, __popc(mk));
+                    base = __shfl_sync(FULL, base, 0);
+                    if (alive) sm.alive[base + __popc(mk & ((1u << lane) - 1u))] = (short)k;
+                }
             }
-            if (origin_hit | !first_live) {
+            if (WPE > 1) __syncthreads(); else __syncwarp();  // any lane may be dealt any survivor
+            PROF_MARK(2);
+            {
+                const int n_alive = sm.n_alive;
+                int kb[MARCH_SLOTS];  // the slot's current beam, -1 = none left
+                float t[MARCH_SLOTS], dx[MARCH_SLOTS], dy[MARCH_SLOTS];
 #pragma unroll
-                for (int i = 0; i < BPL; i++)
-                    sm.scan[BEAM(i)] = origin_hit ? (cj << 16 | ci) : -1;
-            } else {
-                for (;;) {
-                    float d[MARCH_SLOTS];
-                    int cx[MARCH_SLOTS], cy[MARCH_SLOTS];
-                    bool inb[MARCH_SLOTS];
+                for (int s = 0; s < MARCH_SLOTS; s++) {
+                    const int i = s * TPB + tid;
+                    kb[s] = i < n_alive ? (int)sm.alive[i] : -1;
+                    const int kk = kb[s] >= 0 ? kb[s] : 0;
+                    t[s] = __int_as_float(sm.scan[kk]);
+                    const float2 dd = sm.dir[kk];
+                    dx[s] = dd.x;
+                    dy[s] = dd.y;
+                }
+                if (n_alive > 0) {
+                    for (;;) {
+                        float d[MARCH_SLOTS];
+                        int cx[MARCH_SLOTS], cy[MARCH_SLOTS];
+                        bool inb[MARCH_SLOTS];
 #pragma unroll
-                    for (int s = 0; s < MARCH_SLOTS; s++) {
-                        cx[s] = __float2int_rz(__fmaf_rn(dx[s], t[s], x0));
-                        cy[s] = __float2int_rz(__fmaf_rn(dy[s], t[s], y0));
-                        inb[s] = ((unsigned)cx[s] < (unsigned)W) & ((unsigned)cy[s] < (unsigned)H);
-                        const unsigned idx = inb[s] ? (unsigned)(cy[s] * W + cx[s]) : 0u;
-                        d[s] = __ldg(dist + idx);
-                    }
-#pragma unroll
-                    for (int s = 0; s < MARCH_SLOTS; s++) {
-                        const bool hit = inb[s] & (d[s] <= 0.0f);
-                        float tn = __fadd_rn(t[s], fmaxf(__fmul_rn(d[s], 0.999f), 1.0f));
-                        const bool fin = !inb[s] | hit | !(tn < t_stop);
-                        if (fin & (kb[s] >= 0)) {
-                            // absolute hit cell, (y << 16 | x), or -1 for "no hit"
-                            sm.scan[kb[s]] = hit ? (cy[s] << 16 | cx[s]) : -1;
-                            const int k = atomicAdd(&sm.next_beam, 1);
-                            kb[s] = k < NB ? k : -1;
-                            tn = t1;
-                            if (k < NB) {
-                                const float2 dd = sm.dir[k];
-                                dx[s] = dd.x;
-                                dy[s] = dd.y;
-                            }
+                        for (int s = 0; s < MARCH_SLOTS; s++) {
+                            cx[s] = __float2int_rz(__fmaf_rn(dx[s], t[s], x0));
+                            cy[s] = __float2int_rz(__fmaf_rn(dy[s], t[s], y0));
+                            inb[s] = ((unsigned)cx[s] < (unsigned)W) & ((unsigned)cy[s] < (unsigned)H);
+                            const unsigned idx = (inb[s] & (kb[s] >= 0)) ? (unsigned)(cy[s] * W + cx[s]) : 0u;
+                            d[s] = __ldg(dist + idx);
                         }
-                        t[s] = tn;
-                    }
-                    bool live = false;
 #pragma unroll
-                    for (int s = 0; s < MARCH_SLOTS; s++) live |= kb[s] >= 0;
-                    if (!__any_sync(FULL, live)) break;
+                        for (int s = 0; s < MARCH_SLOTS; s++) {
+                            const bool hit = inb[s] & (d[s] <= 0.0f);
+                            float tn = __fadd_rn(t[s], fmaxf(__fmul_rn(d[s], 0.999f), 1.0f));
+                            const bool fin = !inb[s] | hit | !(tn < t_stop);
+                            if (fin & (kb[s] >= 0)) {
+                                // absolute hit cell, (y << 16 | x), or -1 for "no hit"
+                                sm.scan[kb[s]] = hit ? (cy[s] << 16 | cx[s]) : -1;
+                                const int i = atomicAdd(&sm.next_beam, 1);
+                                kb[s] = -1;
+                                if (i < n_alive) {
+                                    const int k = sm.alive[i];
+                                    kb[s] = k;
+                                    tn = __int_as_float(sm.scan[k]);
+                                    const float2 dd = sm.dir[k];
+                                    dx[s] = dd.x;
+                                    dy[s] = dd.y;
+                                }
+                            }
+                            t[s] = tn;
+                        }
+                        bool live = false;
+#pragma unroll
+                        for (int s = 0; s < MARCH_SLOTS; s++) live |= kb[s] >= 0;
+                        if (!__any_sync(FULL, live)) break;
+                    }
                 }
             }
             if (WPE > 1) __syncthreads(); else __syncwarp();

@@ -8,7 +8,7 @@ OUT = os.path.join(ROOT, 'tools', '_prof', 'libnavgym_b200_prof.so')
 if sys.argv[1] == 'build':
     from nav_gym_b200 import _lib
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    for tag, extra in (('', []), ('_t1280', ['-DNAVGYM_THREADS_PER_SM=1280']), ('_t1536', ['-DNAVGYM_THREADS_PER_SM=1536']), ('_t2048', ['-DNAVGYM_THREADS_PER_SM=2048'])):
+    for tag, extra in (('', []), ('_h1', ['-DNAVGYM_HEAD_STEPS=1']), ('_h2', ['-DNAVGYM_HEAD_STEPS=2']), ('_h4', ['-DNAVGYM_HEAD_STEPS=4']), ('_h6', ['-DNAVGYM_HEAD_STEPS=6'])):
         out = OUT.replace('.so', tag + '.so')
         r = subprocess.run(['nvcc'] + _lib.NVCC_FLAGS + ['-DNAVGYM_PROFILE', '-Xptxas', '-v'] + extra + ['-o', out, _lib.SRC], capture_output=True, text=True)
         lines = r.stderr.splitlines()
