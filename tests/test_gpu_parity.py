@@ -208,3 +208,42 @@ def test_async_host_groups_match_device_step():
             if t + 1 < T:
                 act_h[b0:b1].copy_(acts[t + 1][b0:b1])
                 envs[1].submit_host(g, act_h, obs_h, rew_h, done_h)
+
+
+def test_map_pool_auto_reset_with_pedestrians_is_deterministic():
+    """C4-style world: several maps, per-env pedestrian counts, map re-drawn at auto-reset.
+    Invariants + run-to-run determinism (the Philox streams are keyed by env / episode / step)."""
+    from nav_gym_b200 import maps, _lib
+    from nav_gym_b200.batched_env import BatchedNavGym, MapPool, filter_spawn_pool
+    rng = np.random.RandomState(8)
+    ms = [maps.create_outdoor_map(10, 0.5, rng), maps.create_indoor_map(3, 40, rng, cells=40),
+          maps.create_outdoor_map(10, 0.9, rng, size=300)]
+    pools = [filter_spawn_pool(m, maps.spawn_pool(m, 512, rng, min_goal_dist=3, max_goal_dist=12)) for m in ms]
+    assert all(len(p) > 20 for p in pools)
+    mp = MapPool(ms, 'cuda:0', spawn_pools=pools)
+    B, P = 300, 6
+    map_id = rng.randint(0, 3, B).astype(np.int32)
+    peds = np.stack([maps.spawn_pedestrians(ms[map_id[e]], (-50, -50), P, np.random.RandomState(e)) for e in range(B)])
+    nped = rng.randint(0, P + 1, B).astype(np.int32)
+    acts = torch.from_numpy(rng.uniform([0.2, -0.64], [0.5, 0.64], (40, B, 2)).astype(np.float32)).cuda()
+    runs = []
+    for rep in range(2):
+        env = BatchedNavGym(B, mp, map_id=map_id, seed=11, auto_reset=True, resample_map=True,
+                            max_episode_steps=25)
+        env.reset_from_spawn_pool(np.random.RandomState(9))
+        env.attach_pedestrians(peds, nped=nped)
+        env.reset()
+        log = []
+        for t in range(40):
+            o, r, d, info = env.step(acts[t])
+            log.append((o.clone(), r.clone(), d.clone(), env.map_id.clone(), info['truncated'].clone()))
+        runs.append(log)
+        assert int(env.episodes.sum()) > B // 4                      # episodes ended and restarted
+        assert int(sum(x[4].sum() for x in log)) > 0                  # some by the step limit
+        mid = env.map_id.cpu().numpy()
+        assert mid.min() >= 0 and mid.max() <= 2 and len(np.unique(mid)) == 3
+        o = log[-1][0].cpu().numpy()
+        assert np.isfinite(o).all() and o[:, :512].min() > -0.5 and o[:, :512].max() < 25.5
+        assert int(env.steps.max()) <= 25
+    for a, b in zip(*runs):
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
