@@ -268,19 +268,21 @@ def main():
     e2e_sync_ms = (time.perf_counter() - t_s) * 1e3
 
     n_groups = int(os.environ.get('NAVGYM_HOST_GROUPS', '4'))
-    bounds = env.host_groups(n_groups)
     cur = torch.empty(B, 2, dtype=torch.float32).pin_memory()
+    bounds = env.host_groups(n_groups, cur, obs_h, rew_h, done_h)
+    cur_np, bank_np = cur.numpy(), act_h.numpy()
 
     def pipelined(n):
-        cur.copy_(act_h[0])
+        cur_np[:] = bank_np[0]
         for g in range(n_groups):
-            env.submit_host(g, cur, obs_h, rew_h, done_h)
+            env.submit_host(g)
         for i in range(n):
+            nxt = bank_np[(i + 1) % n_bank]
             for g, (b0, b1) in enumerate(bounds):
                 env.wait_host(g)                      # group g's obs / reward / done are on the host
                 if i + 1 < n:
-                    cur[b0:b1].copy_(act_h[(i + 1) % n_bank, b0:b1])   # "policy": next actions
-                    env.submit_host(g, cur, obs_h, rew_h, done_h)
+                    cur_np[b0:b1] = nxt[b0:b1]        # "policy": the group's next actions
+                    env.submit_host(g)
     pipelined(3)
     barrier()
     t_s = time.perf_counter()

@@ -288,11 +288,18 @@ class BatchedNavGym(object):
         return obs_host, reward_host, done_host
 
     # ---- asynchronous host API: several env groups in flight (EnvPool style) ----------------
-    def host_groups(self, groups=2):
-        """Split the batch into `groups` consecutive env ranges for submit_host / wait_host and
-        return their (begin, end) bounds."""
+    def host_groups(self, groups, actions_host, obs_host, reward_host, done_host):
+        """Split the batch into `groups` consecutive env ranges for submit_host / wait_host,
+        bind the pinned [B, ...] host tensors they read / write, and return the ranges'
+        (begin, end) bounds."""
         if self.peds is not None:
             raise NotImplementedError('async host groups with device pedestrians')
+        for t in (actions_host, obs_host, reward_host, done_host):
+            if not t.is_pinned() or not t.is_contiguous():
+                raise ValueError('host_groups needs contiguous pinned host tensors')
+        assert obs_host.dtype == torch.float32 and tuple(obs_host.shape) == (self.B, self.obs_dim)
+        assert actions_host.dtype == torch.float32 and actions_host.numel() == 2 * self.B
+        assert reward_host.dtype == torch.float32 and done_host.dtype == torch.uint8
         if self._pipe is not None:
             self.lib.navgym_host_pipe_destroy(self._pipe[0])
         h = self.lib.navgym_host_pipe_create(groups, self.B, int(self.sched is not None))
@@ -302,20 +309,25 @@ class BatchedNavGym(object):
         self._act_dev = torch.empty(self.B, 2, dtype=torch.float32, device=self.device)
         self.args.actions = _ptr(self._act_dev)
         self._geom(None, None, None, None, None)
+        self._host_bufs = (actions_host, obs_host, reward_host, done_host)
+        self._host_ptrs = tuple(_ptr(t) for t in self._host_bufs)
+        self._args_ref = C.byref(self.args)
         torch.cuda.synchronize(self.device)
         return [(self.B * g // groups, self.B * (g + 1) // groups) for g in range(groups)]
 
-    def submit_host(self, group, actions_host, obs_host, reward_host, done_host):
-        """Enqueue one step of env group `group`: its rows of the pinned [B, ...] host tensors
-        are read / written; returns immediately."""
-        self.args.actions = _ptr(self._act_dev)
-        _lib.check(self.lib.navgym_step_batch_host_submit(
-            self._pipe[0], C.byref(self.args), int(group), _ptr(actions_host), _ptr(obs_host),
-            _ptr(reward_host), _ptr(done_host)), 'step_host_submit')
+    def submit_host(self, group):
+        """Enqueue one step of env group `group` (its rows of the bound host tensors are read /
+        written); returns immediately."""
+        p = self._host_ptrs
+        err = self.lib.navgym_step_batch_host_submit(self._pipe[0], self._args_ref, group, p[0], p[1], p[2], p[3])
+        if err:
+            _lib.check(err, 'step_host_submit')
 
     def wait_host(self, group):
         """Block until the results of the last submit_host(group) are on the host."""
-        _lib.check(self.lib.navgym_step_batch_host_wait(self._pipe[0], int(group)), 'step_host_wait')
+        err = self.lib.navgym_step_batch_host_wait(self._pipe[0], group)
+        if err:
+            _lib.check(err, 'step_host_wait')
 
     def __del__(self):
         p, self._pipe = getattr(self, '_pipe', None), None

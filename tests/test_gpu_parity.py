@@ -186,11 +186,11 @@ def test_async_host_groups_match_device_step():
     envs = [BatchedNavGym(B, mp, seed=3, auto_reset=True) for _ in range(2)]
     for e in envs:
         e.reset_from_spawn_pool(np.random.RandomState(7))
-    bounds = envs[1].host_groups(2)
     act_h = torch.empty(B, 2).pin_memory()
     obs_h = torch.empty(B, 519).pin_memory()
     rew_h = torch.empty(B).pin_memory()
     done_h = torch.empty(B, dtype=torch.uint8).pin_memory()
+    bounds = envs[1].host_groups(2, act_h, obs_h, rew_h, done_h)
     T = 12
     acts = torch.from_numpy(rng.uniform([0.2, -0.64], [0.5, 0.64], (T, B, 2)).astype(np.float32))
     want = []
@@ -199,7 +199,7 @@ def test_async_host_groups_match_device_step():
         want.append((o.cpu().clone(), r.cpu().clone(), d.cpu().clone()))
     act_h.copy_(acts[0])
     for g in range(2):
-        envs[1].submit_host(g, act_h, obs_h, rew_h, done_h)
+        envs[1].submit_host(g)
     for t in range(T):
         for g, (b0, b1) in enumerate(bounds):
             envs[1].wait_host(g)
@@ -207,7 +207,7 @@ def test_async_host_groups_match_device_step():
             assert torch.equal(rew_h[b0:b1], want[t][1][b0:b1]) and torch.equal(done_h[b0:b1], want[t][2][b0:b1])
             if t + 1 < T:
                 act_h[b0:b1].copy_(acts[t + 1][b0:b1])
-                envs[1].submit_host(g, act_h, obs_h, rew_h, done_h)
+                envs[1].submit_host(g)
 
 
 def test_map_pool_auto_reset_with_pedestrians_is_deterministic():
