@@ -47,5 +47,12 @@ else:
     for i, nm in enumerate(names):
         print('%-22s %8.0f cycles/CTA  %5.1f%%' % (nm, buf[i] / (n * B), 100.0 * buf[i] / tot))
     print('total %.0f cycles/CTA' % (tot / (n * B)))
-    d = env.truncated.cpu().numpy().astype(float); dn = env.done.cpu().numpy() > 0
-    print('CTA duration kcycles: mean %.1f p50 %.0f p90 %.0f p99 %.0f max %.0f | done envs (%d): mean %.1f | not done: mean %.1f max %.0f' % (d.mean(), np.percentile(d,50), np.percentile(d,90), np.percentile(d,99), d.max(), dn.sum(), d[dn].mean() if dn.any() else 0, d[~dn].mean(), d[~dn].max()))
+    tl = env.tail64.cpu().numpy()
+    t0 = tl[:, 0].min(); st = (tl[:, 0] - t0) / 1e3; en = (tl[:, 1] - t0) / 1e3; dur = en - st
+    print('kernel span %.1f us; CTA duration us: mean %.1f p50 %.1f p90 %.1f p99 %.1f max %.1f' % (en.max(), dur.mean(), np.percentile(dur, 50), np.percentile(dur, 90), np.percentile(dur, 99), dur.max()))
+    print('CTA start us: p50 %.1f p90 %.1f max %.1f ; last 5 to end: ' % (np.percentile(st, 50), np.percentile(st, 90), st.max()), [(round(st[i], 1), round(en[i], 1), int(tl[i, 3])) for i in np.argsort(en)[-5:]])
+    ts = np.linspace(0, en.max(), 23)[1:-1]
+    print('resident CTAs over time:', [int(((st <= t) & (en > t)).sum()) for t in ts])
+    sm = tl[:, 2].astype(int)
+    busy = np.array([en[sm == i].max() for i in np.unique(sm)])
+    print('per-SM finish time us: min %.1f mean %.1f max %.1f' % (busy.min(), busy.mean(), busy.max()))
