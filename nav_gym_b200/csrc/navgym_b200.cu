@@ -166,7 +166,7 @@ __device__ __forceinline__ float beam_normal(uint64_t seed, uint32_t env, uint32
 // Optional per-phase cycle accounting (tools/phase_prof.py builds with -DNAVGYM_PROFILE).
 #ifdef NAVGYM_PROFILE
 __device__ unsigned long long g_prof[16];
-#define PROF_DECL long long _pt = clock64(); const long long _t_begin = _pt;
+#define PROF_DECL long long _pt = clock64(); unsigned long long _g_begin; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_g_begin));
 #define PROF_MARK(i) do { if (tid == 0) { long long _n = clock64(); atomicAdd(&g_prof[i], (unsigned long long)(_n - _pt)); _pt = _n; } } while (0)
 #else
 #define PROF_DECL
@@ -734,9 +734,15 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
     }
     PROF_MARK(7);
 #ifdef NAVGYM_PROFILE
-    if (tid == 0 && a.truncated) {  // per-CTA duration (kilo-cycles, saturating) for tail analysis
-        long long dur = (clock64() - _t_begin) >> 10;
-        a.truncated[e] = (uint8_t)(dur > 255 ? 255 : dur);
+    if (tid == 0 && a.tail64) {  // CTA timeline (global ns clock, SM id) for tail analysis
+        unsigned long long t_end;
+        unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        a.tail64[(size_t)e * 7 + 0] = (double)_g_begin;
+        a.tail64[(size_t)e * 7 + 1] = (double)t_end;
+        a.tail64[(size_t)e * 7 + 2] = (double)smid;
+        a.tail64[(size_t)e * 7 + 3] = (double)blockIdx.x;
     }
 #endif
 #undef ST
