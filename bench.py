@@ -140,9 +140,11 @@ def cpu_reference_run(steps, warmup, B_cpu=512, seed=0):
 def cpu_baseline_block(sample_steps=20):
     r = cpu_reference_run(sample_steps, 2)
     return {"value": r['value'], "unit": METRIC, "cores": r['cores'], "kind": "port",
+            "rays_per_s": r['value'] * NB,
             "sample": "%d envs x %d steps of the same world/action law, C restatement "
-                      "(oracle/navgym_oracle.c) with OpenMP over %d threads; noise pre-drawn"
-                      % (r['B'], sample_steps, r['cores'])}
+                      "(oracle/navgym_oracle.c) with OpenMP over %d threads; noise pre-drawn; the "
+                      "reference itself (one env per Python process, pip natives absent here) "
+                      "cannot run on this box" % (r['B'], sample_steps, r['cores'])}
 
 
 # ------------------------------------------------------------------------------ main

@@ -437,59 +437,96 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
             PROF_MARK(2);
             {
                 const int n_alive = sm.n_alive;
-                int kb[MARCH_SLOTS];  // the slot's current beam, -1 = none left
-                float t[MARCH_SLOTS], dx[MARCH_SLOTS], dy[MARCH_SLOTS];
-#pragma unroll
-                for (int s = 0; s < MARCH_SLOTS; s++) {
-                    const int i = s * TPB + tid;
-                    kb[s] = i < n_alive ? (int)sm.alive[i] : -1;
-                    const int kk = kb[s] >= 0 ? kb[s] : 0;
-                    t[s] = __int_as_float(sm.scan[kk]);
-                    const float2 dd = sm.dir[kk];
-                    dx[s] = dd.x;
-                    dy[s] = dd.y;
-                }
-                if (n_alive > 0) {
-                    for (;;) {
-                        float d[MARCH_SLOTS];
-                        int cx[MARCH_SLOTS], cy[MARCH_SLOTS];
-                        bool inb[MARCH_SLOTS];
-#pragma unroll
-                        for (int s = 0; s < MARCH_SLOTS; s++) {
-                            cx[s] = __float2int_rz(__fmaf_rn(dx[s], t[s], x0));
-                            cy[s] = __float2int_rz(__fmaf_rn(dy[s], t[s], y0));
-                            inb[s] = ((unsigned)cx[s] < (unsigned)W) & ((unsigned)cy[s] < (unsigned)H);
-                            const unsigned idx = (inb[s] & (kb[s] >= 0)) ? (unsigned)(cy[s] * W + cx[s]) : 0u;
-                            d[s] = __ldg(dist + idx);
-                        }
-#pragma unroll
-                        for (int s = 0; s < MARCH_SLOTS; s++) {
-                            const bool hit = inb[s] & (d[s] <= 0.0f);
-                            float tn = __fadd_rn(t[s], fmaxf(__fmul_rn(d[s], 0.999f), 1.0f));
-                            const bool fin = !inb[s] | hit | !(tn < t_stop);
-                            if (fin & (kb[s] >= 0)) {
+                if (MARCH_SLOTS == 1) {
+                    // Warp w owns list entries w, w + WPE, w + 2 WPE, ...; they are dealt to its
+                    // lanes with ballot ranks (no atomics, no cross-warp traffic): a lane whose
+                    // beam ends takes the warp's next undealt entry.
+                    int next_j = 32;                       // warp-uniform: entries dealt so far
+                    int idx = warp + WPE * lane;
+                    int kb = idx < n_alive ? (int)sm.alive[idx] : -1;
+                    float t = __int_as_float(sm.scan[kb >= 0 ? kb : 0]);
+                    float2 dd = sm.dir[kb >= 0 ? kb : 0];
+                    if (__any_sync(FULL, kb >= 0)) {
+                        for (;;) {
+                            const int cx = __float2int_rz(__fmaf_rn(dd.x, t, x0));
+                            const int cy = __float2int_rz(__fmaf_rn(dd.y, t, y0));
+                            const bool inb = ((unsigned)cx < (unsigned)W) & ((unsigned)cy < (unsigned)H);
+                            const unsigned ci_ = (inb & (kb >= 0)) ? (unsigned)(cy * W + cx) : 0u;
+                            const float d = __ldg(dist + ci_);
+                            const bool hit = inb & (d <= 0.0f);
+                            t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+                            const bool fin = (kb >= 0) & (!inb | hit | !(t < t_stop));
+                            const unsigned fm = __ballot_sync(FULL, fin);
+                            if (fin) {
                                 // absolute hit cell, (y << 16 | x), or -1 for "no hit"
-                                sm.scan[kb[s]] = hit ? (cy[s] << 16 | cx[s]) : -1;
-                                const int i = atomicAdd(&sm.next_beam, 1);
-                                kb[s] = -1;
-                                if (i < n_alive) {
-                                    const int k = sm.alive[i];
-                                    kb[s] = k;
-                                    tn = __int_as_float(sm.scan[k]);
-                                    const float2 dd = sm.dir[k];
-                                    dx[s] = dd.x;
-                                    dy[s] = dd.y;
+                                sm.scan[kb] = hit ? (cy << 16 | cx) : -1;
+                                idx = warp + WPE * (next_j + __popc(fm & ((1u << lane) - 1u)));
+                                kb = -1;
+                                if (idx < n_alive) {
+                                    kb = sm.alive[idx];
+                                    t = __int_as_float(sm.scan[kb]);
+                                    dd = sm.dir[kb];
                                 }
                             }
-                            t[s] = tn;
+                            next_j += __popc(fm);
+                            if (!__any_sync(FULL, kb >= 0)) break;
                         }
-                        bool live = false;
-#pragma unroll
-                        for (int s = 0; s < MARCH_SLOTS; s++) live |= kb[s] >= 0;
-                        if (!__any_sync(FULL, live)) break;
                     }
-                }
+                } else {
+                int kb[MARCH_SLOTS];  // the slot's current beam, -1 = none left
+                    float t[MARCH_SLOTS], dx[MARCH_SLOTS], dy[MARCH_SLOTS];
+#pragma unroll
+                    for (int s = 0; s < MARCH_SLOTS; s++) {
+                        const int i = s * TPB + tid;
+                        kb[s] = i < n_alive ? (int)sm.alive[i] : -1;
+                        const int kk = kb[s] >= 0 ? kb[s] : 0;
+                        t[s] = __int_as_float(sm.scan[kk]);
+                        const float2 dd = sm.dir[kk];
+                        dx[s] = dd.x;
+                        dy[s] = dd.y;
+                    }
+                    if (n_alive > 0) {
+                        for (;;) {
+                            float d[MARCH_SLOTS];
+                            int cx[MARCH_SLOTS], cy[MARCH_SLOTS];
+                            bool inb[MARCH_SLOTS];
+#pragma unroll
+                            for (int s = 0; s < MARCH_SLOTS; s++) {
+                                cx[s] = __float2int_rz(__fmaf_rn(dx[s], t[s], x0));
+                                cy[s] = __float2int_rz(__fmaf_rn(dy[s], t[s], y0));
+                                inb[s] = ((unsigned)cx[s] < (unsigned)W) & ((unsigned)cy[s] < (unsigned)H);
+                                const unsigned idx = (inb[s] & (kb[s] >= 0)) ? (unsigned)(cy[s] * W + cx[s]) : 0u;
+                                d[s] = __ldg(dist + idx);
+                            }
+#pragma unroll
+                            for (int s = 0; s < MARCH_SLOTS; s++) {
+                                const bool hit = inb[s] & (d[s] <= 0.0f);
+                                float tn = __fadd_rn(t[s], fmaxf(__fmul_rn(d[s], 0.999f), 1.0f));
+                                const bool fin = !inb[s] | hit | !(tn < t_stop);
+                                if (fin & (kb[s] >= 0)) {
+                                    // absolute hit cell, (y << 16 | x), or -1 for "no hit"
+                                    sm.scan[kb[s]] = hit ? (cy[s] << 16 | cx[s]) : -1;
+                                    const int i = atomicAdd(&sm.next_beam, 1);
+                                    kb[s] = -1;
+                                    if (i < n_alive) {
+                                        const int k = sm.alive[i];
+                                        kb[s] = k;
+                                        tn = __int_as_float(sm.scan[k]);
+                                        const float2 dd = sm.dir[k];
+                                        dx[s] = dd.x;
+                                        dy[s] = dd.y;
+                                    }
+                                }
+                                t[s] = tn;
+                            }
+                            bool live = false;
+#pragma unroll
+                            for (int s = 0; s < MARCH_SLOTS; s++) live |= kb[s] >= 0;
+                            if (!__any_sync(FULL, live)) break;
+                        }
+                    }
             }
+                }
             if (WPE > 1) __syncthreads(); else __syncwarp();
             // ranges (env.py:426), all lanes active: sqrt(di^2 + dj^2) * resolution
             const bool rec = pass == (IS_RESET_KERNEL ? PASS_RESET : PASS_STEP) && a.hits;

@@ -1,6 +1,6 @@
-"""One-off analysis: distribution of march steps and unit-step runs on the bench world."""
+"""One-off analysis (uses the CPU oracle, so it lives under oracle/): distribution of march steps and unit-step runs on the bench world."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, numba
 from oracle import oracle as orc
 from bench import build_world

@@ -1,6 +1,6 @@
 """One-off: fraction of march samples that fall within +-h cells of the origin cell."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, numba
 from oracle import oracle as orc
 from bench import build_world
