@@ -67,7 +67,7 @@ class ClockSampler(object):
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                 '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 '-lms', '50'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -151,8 +151,8 @@ def cpu_baseline_block(sample_steps=20):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
-    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=2000)    # 2000 timed steps
+    ap.add_argument('--warmup', type=int, default=200)   # after 200 warm-up steps
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--envs', type=int, default=ENVS_PER_GPU, help='environments per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -173,9 +173,9 @@ def main():
     if a.impl == 'reference':
         if rank != 0:
             return
-        r = cpu_reference_run(a.steps, a.warmup)
+        r = cpu_reference_run(min(a.steps, 400), min(a.warmup, 10))
         line = {"impl": "reference", "metric": METRIC, "value": r['value'], "unit": "env-steps/s",
-                "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                "n_gpus": a.gpus, "steps": min(a.steps, 400), "warmup": min(a.warmup, 10),
                 "ms_per_step": r['ms_per_step'], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32 scan / f64 pose", "data": "synthetic",
                 "rays_per_s": r['value'] * NB,
@@ -251,7 +251,7 @@ def main():
 
     # ---- end-to-end legs: HOST buffers, copies inside the timed region ----------------------
     # (a) synchronous call: navgym_step_batch_host = H2D actions -> step -> D2H obs/reward/done
-    # (b) two env groups in flight (submit/wait): each group's next actions are only handed in
+    # (b) several env groups in flight (submit/wait): each group's next actions are only handed in
     #     after its previous observations have landed on the host; while the host holds group
     #     A's results, group B is stepping, so PCIe hides behind the raycast.
     act_h = torch.empty(n_bank, B, 2, dtype=torch.float32).pin_memory()
@@ -323,10 +323,10 @@ def main():
         "e2e": {"value": world * B * Ke / (e2e_ms * 1e-3), "unit": "env-steps/s",
                 "h2d_bytes_per_step": B * 2 * 4, "d2h_bytes_per_step": B * ((NB + 7) * 4 + 4 + 1),
                 "steps": Ke, "timing": "host wall clock, max over ranks",
-                "api": "BatchedNavGym.submit_host/wait_host (C ABI navgym_step_batch_host_submit/"
-                       "_wait): pinned host actions in, pinned host obs/reward/done out, two env "
-                       "groups in flight; a group's next actions are submitted only after its "
-                       "previous results landed",
+                "api": ("BatchedNavGym.submit_host/wait_host (C ABI navgym_step_batch_host_submit/"
+                        "_wait): pinned host actions in, pinned host obs/reward/done out, %d env "
+                        "groups in flight; a group's next actions are submitted only after its "
+                        "previous results landed") % n_groups,
                 "sync_value": world * B * Ke / (e2e_sync_ms * 1e-3),
                 "sync_api": "BatchedNavGym.step_host (navgym_step_batch_host), one blocking call per step"},
         "gpu_launches": launches,
