@@ -260,7 +260,7 @@ def main():
     rew_h = torch.empty(B, dtype=torch.float32).pin_memory()
     done_h = torch.empty(B, dtype=torch.uint8).pin_memory()
     Ke = min(K, 200)
-    for i in range(3):
+    for i in range(30):
         env.step_host(act_h[i % n_bank], obs_h, rew_h, done_h)
     barrier()
     t_s = time.perf_counter()
@@ -285,7 +285,7 @@ def main():
                 if i + 1 < n:
                     cur_np[b0:b1] = nxt[b0:b1]        # "policy": the group's next actions
                     env.submit_host(g)
-    pipelined(3)
+    pipelined(30)
     barrier()
     t_s = time.perf_counter()
     pipelined(Ke)
