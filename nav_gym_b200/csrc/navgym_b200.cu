@@ -668,6 +668,7 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
                 const double ddx = __dsub_rn(gx, qx), ddy = __dsub_rn(gy, qy);
                 const double dq = sqrt(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)));
                 const double dist_g = __shfl_sync(FULL, dq, 0), pdist = __shfl_sync(FULL, dq, 1);
+                __syncwarp();  // lane 1 has read sm.ppx / sm.ppy before lane 0 may rewrite the pose below
                 const int success = dist_g < a.dist_thresh;
                 const int trunc = a.max_episode_steps > 0 && sm.steps >= a.max_episode_steps && !(success || crash);
                 const int done = success || crash || trunc;
