@@ -235,6 +235,9 @@ __device__ __forceinline__ void normal4(uint64_t seed, uint32_t env, uint32_t ep
 #ifndef NAVGYM_HEAD_STEPS
 #define NAVGYM_HEAD_STEPS 4  // samples every beam marches in the lockstep head phase
 #endif
+#ifndef NAVGYM_RISK_MARGIN
+#define NAVGYM_RISK_MARGIN 0.25f  // [m] clearance under which the next step may end the episode
+#endif
 #ifndef NAVGYM_THREADS_PER_SM
 #define NAVGYM_THREADS_PER_SM 1024  // resident threads the register budget is tuned for
 #endif
@@ -340,9 +343,13 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
     int pass = IS_RESET_KERNEL ? PASS_RESET : PASS_STEP;
     float *orow = a.obs + (size_t)e * a.obs_stride;
 
+    long long t_pass = t_begin;  // start of the pass that produces the returned observation
+    float margin = CUDART_INF_F; // its smallest clearance over the crash thresholds [m]
     for (;;) {
         // ---- per-pass setup: float32 lidar pose, origin cell (env.py:386, 419)
         if (WPE > 1) __syncthreads(); else __syncwarp();
+        if (!IS_RESET_KERNEL && pass != PASS_STEP) t_pass = clock64();
+        margin = CUDART_INF_F;
         PROF_MARK(0);
         if (tid == 0) {
             const navgym_map_t m = a.maps[sm.map];
@@ -627,8 +634,10 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
                         }
                         orow[(SS - 1) * NB + k] = v;
                     }
-                    c_any |= v < a.thr[k];
+                    const float thr_k = a.thr[k];
+                    c_any |= v < thr_k;
                     d_any |= v < a.dthr[k];
+                    margin = fminf(margin, v - thr_k);
                 }
             }
         }
@@ -764,11 +773,25 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
             if (a.noise_std) a.noise_std[e] = sm.noise_std;
         }
     }
-    if (sched_cnt && tid == 0) {  // file this environment under its cost class for the next step
-        const long long kc = (clock64() - t_begin) >> 13;
-        const int b = NAVGYM_SCHED_BUCKETS - 1 - (int)(kc > NAVGYM_SCHED_BUCKETS - 1 ? NAVGYM_SCHED_BUCKETS - 1 : kc);
-        const int pos = atomicAdd(&sched_cnt[b], 1);
-        sched_list[(size_t)b * B + pos] = e;
+    if (sched_cnt) {
+        // File this environment under its cost class for the next step: the cycles its last
+        // scan took (an auto-reset first scan is taken at the pose the next step starts from),
+        // doubled when the next step is likely to end the episode and run a second scan -- the
+        // robot is within one step of a crash threshold, of the goal, or of the step limit.
+        // Such environments then start first instead of stretching the end of the launch.
+        bool risky = margin < NAVGYM_RISK_MARGIN;
+        if (tid == 0) {
+            const double gx = sm.gx - sm.px, gy = sm.gy - sm.py;
+            risky |= gx * gx + gy * gy < (a.dist_thresh + NAVGYM_RISK_MARGIN) * (a.dist_thresh + NAVGYM_RISK_MARGIN);
+            risky |= a.max_episode_steps > 0 && sm.steps + 1 >= a.max_episode_steps;
+        }
+        risky = (WPE > 1 ? __syncthreads_or(risky) : __any_sync(FULL, risky)) && a.auto_reset;
+        if (tid == 0) {
+            const long long kc = ((clock64() - t_pass) << (risky ? 1 : 0)) >> 13;
+            const int b = NAVGYM_SCHED_BUCKETS - 1 - (int)(kc > NAVGYM_SCHED_BUCKETS - 1 ? NAVGYM_SCHED_BUCKETS - 1 : kc);
+            const int pos = atomicAdd(&sched_cnt[b], 1);
+            sched_list[(size_t)b * B + pos] = e;
+        }
     }
     PROF_MARK(7);
 #ifdef NAVGYM_PROFILE
