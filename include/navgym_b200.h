@@ -111,6 +111,12 @@ typedef struct {
      * (count = num_envs, list = 0..num_envs-1), everything else zero, and advance sched_phase by
      * one (mod 3) after every navgym_step_batch.  NULL = block i steps env i. */
     int32_t *sched;
+    /* optional second destinations of reward / done (NULL = none): device-visible addresses the
+     * kernel also stores to, e.g. mapped pinned host memory -- the host-buffer entry points
+     * below point them at reward_host / done_host so that a group needs one D2H copy (its
+     * observation rows) instead of three. */
+    float *reward_mirror;
+    uint8_t *done_mirror;
 } navgym_step_args_t;
 
 /* ---- fused hot path: NavGymEnv.step (env.py:591-728) over num_envs environments ------ */

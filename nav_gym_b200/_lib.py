@@ -81,6 +81,7 @@ class StepArgs(C.Structure):
         ('obs', _P), ('tail64', _P), ('reward', _P),
         ('done', _P), ('is_success', _P), ('is_crash', _P), ('truncated', _P),
         ('distance', _P), ('hits', _P), ('sched', _P),
+        ('reward_mirror', _P), ('done_mirror', _P),
     ]
 
 

@@ -693,6 +693,8 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
                     double rew = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(r_s, r_c), r_p), r_f), r_r), r_d);
                     a.reward[e] = (float)rew;
                     a.done[e] = (uint8_t)done;
+                    if (a.reward_mirror) a.reward_mirror[e] = (float)rew;
+                    if (a.done_mirror) a.done_mirror[e] = (uint8_t)done;
                     a.is_success[e] = (uint8_t)success;
                     a.is_crash[e] = (uint8_t)crash;
                     if (a.truncated) a.truncated[e] = (uint8_t)trunc;
@@ -1082,6 +1084,15 @@ int navgym_step_batch(const navgym_step_args_t *args, void *stream)
 // ---- host-buffer step: chunked launches on prioritised streams, D2H of early chunks
 // overlapping the raycast of later ones -----------------------------------------------------
 #define NAVGYM_MAX_CHUNKS 8
+// One submit = H2D(actions) -> step -> 3 x D2H on the group's stream.  Issued call by call that
+// is five driver calls per group and step; the sequence only depends on the argument block, the
+// host pointers and the schedule phase, so it is captured once per (group, phase) into a CUDA
+// graph and replayed with one cudaGraphLaunch while those stay the same.
+struct navgym_group_graph {
+    cudaGraphExec_t exec;
+    navgym_step_args_t key;
+    const void *host[4];
+};
 struct navgym_host_pipe {
     int chunks, num_envs;
     cudaStream_t streams[NAVGYM_MAX_CHUNKS];
@@ -1089,6 +1100,8 @@ struct navgym_host_pipe {
     int32_t *sched[NAVGYM_MAX_CHUNKS];
     int phase[NAVGYM_MAX_CHUNKS];
     int b0[NAVGYM_MAX_CHUNKS + 1];
+    navgym_group_graph graphs[NAVGYM_MAX_CHUNKS][3];
+    int use_graphs;
 };
 
 navgym_host_pipe_t *navgym_host_pipe_create(int chunks, int num_envs, int longest_first)
@@ -1119,6 +1132,8 @@ navgym_host_pipe_t *navgym_host_pipe_create(int chunks, int num_envs, int longes
         }
     }
     cudaEventCreateWithFlags(&p->ready, cudaEventDisableTiming);
+    memset(p->graphs, 0, sizeof(p->graphs));
+    p->use_graphs = env_int("NAVGYM_HOST_GRAPHS", 1);
     return p;
 }
 
@@ -1126,11 +1141,47 @@ void navgym_host_pipe_destroy(navgym_host_pipe_t *p)
 {
     if (!p) return;
     for (int c = 0; c < p->chunks; c++) {
+        cudaStreamSynchronize(p->streams[c]);
+        for (int i = 0; i < 3; i++)
+            if (p->graphs[c][i].exec) cudaGraphExecDestroy(p->graphs[c][i].exec);
         cudaStreamDestroy(p->streams[c]);
         if (p->sched[c]) cudaFree(p->sched[c]);
     }
     cudaEventDestroy(p->ready);
     delete p;
+}
+
+// Device-visible alias of a pinned (mapped) host address, or NULL for pageable memory.
+static void *mapped_alias(const void *ptr)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+static bool is_pinned_host(const void *ptr) { return mapped_alias(ptr) != nullptr; }
+
+// H2D(actions) -> step -> D2H for environments [a.env_begin, +a.env_count) on `st`.  reward and
+// done are a few bytes per environment: when their host arrays are mapped the kernel stores them
+// there itself (reward_mirror / done_mirror) and the observation rows are the only D2H copy.
+static int enqueue_group(navgym_step_args_t a, cudaStream_t st, const float *actions_host,
+                         float *obs_host, float *reward_host, uint8_t *done_host, bool h2d)
+{
+    const size_t b0 = (size_t)a.env_begin, n = (size_t)a.env_count;
+    static const int mirrors = env_int("NAVGYM_HOST_MIRRORS", 1);
+    a.reward_mirror = mirrors ? (float *)mapped_alias(reward_host) : nullptr;
+    a.done_mirror = mirrors ? (uint8_t *)mapped_alias(done_host) : nullptr;
+    if (h2d)
+        CK(cudaMemcpyAsync((void *)(a.actions + 2 * b0), actions_host + 2 * b0, n * 2 * sizeof(float),
+                           cudaMemcpyHostToDevice, st));
+    int err = navgym_step_batch(&a, st);
+    if (err) return err;
+    CK(cudaMemcpyAsync(obs_host + b0 * a.obs_stride, a.obs + b0 * a.obs_stride,
+                       n * a.obs_stride * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (!a.reward_mirror)
+        CK(cudaMemcpyAsync(reward_host + b0, a.reward + b0, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (!a.done_mirror)
+        CK(cudaMemcpyAsync(done_host + b0, a.done + b0, n, cudaMemcpyDeviceToHost, st));
+    return 0;
 }
 
 int navgym_step_batch_host(navgym_host_pipe_t *p, const navgym_step_args_t *args, void *stream,
@@ -1151,14 +1202,9 @@ int navgym_step_batch_host(navgym_host_pipe_t *p, const navgym_step_args_t *args
         a.sched = p->sched[c];
         a.sched_phase = p->phase[c];
         CK(cudaStreamWaitEvent(st, p->ready, 0));
-        int err = navgym_step_batch(&a, st);
+        int err = enqueue_group(a, st, actions_host, obs_host, reward_host, done_host, false);
         if (err) return err;
         if (p->sched[c]) p->phase[c] = (p->phase[c] + 1) % 3;
-        const size_t b0 = (size_t)a.env_begin, n = (size_t)a.env_count;
-        CK(cudaMemcpyAsync(obs_host + b0 * args->obs_stride, args->obs + b0 * args->obs_stride,
-                           n * args->obs_stride * sizeof(float), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(reward_host + b0, args->reward + b0, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(done_host + b0, args->done + b0, n, cudaMemcpyDeviceToHost, st));
     }
     for (int c = 0; c < p->chunks; c++) CK(cudaStreamSynchronize(p->streams[c]));
     return 0;
@@ -1181,16 +1227,34 @@ int navgym_step_batch_host_submit(navgym_host_pipe_t *p, const navgym_step_args_
     if (a.env_count <= 0) return 0;
     a.sched = p->sched[group];
     a.sched_phase = p->phase[group];
-    const size_t b0 = (size_t)a.env_begin, n = (size_t)a.env_count;
-    CK(cudaMemcpyAsync((void *)(args->actions + 2 * b0), actions_host + 2 * b0, n * 2 * sizeof(float),
-                       cudaMemcpyHostToDevice, st));
-    int err = navgym_step_batch(&a, st);
-    if (err) return err;
     if (p->sched[group]) p->phase[group] = (p->phase[group] + 1) % 3;
-    CK(cudaMemcpyAsync(obs_host + b0 * args->obs_stride, args->obs + b0 * args->obs_stride,
-                       n * args->obs_stride * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(reward_host + b0, args->reward + b0, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(done_host + b0, args->done + b0, n, cudaMemcpyDeviceToHost, st));
+    if (!p->use_graphs) return enqueue_group(a, st, actions_host, obs_host, reward_host, done_host, true);
+
+    navgym_group_graph &g = p->graphs[group][a.sched_phase];
+    const void *host[4] = {actions_host, obs_host, reward_host, done_host};
+    if (!g.exec || memcmp(&g.key, &a, sizeof(a)) != 0 || memcmp(g.host, host, sizeof(host)) != 0) {
+        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+        // pageable host memory cannot be captured: such callers keep the call-by-call path
+        for (int i = 0; i < 4; i++)
+            if (!is_pinned_host(host[i])) return enqueue_group(a, st, actions_host, obs_host, reward_host, done_host, true);
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const uint64_t launches = g_launches;
+        int err = enqueue_group(a, st, actions_host, obs_host, reward_host, done_host, true);
+        g_launches = launches;  // captured, not launched
+        cudaError_t cap = cudaStreamEndCapture(st, &graph);
+        if (err || cap != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            return err ? err : (int)cap;
+        }
+        cap = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (cap != cudaSuccess) { g.exec = nullptr; return (int)cap; }
+        g.key = a;
+        memcpy(g.host, host, sizeof(host));
+    }
+    CK(cudaGraphLaunch(g.exec, st));
+    g_launches++;
     return 0;
 }
 

@@ -8,7 +8,7 @@ OUT = os.path.join(ROOT, 'tools', '_prof', 'libnavgym_b200_prof.so')
 if sys.argv[1] == 'build':
     from nav_gym_b200 import _lib
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    for tag, extra in (('', []), ('_h1', ['-DNAVGYM_HEAD_STEPS=1']), ('_h2', ['-DNAVGYM_HEAD_STEPS=2']), ('_h4', ['-DNAVGYM_HEAD_STEPS=4']), ('_h6', ['-DNAVGYM_HEAD_STEPS=6'])):
+    for tag, extra in (('', []),):
         out = OUT.replace('.so', tag + '.so')
         r = subprocess.run(['nvcc'] + _lib.NVCC_FLAGS + ['-DNAVGYM_PROFILE', '-Xptxas', '-v'] + extra + ['-o', out, _lib.SRC], capture_output=True, text=True)
         lines = r.stderr.splitlines()
@@ -53,6 +53,12 @@ else:
     print('CTA start us: p50 %.1f p90 %.1f max %.1f ; last 5 to end: ' % (np.percentile(st, 50), np.percentile(st, 90), st.max()), [(round(st[i], 1), round(en[i], 1), int(tl[i, 3])) for i in np.argsort(en)[-5:]])
     ts = np.linspace(0, en.max(), 23)[1:-1]
     print('resident CTAs over time:', [int(((st <= t) & (en > t)).sum()) for t in ts])
+    dn = env.done.cpu().numpy().astype(bool)
+    print('episode-ending envs: %d of %d; start us p50 %.1f p90 %.1f max %.1f; duration us mean %.1f max %.1f; end us p50 %.1f max %.1f' % (
+        dn.sum(), B, np.percentile(st[dn], 50), np.percentile(st[dn], 90), st[dn].max(), dur[dn].mean(), dur[dn].max(), np.percentile(en[dn], 50), en[dn].max()))
+    print('others: duration us mean %.1f p99 %.1f max %.1f; end us max %.1f' % (dur[~dn].mean(), np.percentile(dur[~dn], 99), dur[~dn].max(), en[~dn].max()))
+    late = np.argsort(en)[-40:]
+    print('last 40 CTAs to end: %d episode-ending; their starts us: %s' % (dn[late].sum(), np.round(np.sort(st[late]), 1).tolist()))
     sm = tl[:, 2].astype(int)
     busy = np.array([en[sm == i].max() for i in np.unique(sm)])
     print('per-SM finish time us: min %.1f mean %.1f max %.1f' % (busy.min(), busy.mean(), busy.max()))
