@@ -180,6 +180,7 @@ struct EnvSmem {
     // per-environment scalars parked here between the phases that need them, so the march
     // loop runs with a small register footprint
     double px, py, th, gx, gy, ppx, ppy, pyaw, pv, pw, act_v, act_w;
+    double th_spec, yaw_spec;  // heading warp 1 assumed for the final pose, and its yaw
     int map, steps, episode, next_pass;
     int next_beam;         // next undealt entry of the survivor list
     int n_alive;           // beams still marching after the head phase
@@ -222,6 +223,103 @@ __device__ __forceinline__ void normal4(uint64_t seed, uint32_t env, uint32_t ep
     __sincosf(6.283185307179586f * u01(r.y), &s0, &c0);
     __sincosf(6.283185307179586f * u01(r.w), &s1, &c1);
     z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
+}
+
+// theta mod 2 pi with the sign of the divisor (numpy's float64 `%`, keti_robot.py:93).  One step
+// turns by far less than 2 pi, so |x| < 4 pi in practice: there fmod is the identity or one
+// exact subtraction (Sterbenz), bit-identical to the library call kept for anything larger.
+__device__ __forceinline__ double wrap_2pi(double x)
+{
+    const double twopi = 6.283185307179586;
+    double r;
+    const double ax = fabs(x);
+    if (ax < twopi) r = x;
+    else if (ax < 2.0 * twopi) r = x < 0 ? __dadd_rn(x, twopi) : __dsub_rn(x, twopi);
+    else r = fmod(x, twopi);
+    if (r != 0 && r < 0) r = __dadd_rn(r, twopi);
+    return r;
+}
+
+// Heading after this step's action (keti_robot.py:86-93); warps 0 and 1 both evaluate it.
+__device__ __forceinline__ double turned_heading(double th0, double w, double dt, double &th1)
+{
+    th1 = __dadd_rn(th0, __dmul_rn(w, dt));
+    return wrap_2pi(th1);
+}
+
+// Per-pass scan setup from the pose in shared memory: float32 lidar pose, origin cell
+// (env.py:386, 419), map geometry.  Run by one thread.
+__device__ __forceinline__ void pass_setup(EnvSmem &sm, const navgym_map_t &m, const navgym_step_args_t &a, int next_beam)
+{
+    sm.lx = (float)sm.px; sm.ly = (float)sm.py; sm.lt = (float)sm.th;
+    sm.ci = xy_to_cell(sm.lx, m.ox, m.res, m.H, a.cell_rule);
+    sm.cj = xy_to_cell(sm.ly, m.oy, m.res, m.W, a.cell_rule);
+    sm.W = m.W; sm.H = m.H; sm.edt_off = m.edt_offset;
+    sm.res32 = (float)m.res;
+    sm.max_range = (float)((double)m.W * (double)m.H);
+    sm.t_stop = fminf(fminf(a.t_stop, sm.max_range), 8.0e6f);
+    sm.n_alive = 0;
+    sm.next_beam = next_beam;
+}
+
+// Tail phase with S survivors per lane in flight, dealt from a shared counter (sm.next_beam
+// starts at S * TPB): a slot whose beam ends takes the next undealt survivor.
+template <int S, int TPB>
+__device__ __forceinline__ void march_tail_slots(EnvSmem &sm, const float *__restrict__ dist, float x0, float y0,
+                                                 int W, int H, float t_stop, int n_alive, int tid)
+{
+    const unsigned FULL = 0xffffffffu;
+    int kb[S];  // the slot's current beam, -1 = none left
+    float t[S], dx[S], dy[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        const int i = s * TPB + tid;
+        kb[s] = i < n_alive ? (int)sm.alive[i] : -1;
+        const int kk = kb[s] >= 0 ? kb[s] : 0;
+        t[s] = __int_as_float(sm.scan[kk]);
+        const float2 dd = sm.dir[kk];
+        dx[s] = dd.x;
+        dy[s] = dd.y;
+    }
+    if (n_alive <= 0) return;
+    for (;;) {
+        float d[S];
+        int cx[S], cy[S];
+        bool inb[S];
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            cx[s] = __float2int_rz(__fmaf_rn(dx[s], t[s], x0));
+            cy[s] = __float2int_rz(__fmaf_rn(dy[s], t[s], y0));
+            inb[s] = ((unsigned)cx[s] < (unsigned)W) & ((unsigned)cy[s] < (unsigned)H);
+            const unsigned idx = (inb[s] & (kb[s] >= 0)) ? (unsigned)(cy[s] * W + cx[s]) : 0u;
+            d[s] = __ldg(dist + idx);
+        }
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            const bool hit = inb[s] & (d[s] <= 0.0f);
+            float tn = __fadd_rn(t[s], fmaxf(__fmul_rn(d[s], 0.999f), 1.0f));
+            const bool fin = !inb[s] | hit | !(tn < t_stop);
+            if (fin & (kb[s] >= 0)) {
+                // absolute hit cell, (y << 16 | x), or -1 for "no hit"
+                sm.scan[kb[s]] = hit ? (cy[s] << 16 | cx[s]) : -1;
+                const int i = atomicAdd(&sm.next_beam, 1);
+                kb[s] = -1;
+                if (i < n_alive) {
+                    const int k = sm.alive[i];
+                    kb[s] = k;
+                    tn = __int_as_float(sm.scan[k]);
+                    const float2 dd = sm.dir[k];
+                    dx[s] = dd.x;
+                    dy[s] = dd.y;
+                }
+            }
+            t[s] = tn;
+        }
+        bool live = false;
+#pragma unroll
+        for (int s = 0; s < S; s++) live |= kb[s] >= 0;
+        if (!__any_sync(FULL, live)) break;
+    }
 }
 
 // One CTA = one environment, WPE warps.  Lane l of warp w owns beams l + 32 (w + WPE i),
@@ -284,14 +382,35 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
 
     PROF_DECL
     // ---------------- prologue (warp 0): state (lane f holds row f), kinematics ----------
+    // Every global load the prologue needs is issued up front (they only depend on e), the map
+    // descriptor as soon as the map id is back, so one L2 round trip overlaps the next and the
+    // float64 kinematics.  Warp 1 meanwhile evaluates the yaw the epilogue will need (the same
+    // heading arithmetic as warp 0): for every environment that neither rolls back nor resets,
+    // the float64 sincos + atan2 of the final heading leave the critical path.
+    if (WPE > 1 && warp == 1) {
+        double th = ST(NAVGYM_S_TH);
+        if (!IS_RESET_KERNEL) {
+            double th1;
+            th = turned_heading(th, (double)a.actions[2 * (size_t)e + 1], a.dt, th1);
+        }
+        double sn, cn;
+        sincos(th, &sn, &cn);
+        const double yaw = atan2(sn, cn);  // utils.py:5-9
+        if (lane == 0) { sm.th_spec = th; sm.yaw_spec = yaw; }
+    }
     if (warp == 0) {
         double sv = lane < NAVGYM_NS ? ST(lane) : 0.0;
+        int steps = a.steps[e];
+        const int map0 = a.map_id[e];
+        const int episode0 = a.episodes ? a.episodes[e] : 0;
+        const float noise_std0 = a.noise_std ? a.noise_std[e] : 0.0f;
+        float2 av = make_float2(0.f, 0.f);
+        if (!IS_RESET_KERNEL) av = *reinterpret_cast<const float2 *>(a.actions + 2 * (size_t)e);
+        const navgym_map_t m0 = a.maps[map0];
         double px = __shfl_sync(FULL, sv, NAVGYM_S_PX), py = __shfl_sync(FULL, sv, NAVGYM_S_PY);
         double th0 = __shfl_sync(FULL, sv, NAVGYM_S_TH), th = th0;
         double act_v = 0, act_w = 0;
-        int steps = a.steps[e];
         if (!IS_RESET_KERNEL) {
-            const float2 av = *reinterpret_cast<const float2 *>(a.actions + 2 * (size_t)e);
             double v = (double)av.x, w = (double)av.y;
             if (a.min_turn_radius > 0) {  // env.py:595-600
                 double lim = __dmul_rn(fabs(w), a.min_turn_radius);
@@ -300,7 +419,8 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
             }
             act_v = a.min_turn_radius > 0 ? v : (double)av.x;  // env.py:725 (the clamp edits `action`)
             act_w = (double)av.y;
-            double th1 = __dadd_rn(th0, __dmul_rn(w, a.dt));
+            double th1;
+            th = turned_heading(th0, w, a.dt, th1);
             double s_, c_;
             sincos(lane == 0 ? th0 : th1, &s_, &c_);  // lanes 0 / 1 in parallel
             double s0 = __shfl_sync(FULL, s_, 0), c0 = __shfl_sync(FULL, c_, 0);
@@ -312,21 +432,9 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
             ry = __dadd_rn(ry, __dmul_rn(__dmul_rn(s1, v), a.dt));
             px = __dadd_rn(__dmul_rn(-0.14474, c1), rx);
             py = __dadd_rn(__dmul_rn(-0.14474, s1), ry);
-            const double twopi = 6.283185307179586;
-            th = fmod(th1, twopi);
-            if (th != 0 && th < 0) th = __dadd_rn(th, twopi);
             steps += 1;  // env.py:592
         } else {
             steps = 0;
-        }
-        if (lane == 0) {
-            sm.px = px; sm.py = py; sm.th = th;
-            sm.act_v = act_v; sm.act_w = act_w;
-            sm.map = a.map_id[e];
-            sm.steps = steps;
-            sm.episode = a.episodes ? a.episodes[e] : 0;
-            sm.noise_std = a.noise_std ? a.noise_std[e] : 0.0f;
-            if (IS_RESET_KERNEL) { sm.ppx = px; sm.ppy = py; sm.pyaw = 0; sm.pv = 0; sm.pw = 0; }
         }
         if (lane == NAVGYM_S_GX) sm.gx = sv;
         if (lane == NAVGYM_S_GY) sm.gy = sv;
@@ -337,6 +445,17 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
             if (lane == NAVGYM_S_PV) sm.pv = sv;
             if (lane == NAVGYM_S_PW) sm.pw = sv;
         }
+        if (lane == 0) {
+            sm.px = px; sm.py = py; sm.th = th;
+            sm.act_v = act_v; sm.act_w = act_w;
+            sm.map = map0;
+            sm.steps = steps;
+            sm.episode = episode0;
+            sm.noise_std = noise_std0;
+            if (IS_RESET_KERNEL) { sm.ppx = px; sm.ppy = py; sm.pyaw = 0; sm.pv = 0; sm.pw = 0; }
+            if (WPE == 1) sm.th_spec = CUDART_NAN;
+            pass_setup(sm, m0, a, TPB * MARCH_SLOTS);  // first pass: the map descriptor is already here
+        }
     }
     const int nd = a.discs ? min(a.ndisc[e], a.max_disc) : 0;
     const int ns = a.segs ? min(a.nseg[e], a.max_seg) : 0;
@@ -345,25 +464,16 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
 
     long long t_pass = t_begin;  // start of the pass that produces the returned observation
     float margin = CUDART_INF_F; // its smallest clearance over the crash thresholds [m]
-    for (;;) {
-        // ---- per-pass setup: float32 lidar pose, origin cell (env.py:386, 419)
+    for (bool first = true;; first = false) {
+        // ---- per-pass setup; the first pass was set up by the prologue
         if (WPE > 1) __syncthreads(); else __syncwarp();
-        if (!IS_RESET_KERNEL && pass != PASS_STEP) t_pass = clock64();
+        if (!first) {
+            t_pass = clock64();
+            if (tid == 0) pass_setup(sm, a.maps[sm.map], a, TPB * MARCH_SLOTS);
+            if (WPE > 1) __syncthreads(); else __syncwarp();
+        }
         margin = CUDART_INF_F;
         PROF_MARK(0);
-        if (tid == 0) {
-            const navgym_map_t m = a.maps[sm.map];
-            sm.lx = (float)sm.px; sm.ly = (float)sm.py; sm.lt = (float)sm.th;
-            sm.ci = xy_to_cell(sm.lx, m.ox, m.res, m.H, a.cell_rule);
-            sm.cj = xy_to_cell(sm.ly, m.oy, m.res, m.W, a.cell_rule);
-            sm.W = m.W; sm.H = m.H; sm.edt_off = m.edt_offset;
-            sm.res32 = (float)m.res;
-            sm.max_range = (float)((double)m.W * (double)m.H);
-            sm.t_stop = fminf(fminf(a.t_stop, sm.max_range), 8.0e6f);
-            sm.next_beam = TPB * MARCH_SLOTS;
-            sm.n_alive = 0;
-        }
-        if (WPE > 1) __syncthreads(); else __syncwarp();
         const float lx = sm.lx, ly = sm.ly, lt = sm.lt;
         PROF_MARK(1);
         // ---- occupancy-grid march (env.py:425-426).
@@ -480,60 +590,9 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
                         }
                     }
                 } else {
-                int kb[MARCH_SLOTS];  // the slot's current beam, -1 = none left
-                    float t[MARCH_SLOTS], dx[MARCH_SLOTS], dy[MARCH_SLOTS];
-#pragma unroll
-                    for (int s = 0; s < MARCH_SLOTS; s++) {
-                        const int i = s * TPB + tid;
-                        kb[s] = i < n_alive ? (int)sm.alive[i] : -1;
-                        const int kk = kb[s] >= 0 ? kb[s] : 0;
-                        t[s] = __int_as_float(sm.scan[kk]);
-                        const float2 dd = sm.dir[kk];
-                        dx[s] = dd.x;
-                        dy[s] = dd.y;
-                    }
-                    if (n_alive > 0) {
-                        for (;;) {
-                            float d[MARCH_SLOTS];
-                            int cx[MARCH_SLOTS], cy[MARCH_SLOTS];
-                            bool inb[MARCH_SLOTS];
-#pragma unroll
-                            for (int s = 0; s < MARCH_SLOTS; s++) {
-                                cx[s] = __float2int_rz(__fmaf_rn(dx[s], t[s], x0));
-                                cy[s] = __float2int_rz(__fmaf_rn(dy[s], t[s], y0));
-                                inb[s] = ((unsigned)cx[s] < (unsigned)W) & ((unsigned)cy[s] < (unsigned)H);
-                                const unsigned idx = (inb[s] & (kb[s] >= 0)) ? (unsigned)(cy[s] * W + cx[s]) : 0u;
-                                d[s] = __ldg(dist + idx);
-                            }
-#pragma unroll
-                            for (int s = 0; s < MARCH_SLOTS; s++) {
-                                const bool hit = inb[s] & (d[s] <= 0.0f);
-                                float tn = __fadd_rn(t[s], fmaxf(__fmul_rn(d[s], 0.999f), 1.0f));
-                                const bool fin = !inb[s] | hit | !(tn < t_stop);
-                                if (fin & (kb[s] >= 0)) {
-                                    // absolute hit cell, (y << 16 | x), or -1 for "no hit"
-                                    sm.scan[kb[s]] = hit ? (cy[s] << 16 | cx[s]) : -1;
-                                    const int i = atomicAdd(&sm.next_beam, 1);
-                                    kb[s] = -1;
-                                    if (i < n_alive) {
-                                        const int k = sm.alive[i];
-                                        kb[s] = k;
-                                        tn = __int_as_float(sm.scan[k]);
-                                        const float2 dd = sm.dir[k];
-                                        dx[s] = dd.x;
-                                        dy[s] = dd.y;
-                                    }
-                                }
-                                t[s] = tn;
-                            }
-                            bool live = false;
-#pragma unroll
-                            for (int s = 0; s < MARCH_SLOTS; s++) live |= kb[s] >= 0;
-                            if (!__any_sync(FULL, live)) break;
-                        }
-                    }
-            }
+                    march_tail_slots<MARCH_SLOTS, TPB>(sm, dist, x0, y0, W, H, t_stop, n_alive, tid);
                 }
+            }
             if (WPE > 1) __syncthreads(); else __syncwarp();
             // ranges (env.py:426), all lanes active: sqrt(di^2 + dj^2) * resolution
             const bool rec = pass == (IS_RESET_KERNEL ? PASS_RESET : PASS_STEP) && a.hits;
@@ -735,11 +794,38 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
     }
 
     PROF_MARK(6);
+    // File this environment under its cost class for the next step: the cycles its last scan
+    // took (an auto-reset first scan is taken at the pose the next step starts from), doubled
+    // when the next step is likely to end the episode and run a second scan -- the robot is
+    // within one step of a crash threshold, of the goal, or of the step limit.  Such
+    // environments then start first instead of stretching the end of the launch.  The slot in
+    // the class list is claimed here and filled in at the very end, so the atomic's round trip
+    // overlaps the epilogue.
+    int sched_pos = 0, sched_b = 0;
+    if (sched_cnt) {
+        bool risky = margin < NAVGYM_RISK_MARGIN;
+        if (tid == 0) {
+            const double gx = sm.gx - sm.px, gy = sm.gy - sm.py;
+            risky |= gx * gx + gy * gy < (a.dist_thresh + NAVGYM_RISK_MARGIN) * (a.dist_thresh + NAVGYM_RISK_MARGIN);
+            risky |= a.max_episode_steps > 0 && sm.steps + 1 >= a.max_episode_steps;
+        }
+        risky = (WPE > 1 ? __syncthreads_or(risky) : __any_sync(FULL, risky)) && a.auto_reset;
+        if (tid == 0) {
+            const long long kc = ((clock64() - t_pass) << (risky ? 1 : 0)) >> 13;
+            sched_b = NAVGYM_SCHED_BUCKETS - 1 - (int)(kc > NAVGYM_SCHED_BUCKETS - 1 ? NAVGYM_SCHED_BUCKETS - 1 : kc);
+            sched_pos = atomicAdd(&sched_cnt[sched_b], 1);
+        }
+    }
     // ---------------- epilogue (warp 0): observation tail + state (env.py:455, 725-727) ---
     if (warp == 0) {
-        double sn, cn;
-        sincos(sm.th, &sn, &cn);
-        const double yaw = atan2(sn, cn);  // utils.py:5-9
+        double yaw;
+        if (WPE > 1 && sm.th_spec == sm.th) {
+            yaw = sm.yaw_spec;  // warp 1 had the final heading right
+        } else {
+            double sn, cn;
+            sincos(sm.th, &sn, &cn);
+            yaw = atan2(sn, cn);  // utils.py:5-9
+        }
         double tv = 0.0;
         switch (lane) {
         case 0: tv = sm.ppx; break;
@@ -775,26 +861,7 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
             if (a.noise_std) a.noise_std[e] = sm.noise_std;
         }
     }
-    if (sched_cnt) {
-        // File this environment under its cost class for the next step: the cycles its last
-        // scan took (an auto-reset first scan is taken at the pose the next step starts from),
-        // doubled when the next step is likely to end the episode and run a second scan -- the
-        // robot is within one step of a crash threshold, of the goal, or of the step limit.
-        // Such environments then start first instead of stretching the end of the launch.
-        bool risky = margin < NAVGYM_RISK_MARGIN;
-        if (tid == 0) {
-            const double gx = sm.gx - sm.px, gy = sm.gy - sm.py;
-            risky |= gx * gx + gy * gy < (a.dist_thresh + NAVGYM_RISK_MARGIN) * (a.dist_thresh + NAVGYM_RISK_MARGIN);
-            risky |= a.max_episode_steps > 0 && sm.steps + 1 >= a.max_episode_steps;
-        }
-        risky = (WPE > 1 ? __syncthreads_or(risky) : __any_sync(FULL, risky)) && a.auto_reset;
-        if (tid == 0) {
-            const long long kc = ((clock64() - t_pass) << (risky ? 1 : 0)) >> 13;
-            const int b = NAVGYM_SCHED_BUCKETS - 1 - (int)(kc > NAVGYM_SCHED_BUCKETS - 1 ? NAVGYM_SCHED_BUCKETS - 1 : kc);
-            const int pos = atomicAdd(&sched_cnt[b], 1);
-            sched_list[(size_t)b * B + pos] = e;
-        }
-    }
+    if (sched_cnt && tid == 0) sched_list[(size_t)sched_b * B + sched_pos] = e;
     PROF_MARK(7);
 #ifdef NAVGYM_PROFILE
     if (tid == 0 && a.tail64) {  // CTA timeline (global ns clock, SM id) for tail analysis
@@ -1090,6 +1157,7 @@ int navgym_step_batch(const navgym_step_args_t *args, void *stream)
 // graph and replayed with one cudaGraphLaunch while those stay the same.
 struct navgym_group_graph {
     cudaGraphExec_t exec;
+    int kernels;            // kernel nodes in the graph
     navgym_step_args_t key;
     const void *host[4];
 };
@@ -1241,6 +1309,7 @@ int navgym_step_batch_host_submit(navgym_host_pipe_t *p, const navgym_step_args_
         CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         const uint64_t launches = g_launches;
         int err = enqueue_group(a, st, actions_host, obs_host, reward_host, done_host, true);
+        g.kernels = (int)(g_launches - launches);
         g_launches = launches;  // captured, not launched
         cudaError_t cap = cudaStreamEndCapture(st, &graph);
         if (err || cap != cudaSuccess) {
@@ -1254,7 +1323,7 @@ int navgym_step_batch_host_submit(navgym_host_pipe_t *p, const navgym_step_args_
         memcpy(g.host, host, sizeof(host));
     }
     CK(cudaGraphLaunch(g.exec, st));
-    g_launches++;
+    g_launches += g.kernels;
     return 0;
 }
 
