@@ -341,7 +341,7 @@ def main():
 
 # dram__bytes_read.sum + dram__bytes_write.sum of step_kernel<false> per launch, from the
 # `ncu --set full` capture summarised in profiles/ (None until measured).
-TRAFFIC_BYTES_PER_LAUNCH = 3185664  # profiles/r1_step_kernel_ncu_full_summary.txt
+TRAFFIC_BYTES_PER_LAUNCH = 3193600  # profiles/r1_step_kernel_ncu_full_summary.txt
 
 if __name__ == '__main__':
     main()
