@@ -320,6 +320,14 @@ def main():
                      "algorithmic_bytes_per_launch": B * BYTES_PER_ENV_STEP,
                      "kernel_ms": kernel_ms,
                      "note": "latency/issue-bound gather kernel: see DESIGN.md roofline section"},
+        # second ceiling (SURVEY 8d ii): every march sample is one dependent 4-byte gather from the
+        # L2-resident EDT; the peak is the dependent-random-gather rate tools/gather_peak.cu measured
+        # on this pool's B200 at the kernel's launch shape (profiles/r1_gather_peak.txt)
+        "roofline_gather": {"bound": "l2-gather", "achieved": B * GATHERS_PER_ENV_STEP / (kernel_ms * 1e-3) / 1e9,
+                            "peak": GATHER_PEAK_G, "unit": "G gathers/s",
+                            "frac": B * GATHERS_PER_ENV_STEP / (kernel_ms * 1e-3) / 1e9 / GATHER_PEAK_G,
+                            "gathers_per_env_step": GATHERS_PER_ENV_STEP,
+                            "peak_source": "tools/gather_peak.cu on B200, 4 MB table, 64 warps/SM (profiles/r1_gather_peak.txt)"},
         "e2e": {"value": world * B * Ke / (e2e_ms * 1e-3), "unit": "env-steps/s",
                 "h2d_bytes_per_step": B * 2 * 4, "d2h_bytes_per_step": B * ((NB + 7) * 4 + 4 + 1),
                 "steps": Ke, "timing": "host wall clock, max over ranks",
@@ -342,6 +350,10 @@ def main():
 # dram__bytes_read.sum + dram__bytes_write.sum of step_kernel<false> per launch, from the
 # `ncu --set full` capture summarised in profiles/ (None until measured).
 TRAFFIC_BYTES_PER_LAUNCH = 3193600  # profiles/r1_step_kernel_ncu_full_summary.txt
+# EDT gathers per env-step on the bench world: 512 beams x 6.94 march samples per ray
+# (oracle/analysis/march_stats.py, first sample shared per scan) x 1.01 scans per step.
+GATHERS_PER_ENV_STEP = 3590
+GATHER_PEAK_G = 700.0  # profiles/r1_gather_peak.txt
 
 if __name__ == '__main__':
     main()

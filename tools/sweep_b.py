@@ -21,4 +21,4 @@ for B in [int(x) for x in sys.argv[1:]] or [1184, 2368, 3552, 4096, 4736, 8192, 
     for i in range(n): env.step(bank[i % 16])
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
-    print('B=%6d  %.4f ms/step  %.2f M env-steps/s  %.1f ns/env' % (B, ms, B / ms / 1e3, ms * 1e6 / B))
+    print('B=%6d  %.4f ms/step  %.2f M env-steps/s  %.1f ns/env   obs checksum %.6f' % (B, ms, B / ms / 1e3, ms * 1e6 / B, float(env.obs.double().sum())))
