@@ -188,6 +188,34 @@ typedef struct {
 } navgym_peds_args_t;
 int navgym_peds_advance(const navgym_peds_args_t *args, void *stream);
 
+/* ---- lidar of the simulated pedestrians: _convert_obs(human, [robot] + other humans,
+ * add_scan_noise=False, lidar_legs=False) (env.py:683-693, 808-815) for every pedestrian of
+ * every environment in one launch.  Agent n = (environment n / agents_per_env, slot n %
+ * agents_per_env); each casts K beams lin[k] + float32(theta) from float32(x, y) through its
+ * environment's map (env.py:386-426), min-merges the closed footprints of the other agents
+ * (segs of its environment, minus its own [skip_first, +skip_count)), clips to [0, range_max]
+ * (env.py:435).  No noise.  ranges[n][k] of slots >= nagent[env] are left untouched. */
+typedef struct {
+    int32_t num_envs, agents_per_env;
+    int32_t num_beams;           /* K (human.py:16: 512) */
+    int32_t max_seg;             /* segment slots per environment */
+    int32_t cell_rule, _pad;
+    float range_max;             /* metres (human.py:15: 6.0) */
+    float t_stop;                /* march cut-off in cells, as navgym_step_args_t.t_stop */
+    const navgym_map_t *maps;
+    const float *edt_pool;
+    const int32_t *map_id;       /* [num_envs] */
+    const int32_t *nagent;       /* [num_envs] live slots, or NULL = agents_per_env */
+    const double *pose;          /* [num_envs][agents_per_env][3] x, y, theta */
+    const double *lin;           /* [K] beam angles before the heading is added */
+    const float *segs;           /* [num_envs][max_seg][4] ax, ay, bx, by */
+    const int32_t *nseg;         /* [num_envs] */
+    const int32_t *skip;         /* [num_envs][agents_per_env][2] first, count; or NULL */
+    float *ranges;               /* [num_envs][agents_per_env][K] out */
+} navgym_scan_args_t;
+int navgym_agent_scan_batch(const navgym_scan_args_t *args, void *stream);
+int navgym_sizeof_scan_args(void);
+
 /* ---- inner native boundary: range_libc --------------------------------------------- */
 /* PyOMap(bool[H,W]) + PyRayMarching(omap, max_range) (env.py:337-340): exact Euclidean
  * distance transform of occ_dev (u8, non-zero = occupied, [H][W], row = y) into dist_dev. */

@@ -95,6 +95,14 @@ class HerArgs(C.Structure):
                 ('done', _P), ('is_success', _P), ('is_crash', _P), ('distance', _P)]
 
 
+class ScanArgs(C.Structure):
+    _fields_ = [('num_envs', C.c_int32), ('agents_per_env', C.c_int32), ('num_beams', C.c_int32),
+                ('max_seg', C.c_int32), ('cell_rule', C.c_int32), ('_pad', C.c_int32),
+                ('range_max', C.c_float), ('t_stop', C.c_float),
+                ('maps', _P), ('edt_pool', _P), ('map_id', _P), ('nagent', _P), ('pose', _P),
+                ('lin', _P), ('segs', _P), ('nseg', _P), ('skip', _P), ('ranges', _P)]
+
+
 PED_F = 16
 
 
@@ -114,6 +122,7 @@ EXPORTS = [
     'navgym_error_string', 'navgym_device_count', 'navgym_abi_version', 'navgym_launch_count',
     'navgym_sizeof_step_args', 'navgym_sizeof_map', 'navgym_grid_bfs',
     'navgym_sizeof_her_args', 'navgym_sizeof_peds_args', 'navgym_compute_rewards', 'navgym_peds_advance',
+    'navgym_agent_scan_batch', 'navgym_sizeof_scan_args',
 ]
 
 _lib = None
@@ -162,9 +171,11 @@ def load():
     lib.navgym_launch_count.restype = C.c_uint64
     lib.navgym_compute_rewards.argtypes = [C.POINTER(HerArgs), _P]
     lib.navgym_peds_advance.argtypes = [C.POINTER(PedsArgs), _P]
+    lib.navgym_agent_scan_batch.argtypes = [C.POINTER(ScanArgs), _P]
     if (lib.navgym_sizeof_step_args() != C.sizeof(StepArgs) or lib.navgym_sizeof_map() != C.sizeof(MapT)
             or lib.navgym_sizeof_her_args() != C.sizeof(HerArgs)
-            or lib.navgym_sizeof_peds_args() != C.sizeof(PedsArgs)):
+            or lib.navgym_sizeof_peds_args() != C.sizeof(PedsArgs)
+            or lib.navgym_sizeof_scan_args() != C.sizeof(ScanArgs)):
         raise RuntimeError('libnavgym_b200.so ABI mismatch with nav_gym_b200/_lib.py (rebuild)')
     _lib = lib
     return lib

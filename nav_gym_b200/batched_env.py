@@ -334,6 +334,38 @@ class BatchedNavGym(object):
         if p is not None:
             self.lib.navgym_host_pipe_destroy(p[0])
 
+    # ---- host export of one environment --------------------------------
+    def export_env(self, i):
+        """Copy environment `i` back to the attribute surface ros_env.py and render read from a
+        NavGymEnv (ros_env.py:69-176): map_info, robot.{px,py,theta,gx,gy,...}, humans[...],
+        prev_obs (the dict form of its last observation row), num_scan_stack, steps_since_reset.
+        Synchronises the device; a debugging aid, not part of the step path."""
+        from types import SimpleNamespace
+        from .robot import Human
+        torch.cuda.synchronize(self.device)
+        st = self.state[:, i].cpu().numpy()
+        m = self.pool.maps[int(self.map_id[i].item())]
+        robot = KetiRobot(float(st[_lib.S_PX]), float(st[_lib.S_PY]), float(st[_lib.S_TH]),
+                          float(st[_lib.S_GX]), float(st[_lib.S_GY]), self.args.dt)
+        robot.v, robot.r = float(st[_lib.S_PV]), float(st[_lib.S_PW])
+        robot.vx, robot.vy = robot.v * np.cos(robot.theta), robot.v * np.sin(robot.theta)
+        humans = []
+        if self.peds is not None:
+            n = int(self.nped[i].item()) if getattr(self, 'nped', None) is not None else self.peds.shape[1]
+            for row in self.peds[i, :n].cpu().numpy():
+                tgt = row[6:8] if row[8] > 0.5 else row[4:6]
+                h = Human(float(row[0]), float(row[1]), float(row[2]), float(tgt[0]), float(tgt[1]), self.args.dt)
+                h.v, h.has_legs = float(row[3]), bool(row[12] > 0.5)
+                h.vx, h.vy = h.v * np.cos(h.theta), h.v * np.sin(h.theta)
+                humans.append(h)
+        nscan = self.num_scan_stack * NB
+        tail = self.tail64[i].cpu().numpy()
+        obs = {'observation': np.concatenate([self.obs[i, :nscan].double().cpu().numpy(), tail]),
+               'achieved_goal': tail[2:4].copy(), 'desired_goal': np.array([robot.gx, robot.gy])}
+        return SimpleNamespace(map_info=m, robot=robot, humans=humans, prev_obs=obs,
+                               num_scan_stack=self.num_scan_stack,
+                               steps_since_reset=int(self.steps[i].item()))
+
     # ---- HER batch API (env.py:491-589) on device tensors ---------------------------------
     def compute_rewards(self, obs, goals, **reward):
         """compute_rewards / compute_terminals / compute_info for stored observations:

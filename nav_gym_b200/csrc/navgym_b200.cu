@@ -930,6 +930,45 @@ __global__ void __launch_bounds__(256) her_kernel(const navgym_her_args_t a)
     }
 }
 
+// ------------------------------------------------------------------ pedestrian lidar
+// The scan every simulated pedestrian takes of its surroundings (env.py:683-693): map raycast
+// from its own pose + the closed footprints of the robot and the other pedestrians, clipped,
+// no noise.  One CTA per agent, threads across beams; the same canonical march / segment
+// arithmetic as the robot's scan.
+__global__ void __launch_bounds__(128) agent_scan_kernel(const navgym_scan_args_t a)
+{
+    const int n = blockIdx.x;
+    const int e = n / a.agents_per_env, slot = n - e * a.agents_per_env;
+    if (a.nagent && slot >= a.nagent[e]) return;
+    const double *p = a.pose + (size_t)n * 3;
+    const float lx = (float)p[0], ly = (float)p[1], lt = (float)p[2];  // env.py:386
+    const navgym_map_t m = a.maps[a.map_id[e]];
+    const float *dist = a.edt_pool + m.edt_offset;
+    const int ci = xy_to_cell(lx, m.ox, m.res, m.H, a.cell_rule);
+    const int cj = xy_to_cell(ly, m.oy, m.res, m.W, a.cell_rule);
+    const float max_range = (float)((double)m.W * (double)m.H);
+    const float t_stop = a.t_stop > 0.0f ? fminf(a.t_stop, max_range) : max_range;
+    const float res32 = (float)m.res;
+    const int ns = a.nseg ? min(a.nseg[e], a.max_seg) : 0;
+    const float4 *segs = reinterpret_cast<const float4 *>(a.segs) + (size_t)e * a.max_seg;
+    int s0 = -1, s1 = -1;
+    if (a.skip) { s0 = a.skip[2 * (size_t)n]; s1 = s0 + a.skip[2 * (size_t)n + 1]; }
+    for (int k = threadIdx.x; k < a.num_beams; k += blockDim.x) {
+        const float h = (float)__dadd_rn(a.lin[k], (double)lt);
+        double sd, cd;
+        dir_sincos((double)h, sd, cd);
+        const float dx = (float)cd, dy = (float)sd;
+        int hx, hy;
+        float r = __fmul_rn(march(dist, m.W, m.H, (float)ci, (float)cj, dx, dy, max_range, t_stop, hx, hy), res32);
+        for (int s = 0; s < ns; s++) {
+            if (s >= s0 && s < s1) continue;
+            const float4 sg = __ldg(segs + s);
+            r = fminf(r, seg_hit(lx, ly, dx, dy, sg.x, sg.y, sg.z, sg.w));
+        }
+        a.ranges[(size_t)n * a.num_beams + k] = fminf(fmaxf(r, 0.0f), a.range_max);
+    }
+}
+
 // ------------------------------------------------------------------ scripted pedestrians
 // Pedestrian motion + geometry for the batched simulator (scripted stand-in
 // for the reference's CNN-driven humans whose weights are absent): each pedestrian walks
@@ -1356,6 +1395,17 @@ int navgym_peds_advance(const navgym_peds_args_t *args, void *stream)
 {
     if (args->num_envs <= 0) return 0;
     peds_advance_kernel<<<(args->num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*args);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
+
+int navgym_sizeof_scan_args(void) { return (int)sizeof(navgym_scan_args_t); }
+
+int navgym_agent_scan_batch(const navgym_scan_args_t *args, void *stream)
+{
+    if (args->num_envs <= 0 || args->agents_per_env <= 0) return 0;
+    if (args->num_beams <= 0 || !args->pose || !args->lin || !args->ranges) return (int)cudaErrorInvalidValue;
+    agent_scan_kernel<<<args->num_envs * args->agents_per_env, 128, 0, (cudaStream_t)stream>>>(*args);
     g_launches++;
     return (int)cudaGetLastError();
 }

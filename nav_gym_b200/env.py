@@ -288,7 +288,11 @@ class NavGymEnv(gym.Env, EzPickle):
                 'distance': np.float64(out['distance'][0])}
 
     def render(self, mode='human'):
-        raise NotImplementedError('render is outside the hot-path scope (SURVEY §2)')
+        """Debug view (env.py:833-1058): 'human' opens the cv2 window, 'rgb_array' returns it."""
+        from .render import render
+        if self.map_info is None:
+            raise RuntimeError('reset() the environment first')
+        return render(self, mode)
 
 
 def register_env():

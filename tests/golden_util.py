@@ -10,8 +10,30 @@ NB = 512
 
 
 def trace_names():
+    """the robot-step traces (humans_*.npz hold the pedestrian pipeline, see human_trace_names)"""
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, '*.npz'))
-                  if not p.endswith('known_answers.npz'))
+                  if not p.endswith('known_answers.npz') and not os.path.basename(p).startswith('humans_'))
+
+
+def human_trace_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, 'humans_*.npz')))
+
+
+def human_env_segments(G, t):
+    """Step t of a humans_* trace -> (segs [S, 4], skip [P, 2]): the environment's segment list
+    [robot | pedestrian 0 | pedestrian 1 ...] (5 per closed footprint, as the reference's
+    contours carry them) and, per pedestrian, its own slice to leave out.  Rebuilt from the
+    per-pedestrian lists the reference handed to render_contours_in_lidar
+    ([robot] + the other pedestrians, env.py:683-688)."""
+    P = G['segs_out'].shape[1]
+    polys = [G['segs_out'][t, 0, :5]]
+    for j in range(P):
+        src = 1 if j == 0 else 0          # a list that contains pedestrian j
+        k = j if j > src else j + 1       # its position among that list's pedestrians, 1-based
+        polys.append(G['segs_out'][t, src, 5 * k:5 * k + 5])
+    segs = np.concatenate(polys).astype(np.float32)
+    skip = np.array([[5 * (1 + j), 5] for j in range(P)], np.int32)
+    return segs, skip
 
 
 def load(name):

@@ -69,6 +69,20 @@ def test_gym_make_dropin_contract():
         if done:
             break
     assert abs(env.robot.px - obs['achieved_goal'][0]) < 1e-12
+    # the batch's host export carries the same attribute surface, and the
+    # debug view draws from either
+    view = env._sim.export_env(0)
+    assert view.map_info is env.map_info and view.num_scan_stack == env.num_scan_stack
+    assert (view.robot.px, view.robot.py, view.robot.theta) == (env.robot.px, env.robot.py, env.robot.theta)
+    assert (view.robot.gx, view.robot.gy) == (env.robot.gx, env.robot.gy)
+    assert len(view.humans) == len(env.humans)
+    assert all((a.px, a.py, a.theta) == (b.px, b.py, b.theta) for a, b in zip(view.humans, env.humans))
+    assert np.array_equal(view.prev_obs['observation'], env.prev_obs['observation'])
+    assert view.steps_since_reset == env.steps_since_reset
+    img = env.render(mode='rgb_array')
+    assert img.shape == (800, 800, 3) and img.dtype == np.uint8
+    from nav_gym_b200.render import render
+    assert np.array_equal(render(view, 'rgb_array'), img)
 
 
 def test_pedestrian_kernel():

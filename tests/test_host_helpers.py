@@ -75,3 +75,30 @@ def test_footprint_helpers():
     assert segs.shape == (4, 4) and np.allclose(segs[-1, 2:], segs[0, :2])
     d = robot.legs_to_discs([1, 2, 0.5], [0, 0, 0])
     assert d.shape == (2, 3) and np.allclose(d[:, 2], 0.03)
+
+
+def test_render_draws_the_attribute_surface():
+    """render.draw needs only the host attribute surface: map, robot,
+    humans, last observation.  The goal square, the robot arrow and the lidar returns land on
+    the cells the reference's xy_to_ij would give."""
+    from types import SimpleNamespace
+    from nav_gym_b200 import maps
+    from nav_gym_b200.render import draw, render
+    from nav_gym_b200.robot import KetiRobot, Human, beam_table
+    m = maps.create_outdoor_map(0, 0.5, np.random.RandomState(0))
+    robot = KetiRobot(5.0, 6.0, 0.5, 15.0, 14.0, 0.2)
+    h = Human(8.0, 8.0, 1.0, 9.0, 9.0, 0.2)
+    scan = np.full(512, 25.0)
+    scan[256] = 2.0  # the forward beam returns at 2 m
+    obs = {'observation': np.concatenate([scan, np.zeros(7)])}
+    view = SimpleNamespace(map_info=m, robot=robot, humans=[h], prev_obs=obs, num_scan_stack=1)
+    img = draw(view, size=m['width'])  # one pixel per cell
+    assert img.shape == (m['height'], m['width'], 3)
+    gi, gj = int(15.0 / 0.05), int(14.0 / 0.05)
+    assert tuple(img[gj, gi]) == (0.0, 0.0, 1.0)                       # goal square
+    a = beam_table()[256] + robot.theta
+    hi, hj = int((5.0 + 2.0 * np.cos(a)) / 0.05), int((6.0 + 2.0 * np.sin(a)) / 0.05)
+    assert tuple(img[hj, hi]) == (1.0, 0.0, 1.0)                       # the lidar return
+    assert tuple(img[int(6.0 / 0.05), int(5.0 / 0.05)]) == (1.0, 0.0, 0.0)  # robot arrow base
+    out = render(view, 'rgb_array')
+    assert out.shape == (800, 800, 3) and out.dtype == np.uint8
