@@ -216,6 +216,46 @@ typedef struct {
 int navgym_agent_scan_batch(const navgym_scan_args_t *args, void *stream);
 int navgym_sizeof_scan_args(void);
 
+/* ---- pedestrian route following (env.py:633-645 waypoints, :666-680 new goal on arrival).
+ * The reference plans an A* path on the 0.25 m cost map (env.py:312-332, 343-354) per
+ * pedestrian and walks its waypoints (spaced > 2 m, popped within 1 m).  On the device each
+ * map carries num_goals geodesic distance fields over that cost map (one per candidate goal,
+ * u16 cells, 65535 = unreachable); following a field downhill is a shortest path, so the
+ * waypoint 2 m further along it is found without a path object, and a new goal is a new field
+ * id.  One thread per pedestrian:
+ *   1. within 0.5 m of its goal: draw a new goal (Philox; reachable from here, farther than
+ *      min_goal_dist) -- kept as is when none of 4 draws qualifies, like the reference when
+ *      its planner fails;
+ *   2. waypoint missing or within 1 m: advance it along the field until > 2 m away (or the goal);
+ *   3. emit the waypoint (world) and the local goal the policy sees (env.py:641-645). */
+typedef struct {
+    int32_t W, H;             /* planning grid */
+    int32_t num_goals, _pad;
+    int64_t field_offset;     /* into fields, u16 elements: [num_goals][H][W] */
+    int64_t goal_offset;      /* into goals, rows of 2 doubles */
+    double ox, oy, res;
+} navgym_plan_map_t;
+typedef struct {
+    int32_t num_envs, max_ped;
+    int32_t step;             /* RNG stream position: advance by one per call */
+    int32_t _pad;
+    uint64_t seed;
+    int64_t env_offset;       /* global id of environment 0 (multi-GPU shards) */
+    double min_goal_dist;     /* env.py:669: 10 m */
+    const navgym_plan_map_t *maps;
+    const uint16_t *fields;
+    const double *goals;
+    const int32_t *map_id;    /* [num_envs] */
+    const int32_t *nped;      /* [num_envs] or NULL */
+    const double *pose;       /* [num_envs][max_ped][3] */
+    int32_t *goal_id;         /* [num_envs][max_ped] in/out */
+    double *waypoint;         /* [num_envs][max_ped][2] in/out, NaN = none yet */
+    float *goal_local;        /* [num_envs][max_ped][2] out */
+} navgym_plan_args_t;
+int navgym_peds_plan(const navgym_plan_args_t *args, void *stream);
+int navgym_sizeof_plan_args(void);
+int navgym_sizeof_plan_map(void);
+
 /* ---- inner native boundary: range_libc --------------------------------------------- */
 /* PyOMap(bool[H,W]) + PyRayMarching(omap, max_range) (env.py:337-340): exact Euclidean
  * distance transform of occ_dev (u8, non-zero = occupied, [H][W], row = y) into dist_dev. */

@@ -103,6 +103,19 @@ class ScanArgs(C.Structure):
                 ('lin', _P), ('segs', _P), ('nseg', _P), ('skip', _P), ('ranges', _P)]
 
 
+class PlanMapT(C.Structure):
+    _fields_ = [('W', C.c_int32), ('H', C.c_int32), ('num_goals', C.c_int32), ('_pad', C.c_int32),
+                ('field_offset', C.c_int64), ('goal_offset', C.c_int64),
+                ('ox', C.c_double), ('oy', C.c_double), ('res', C.c_double)]
+
+
+class PlanArgs(C.Structure):
+    _fields_ = [('num_envs', C.c_int32), ('max_ped', C.c_int32), ('step', C.c_int32), ('_pad', C.c_int32),
+                ('seed', C.c_uint64), ('env_offset', C.c_int64), ('min_goal_dist', C.c_double),
+                ('maps', _P), ('fields', _P), ('goals', _P), ('map_id', _P), ('nped', _P), ('pose', _P),
+                ('goal_id', _P), ('waypoint', _P), ('goal_local', _P)]
+
+
 PED_F = 16
 
 
@@ -123,6 +136,7 @@ EXPORTS = [
     'navgym_sizeof_step_args', 'navgym_sizeof_map', 'navgym_grid_bfs',
     'navgym_sizeof_her_args', 'navgym_sizeof_peds_args', 'navgym_compute_rewards', 'navgym_peds_advance',
     'navgym_agent_scan_batch', 'navgym_sizeof_scan_args',
+    'navgym_peds_plan', 'navgym_sizeof_plan_args', 'navgym_sizeof_plan_map',
 ]
 
 _lib = None
@@ -172,10 +186,13 @@ def load():
     lib.navgym_compute_rewards.argtypes = [C.POINTER(HerArgs), _P]
     lib.navgym_peds_advance.argtypes = [C.POINTER(PedsArgs), _P]
     lib.navgym_agent_scan_batch.argtypes = [C.POINTER(ScanArgs), _P]
+    lib.navgym_peds_plan.argtypes = [C.POINTER(PlanArgs), _P]
     if (lib.navgym_sizeof_step_args() != C.sizeof(StepArgs) or lib.navgym_sizeof_map() != C.sizeof(MapT)
             or lib.navgym_sizeof_her_args() != C.sizeof(HerArgs)
             or lib.navgym_sizeof_peds_args() != C.sizeof(PedsArgs)
-            or lib.navgym_sizeof_scan_args() != C.sizeof(ScanArgs)):
+            or lib.navgym_sizeof_scan_args() != C.sizeof(ScanArgs)
+            or lib.navgym_sizeof_plan_args() != C.sizeof(PlanArgs)
+            or lib.navgym_sizeof_plan_map() != C.sizeof(PlanMapT)):
         raise RuntimeError('libnavgym_b200.so ABI mismatch with nav_gym_b200/_lib.py (rebuild)')
     _lib = lib
     return lib

@@ -424,6 +424,7 @@ class BatchedNavGym(object):
         p.peds, p.nped = _ptr(self.peds), _ptr(self.nped)
         p.discs, p.ndisc, p.segs, p.nseg = _ptr(self._pdiscs), _ptr(self._pnd), _ptr(self._psegs), _ptr(self._pns)
         self._pargs = p
+        self.peds_scripted = True  # step() advances them itself; PedestrianSim turns this off
         self._peds_emit(advance=False)
 
     def _peds_emit(self, advance):
@@ -448,7 +449,7 @@ class BatchedNavGym(object):
         """One lockstep NavGymEnv.step.  Returned tensors are owned by the env and overwritten
         by the next call (clone to keep)."""
         if self.peds is not None and discs is None and segs is None:
-            self._peds_emit(advance=True)
+            self._peds_emit(advance=self.peds_scripted)
             discs, ndisc, segs, nseg = self._pdiscs, self._pnd, self._psegs, self._pns
         self._geom(discs, ndisc, segs, nseg, noise, actions)
         with torch.cuda.device(self.device):

