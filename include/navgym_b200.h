@@ -212,6 +212,14 @@ typedef struct {
     const int32_t *nseg;         /* [num_envs] */
     const int32_t *skip;         /* [num_envs][agents_per_env][2] first, count; or NULL */
     float *ranges;               /* [num_envs][agents_per_env][K] out */
+    /* crowd mode (segs == NULL): the other agents' footprints are built in the kernel from
+     * `pose` (every other live agent of the environment, footprint agent_fp) and the robot
+     * (robot_state = navgym_step_args_t.state of the same batch, footprint robot_fp =
+     * KetiRobot.threshold_footprint), float64 transform then float32 as env.py:404-414;
+     * footprints farther than range_max cannot change a clipped scan and are skipped. */
+    const double *robot_state;
+    const uint8_t *env_mask;     /* [num_envs] or NULL: scan only environments with mask != 0 */
+    double robot_fp[8], agent_fp[8];  /* 4 vertices (x, y) each, body frame */
 } navgym_scan_args_t;
 int navgym_agent_scan_batch(const navgym_scan_args_t *args, void *stream);
 int navgym_sizeof_scan_args(void);
@@ -233,6 +241,8 @@ typedef struct {
     int32_t num_goals, _pad;
     int64_t field_offset;     /* into fields, u16 elements: [num_goals][H][W] */
     int64_t goal_offset;      /* into goals, rows of 2 doubles */
+    int64_t free_offset;      /* into free_xy, rows of 2 doubles: centres of free cost-map cells */
+    int64_t free_count;
     double ox, oy, res;
 } navgym_plan_map_t;
 typedef struct {
@@ -251,8 +261,43 @@ typedef struct {
     int32_t *goal_id;         /* [num_envs][max_ped] in/out */
     double *waypoint;         /* [num_envs][max_ped][2] in/out, NaN = none yet */
     float *goal_local;        /* [num_envs][max_ped][2] out */
+    /* respawn (env.py:785-806) of the pedestrians of environments with respawn[e] != 0 (NULL =
+     * none), before the routing: a free cost-map cell at least min_robot_dist from the robot
+     * (robot_state = navgym_step_args_t.state; up to 6 draws), heading U[0, 2 pi), preferred
+     * speed U[v_pref_lo, v_pref_hi], legs with probability has_legs_ratio, a goal field; odometry,
+     * velocity and previous action zeroed.  pose is written, hence not const here. */
+    const uint8_t *respawn;
+    const double *free_xy;
+    const double *robot_state;
+    double min_robot_dist, v_pref_lo, v_pref_hi, has_legs_ratio;
+    double *pose_rw;          /* == pose */
+    double *v_pref;           /* [num_envs][max_ped] */
+    uint8_t *has_legs;        /* [num_envs][max_ped] */
+    double *dist_travelled;   /* [num_envs][max_ped][3] */
+    double *vel;              /* [num_envs][max_ped][2] */
+    float *prev_action;       /* [num_envs][max_ped][2] */
 } navgym_plan_args_t;
 int navgym_peds_plan(const navgym_plan_args_t *args, void *stream);
+
+/* env.py:655-662 + 237-255 for every pedestrian: clip the policy mean to [0, 1] x [-1, 1] (kept
+ * as the next `speed` input), scale by the preferred speed, Human.set_vel (human.py:32-41,
+ * float64), leg-gait odometry in the base frame, and the pedestrian rows of
+ * navgym_peds_args_t.peds (pose, odometry, has_legs) the geometry kernel reads. */
+typedef struct {
+    int32_t num_envs, max_ped;
+    double dt;
+    const int32_t *nped;
+    const float *mean;        /* [num_envs][max_ped][2] policy output */
+    const double *v_pref;
+    const uint8_t *has_legs;
+    double *pose;             /* in/out */
+    double *vel;              /* out: world velocity (vx, vy) */
+    double *dist_travelled;   /* in/out */
+    float *prev_action;       /* out */
+    float *rows;              /* [num_envs][max_ped][NAVGYM_PED_F] out */
+} navgym_move_args_t;
+int navgym_peds_move(const navgym_move_args_t *args, void *stream);
+int navgym_sizeof_move_args(void);
 int navgym_sizeof_plan_args(void);
 int navgym_sizeof_plan_map(void);
 

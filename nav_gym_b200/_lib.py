@@ -100,12 +100,15 @@ class ScanArgs(C.Structure):
                 ('max_seg', C.c_int32), ('cell_rule', C.c_int32), ('_pad', C.c_int32),
                 ('range_max', C.c_float), ('t_stop', C.c_float),
                 ('maps', _P), ('edt_pool', _P), ('map_id', _P), ('nagent', _P), ('pose', _P),
-                ('lin', _P), ('segs', _P), ('nseg', _P), ('skip', _P), ('ranges', _P)]
+                ('lin', _P), ('segs', _P), ('nseg', _P), ('skip', _P), ('ranges', _P),
+                ('robot_state', _P), ('env_mask', _P),
+                ('robot_fp', C.c_double * 8), ('agent_fp', C.c_double * 8)]
 
 
 class PlanMapT(C.Structure):
     _fields_ = [('W', C.c_int32), ('H', C.c_int32), ('num_goals', C.c_int32), ('_pad', C.c_int32),
                 ('field_offset', C.c_int64), ('goal_offset', C.c_int64),
+                ('free_offset', C.c_int64), ('free_count', C.c_int64),
                 ('ox', C.c_double), ('oy', C.c_double), ('res', C.c_double)]
 
 
@@ -113,7 +116,18 @@ class PlanArgs(C.Structure):
     _fields_ = [('num_envs', C.c_int32), ('max_ped', C.c_int32), ('step', C.c_int32), ('_pad', C.c_int32),
                 ('seed', C.c_uint64), ('env_offset', C.c_int64), ('min_goal_dist', C.c_double),
                 ('maps', _P), ('fields', _P), ('goals', _P), ('map_id', _P), ('nped', _P), ('pose', _P),
-                ('goal_id', _P), ('waypoint', _P), ('goal_local', _P)]
+                ('goal_id', _P), ('waypoint', _P), ('goal_local', _P),
+                ('respawn', _P), ('free_xy', _P), ('robot_state', _P),
+                ('min_robot_dist', C.c_double), ('v_pref_lo', C.c_double), ('v_pref_hi', C.c_double),
+                ('has_legs_ratio', C.c_double),
+                ('pose_rw', _P), ('v_pref', _P), ('has_legs', _P), ('dist_travelled', _P), ('vel', _P),
+                ('prev_action', _P)]
+
+
+class MoveArgs(C.Structure):
+    _fields_ = [('num_envs', C.c_int32), ('max_ped', C.c_int32), ('dt', C.c_double),
+                ('nped', _P), ('mean', _P), ('v_pref', _P), ('has_legs', _P), ('pose', _P), ('vel', _P),
+                ('dist_travelled', _P), ('prev_action', _P), ('rows', _P)]
 
 
 PED_F = 16
@@ -137,6 +151,7 @@ EXPORTS = [
     'navgym_sizeof_her_args', 'navgym_sizeof_peds_args', 'navgym_compute_rewards', 'navgym_peds_advance',
     'navgym_agent_scan_batch', 'navgym_sizeof_scan_args',
     'navgym_peds_plan', 'navgym_sizeof_plan_args', 'navgym_sizeof_plan_map',
+    'navgym_peds_move', 'navgym_sizeof_move_args',
 ]
 
 _lib = None
@@ -187,12 +202,14 @@ def load():
     lib.navgym_peds_advance.argtypes = [C.POINTER(PedsArgs), _P]
     lib.navgym_agent_scan_batch.argtypes = [C.POINTER(ScanArgs), _P]
     lib.navgym_peds_plan.argtypes = [C.POINTER(PlanArgs), _P]
+    lib.navgym_peds_move.argtypes = [C.POINTER(MoveArgs), _P]
     if (lib.navgym_sizeof_step_args() != C.sizeof(StepArgs) or lib.navgym_sizeof_map() != C.sizeof(MapT)
             or lib.navgym_sizeof_her_args() != C.sizeof(HerArgs)
             or lib.navgym_sizeof_peds_args() != C.sizeof(PedsArgs)
             or lib.navgym_sizeof_scan_args() != C.sizeof(ScanArgs)
             or lib.navgym_sizeof_plan_args() != C.sizeof(PlanArgs)
-            or lib.navgym_sizeof_plan_map() != C.sizeof(PlanMapT)):
+            or lib.navgym_sizeof_plan_map() != C.sizeof(PlanMapT)
+            or lib.navgym_sizeof_move_args() != C.sizeof(MoveArgs)):
         raise RuntimeError('libnavgym_b200.so ABI mismatch with nav_gym_b200/_lib.py (rebuild)')
     _lib = lib
     return lib

@@ -935,11 +935,31 @@ __global__ void __launch_bounds__(256) her_kernel(const navgym_her_args_t a)
 // from its own pose + the closed footprints of the robot and the other pedestrians, clipped,
 // no noise.  One CTA per agent, threads across beams; the same canonical march / segment
 // arithmetic as the robot's scan.
+// World-frame closed footprint of an agent at (x, y, th) as 4 segments (env.py:408-414):
+// float64 rotation + translation, vertices rounded to float32.
+__device__ __forceinline__ void footprint_segments(double x, double y, double th, const double *fp, float4 *out)
+{
+    const double c = cos(th), s = sin(th);
+    float wx[4], wy[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        wx[i] = (float)(c * fp[2 * i] - s * fp[2 * i + 1] + x);
+        wy[i] = (float)(s * fp[2 * i] + c * fp[2 * i + 1] + y);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[i] = make_float4(wx[i], wy[i], wx[(i + 1) & 3], wy[(i + 1) & 3]);
+}
+
+#define NAVGYM_SCAN_SEGS 128  // nearby-footprint segments kept per agent in crowd mode
 __global__ void __launch_bounds__(128) agent_scan_kernel(const navgym_scan_args_t a)
 {
+    __shared__ float4 near_segs[NAVGYM_SCAN_SEGS];
+    __shared__ int n_near;
     const int n = blockIdx.x;
     const int e = n / a.agents_per_env, slot = n - e * a.agents_per_env;
-    if (a.nagent && slot >= a.nagent[e]) return;
+    if (a.env_mask && !a.env_mask[e]) return;
+    const int live = a.nagent ? min(a.nagent[e], a.agents_per_env) : a.agents_per_env;
+    if (slot >= live) return;
     const double *p = a.pose + (size_t)n * 3;
     const float lx = (float)p[0], ly = (float)p[1], lt = (float)p[2];  // env.py:386
     const navgym_map_t m = a.maps[a.map_id[e]];
@@ -949,10 +969,43 @@ __global__ void __launch_bounds__(128) agent_scan_kernel(const navgym_scan_args_
     const float max_range = (float)((double)m.W * (double)m.H);
     const float t_stop = a.t_stop > 0.0f ? fminf(a.t_stop, max_range) : max_range;
     const float res32 = (float)m.res;
-    const int ns = a.nseg ? min(a.nseg[e], a.max_seg) : 0;
-    const float4 *segs = reinterpret_cast<const float4 *>(a.segs) + (size_t)e * a.max_seg;
-    int s0 = -1, s1 = -1;
-    if (a.skip) { s0 = a.skip[2 * (size_t)n]; s1 = s0 + a.skip[2 * (size_t)n + 1]; }
+    int ns = 0, s0 = -1, s1 = -1;
+    const float4 *segs = nullptr;
+    if (a.segs) {
+        ns = a.nseg ? min(a.nseg[e], a.max_seg) : 0;
+        segs = reinterpret_cast<const float4 *>(a.segs) + (size_t)e * a.max_seg;
+        if (a.skip) { s0 = a.skip[2 * (size_t)n]; s1 = s0 + a.skip[2 * (size_t)n + 1]; }
+    } else if (a.robot_state) {
+        // crowd mode: thread 0 = the robot, thread 1 + j = agent j of this environment
+        if (threadIdx.x == 0) n_near = 0;
+        __syncthreads();
+        const int o = threadIdx.x;
+        if (o <= live && o != slot + 1 && 4 * (live + 1) <= NAVGYM_SCAN_SEGS) {
+            double ox, oy, oth;
+            const double *fp;
+            if (o == 0) {
+                const size_t B = (size_t)a.num_envs;
+                ox = a.robot_state[NAVGYM_S_PX * B + e]; oy = a.robot_state[NAVGYM_S_PY * B + e];
+                oth = a.robot_state[NAVGYM_S_TH * B + e];
+                fp = a.robot_fp;
+            } else {
+                const double *q = a.pose + ((size_t)e * a.agents_per_env + (o - 1)) * 3;
+                ox = q[0]; oy = q[1]; oth = q[2];
+                fp = a.agent_fp;
+            }
+            float reach = 0.0f;  // farthest footprint vertex from the body origin
+#pragma unroll
+            for (int i = 0; i < 4; i++) reach = fmaxf(reach, hypotf((float)fp[2 * i], (float)fp[2 * i + 1]));
+            const float dc = hypotf((float)ox - lx, (float)oy - ly);
+            if (dc <= a.range_max + reach + 0.01f) {
+                const int at = atomicAdd(&n_near, 4);
+                footprint_segments(ox, oy, oth, fp, near_segs + at);
+            }
+        }
+        __syncthreads();
+        ns = n_near;
+        segs = near_segs;
+    }
     for (int k = threadIdx.x; k < a.num_beams; k += blockDim.x) {
         const float h = (float)__dadd_rn(a.lin[k], (double)lt);
         double sd, cd;
@@ -962,7 +1015,7 @@ __global__ void __launch_bounds__(128) agent_scan_kernel(const navgym_scan_args_
         float r = __fmul_rn(march(dist, m.W, m.H, (float)ci, (float)cj, dx, dy, max_range, t_stop, hx, hy), res32);
         for (int s = 0; s < ns; s++) {
             if (s >= s0 && s < s1) continue;
-            const float4 sg = __ldg(segs + s);
+            const float4 sg = segs[s];
             r = fminf(r, seg_hit(lx, ly, dx, dy, sg.x, sg.y, sg.z, sg.w));
         }
         a.ranges[(size_t)n * a.num_beams + k] = fminf(fmaxf(r, 0.0f), a.range_max);
@@ -1011,6 +1064,34 @@ __global__ void peds_plan_kernel(const navgym_plan_args_t a)
     const int e = n / a.max_ped, slot = n - e * a.max_ped;
     if (a.nped && slot >= a.nped[e]) return;
     const navgym_plan_map_t m = a.maps[a.map_id[e]];
+    if (a.respawn && a.respawn[e] && m.free_count > 0) {
+        // env.py:785-806: a new pedestrian for the new episode
+        const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+        const uint32_t ge = (uint32_t)(a.env_offset + e);
+        const size_t B = (size_t)a.num_envs;
+        const double rx = a.robot_state[NAVGYM_S_PX * B + e], ry = a.robot_state[NAVGYM_S_PY * B + e];
+        const uint4 r0 = philox4x32_10(make_uint4(ge, (uint32_t)slot, (uint32_t)a.step, 0x5b0au), key);
+        const uint4 r1 = philox4x32_10(make_uint4(ge, (uint32_t)slot, (uint32_t)a.step, 0x5b0bu), key);
+        const uint32_t draws[6] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
+        double sx = 0, sy = 0;
+        for (int i = 0; i < 6; i++) {
+            const long long row = m.free_offset + (long long)(((uint64_t)draws[i] * (uint64_t)m.free_count) >> 32);
+            sx = a.free_xy[2 * row]; sy = a.free_xy[2 * row + 1];
+            if ((sx - rx) * (sx - rx) + (sy - ry) * (sy - ry) >= a.min_robot_dist * a.min_robot_dist) break;
+        }
+        const uint4 r2 = philox4x32_10(make_uint4(ge, (uint32_t)slot, (uint32_t)a.step, 0x5b0cu), key);
+        a.pose_rw[3 * (size_t)n] = sx;
+        a.pose_rw[3 * (size_t)n + 1] = sy;
+        a.pose_rw[3 * (size_t)n + 2] = 6.283185307179586 * (double)u01(r2.x);
+        a.v_pref[n] = a.v_pref_lo + (a.v_pref_hi - a.v_pref_lo) * (double)u01(r2.y);
+        a.has_legs[n] = (double)u01(r2.z) < a.has_legs_ratio;
+        a.goal_id[n] = (int)(((uint64_t)r2.w * (uint64_t)m.num_goals) >> 32);
+        a.waypoint[2 * (size_t)n] = CUDART_NAN;
+        a.waypoint[2 * (size_t)n + 1] = CUDART_NAN;
+        for (int i = 0; i < 3; i++) a.dist_travelled[3 * (size_t)n + i] = 0.0;
+        a.vel[2 * (size_t)n] = a.vel[2 * (size_t)n + 1] = 0.0;
+        a.prev_action[2 * (size_t)n] = a.prev_action[2 * (size_t)n + 1] = 0.0f;
+    }
     const double px = a.pose[3 * (size_t)n], py = a.pose[3 * (size_t)n + 1], th = a.pose[3 * (size_t)n + 2];
     const int cx = plan_cell(px, m.ox, m.res, m.W), cy = plan_cell(py, m.oy, m.res, m.H);
     const size_t fsz = (size_t)m.W * m.H;
@@ -1056,6 +1137,51 @@ __global__ void peds_plan_kernel(const navgym_plan_args_t a)
     const double c = cos(th), s = sin(th);
     a.goal_local[2 * (size_t)n] = (float)((wx - px) * c + (wy - py) * s);
     a.goal_local[2 * (size_t)n + 1] = (float)(-(wx - px) * s + (wy - py) * c);
+}
+
+// ------------------------------------------------------------------ pedestrian motion
+// (include/navgym_b200.h, navgym_move_args_t.)  One thread per pedestrian.
+__global__ void peds_move_kernel(const navgym_move_args_t a)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= a.num_envs * a.max_ped) return;
+    const int e = n / a.max_ped, slot = n - e * a.max_ped;
+    if (a.nped && slot >= a.nped[e]) return;
+    // env.py:655-661
+    const float m0 = fminf(fmaxf(a.mean[2 * (size_t)n], 0.0f), 1.0f);
+    const float m1 = fminf(fmaxf(a.mean[2 * (size_t)n + 1], -1.0f), 1.0f);
+    a.prev_action[2 * (size_t)n] = m0;
+    a.prev_action[2 * (size_t)n + 1] = m1;
+    const double factor = a.v_pref[n];
+    const double v = (double)m0 * factor, w = (double)m1 * factor;
+    // human.py:32-41
+    double x = a.pose[3 * (size_t)n], y = a.pose[3 * (size_t)n + 1];
+    const double th0 = a.pose[3 * (size_t)n + 2];
+    const double vx = v * cos(th0), vy = v * sin(th0);
+    const double th1 = th0 + w * a.dt;
+    x = x + cos(th1) * v * a.dt;
+    y = y + sin(th1) * v * a.dt;
+    const double twopi = 6.283185307179586;
+    double th = fmod(th1, twopi);
+    if (th != 0 && th < 0) th += twopi;
+    a.pose[3 * (size_t)n] = x;
+    a.pose[3 * (size_t)n + 1] = y;
+    a.pose[3 * (size_t)n + 2] = th;
+    a.vel[2 * (size_t)n] = vx;
+    a.vel[2 * (size_t)n + 1] = vy;
+    // env.py:237-255: rotation rate from the previous observation's yaw, world velocity into
+    // the base frame (pose2d inverse_pose2d / apply_tf_to_vel written out), integrated
+    const double prev_yaw = atan2(sin(th0), cos(th0));
+    const double vrot = (th - prev_yaw) / a.dt;
+    const double c = cos(th), s = sin(th);
+    double *d = a.dist_travelled + 3 * (size_t)n;
+    d[0] += (c * vx + s * vy) * a.dt;
+    d[1] += (-s * vx + c * vy) * a.dt;
+    d[2] += vrot * a.dt;
+    float *q = a.rows + (size_t)n * NAVGYM_PED_F;
+    q[0] = (float)x; q[1] = (float)y; q[2] = (float)th;
+    q[9] = (float)d[0]; q[10] = (float)d[1]; q[11] = (float)d[2];
+    q[12] = a.has_legs[n] ? 1.0f : 0.0f;
 }
 
 // ------------------------------------------------------------------ scripted pedestrians
@@ -1491,12 +1617,28 @@ int navgym_peds_advance(const navgym_peds_args_t *args, void *stream)
 int navgym_sizeof_scan_args(void) { return (int)sizeof(navgym_scan_args_t); }
 int navgym_sizeof_plan_args(void) { return (int)sizeof(navgym_plan_args_t); }
 int navgym_sizeof_plan_map(void) { return (int)sizeof(navgym_plan_map_t); }
+int navgym_sizeof_move_args(void) { return (int)sizeof(navgym_move_args_t); }
+
+int navgym_peds_move(const navgym_move_args_t *args, void *stream)
+{
+    const int n = args->num_envs * args->max_ped;
+    if (n <= 0) return 0;
+    if (!args->mean || !args->v_pref || !args->has_legs || !args->pose || !args->vel || !args->dist_travelled ||
+        !args->prev_action || !args->rows)
+        return (int)cudaErrorInvalidValue;
+    peds_move_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*args);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
 
 int navgym_peds_plan(const navgym_plan_args_t *args, void *stream)
 {
     const int n = args->num_envs * args->max_ped;
     if (n <= 0) return 0;
     if (!args->maps || !args->fields || !args->goals || !args->pose || !args->goal_id || !args->waypoint || !args->goal_local)
+        return (int)cudaErrorInvalidValue;
+    if (args->respawn && (!args->free_xy || !args->robot_state || !args->pose_rw || !args->v_pref || !args->has_legs ||
+                          !args->dist_travelled || !args->vel || !args->prev_action))
         return (int)cudaErrorInvalidValue;
     peds_plan_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*args);
     g_launches++;
@@ -1507,6 +1649,7 @@ int navgym_agent_scan_batch(const navgym_scan_args_t *args, void *stream)
 {
     if (args->num_envs <= 0 || args->agents_per_env <= 0) return 0;
     if (args->num_beams <= 0 || !args->pose || !args->lin || !args->ranges) return (int)cudaErrorInvalidValue;
+    if (!args->segs && args->robot_state && args->agents_per_env + 1 > 128) return (int)cudaErrorInvalidValue;
     agent_scan_kernel<<<args->num_envs * args->agents_per_env, 128, 0, (cudaStream_t)stream>>>(*args);
     g_launches++;
     return (int)cudaGetLastError();

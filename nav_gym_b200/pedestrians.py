@@ -140,62 +140,68 @@ class PedestrianSim(object):
     """The reference's pedestrians for a whole BatchedNavGym, on the device.
 
     Per step, in the reference's order (env.py:617-693):
-        sim.act()            route following -> policy -> Human.set_vel -> leg odometry ->
-                             geometry the robot's lidar sees (discs for legs, boxes otherwise)
+        sim.act()            respawn for episodes that just ended -> route following
+                             (navgym_peds_plan) -> policy (torch) -> clip, Human.set_vel, leg
+                             odometry (navgym_peds_move) -> the geometry the robot's lidar sees
+                             (navgym_peds_advance: discs for legs, boxes otherwise)
         env.step(actions)    the robot's fused step, scanning against that geometry
-        sim.observe()        every pedestrian's own scan from its new pose (robot included),
-                             the next policy input
-    `sim.step(actions)` does the three.  Environments whose episode ended respawn their
-    pedestrians (env.py:785-806) before the next act().
+        sim.observe()        every pedestrian's own scan from its new pose, robot included
+                             (navgym_agent_scan_batch, crowd mode): the next policy input
+    `sim.step(actions)` does the three.
 
     State, all [num_envs, max_ped, ...] device tensors: pose f64 (x, y, theta), vel f64 (vx, vy),
-    v_pref f64, has_legs bool, dist_travelled f64 (x, y, theta in the base frame), prev_yaw f64,
-    prev_action f32 (the clipped policy mean, the policy's `speed` input), scan f32 [.., 512],
-    goal_id i32, waypoint f64.
+    v_pref f64, has_legs bool, dist_travelled f64 (x, y, theta in the base frame), prev_action f32
+    (the clipped policy mean, the policy's `speed` input), scan f32 [.., 512], goal_id i32,
+    waypoint f64, goal_local f32.
+
+    precision: 'fp32' (default; the policy mean matches the reference's CPU forward to ~1e-5),
+    'tf32' or 'bf16' (tensor cores; means move by ~1e-3, the pedestrians' paths are not
+    comparable step by step any more).
+
+    Known deviation: with auto_reset the first observation of a new episode is taken inside the
+    robot's fused step, against the previous episode's pedestrians; they respawn (at least 4 m
+    from the new robot pose) before the first action of the episode.
     """
 
     def __init__(self, env, max_ped, nped=None, policy=None, v_pref_range=(0.0, 0.6), has_legs_ratio=0.5,
-                 num_goals=32, min_goal_dist=10.0, min_robot_dist=4.0, seed=0, fold_frames=True):
+                 num_goals=32, min_goal_dist=10.0, min_robot_dist=4.0, seed=0, fold_frames=True,
+                 precision='fp32'):
         from . import maps as M
+        assert precision in ('fp32', 'tf32', 'bf16')
         self.env, self.device = env, env.device
         self.B, self.P = env.B, int(max_ped)
         self.dt = float(env.args.dt)
-        self.v_pref_range, self.has_legs_ratio = v_pref_range, float(has_legs_ratio)
-        self.min_robot_dist = float(min_robot_dist)
+        self.precision = precision
         self.lib = _lib.load()
         dev, f64, f32, i32 = self.device, torch.float64, torch.float32, torch.int32
         B, P = self.B, self.P
-        self.gen = torch.Generator(device=dev)
-        self.gen.manual_seed(int(seed))
         self.nped = None if nped is None else torch.as_tensor(nped, dtype=i32).to(dev)
-        self.live = (torch.arange(P, device=dev)[None, :] < (self.nped[:, None] if self.nped is not None else P))
         if policy is None:
             policy = HumanPolicy()
         self.policy = policy.to(dev).eval()
         self.fold_frames = bool(fold_frames)
-        # ---- planning fields per map
+        # ---- planning fields + free-cell pools per map
         rng = np.random.RandomState(int(seed) + 77)
         pm = (_lib.PlanMapT * len(env.pool.maps))()
-        fl, gl, self.free_xy, self.free_off = [], [], [], [0]
-        foff = goff = 0
+        fl, gl, xl = [], [], []
+        foff = goff = xoff = 0
         for i, m in enumerate(env.pool.maps):
             fields, goals, cm = M.goal_fields(m, num_goals, rng)
-            pm[i] = _lib.PlanMapT(cm['width'], cm['height'], num_goals, 0, foff, goff,
+            r, c = np.where(cm['data'] == 0)
+            xy = np.column_stack([(c + 0.5) * cm['resolution'] + cm['origin'][0],
+                                  (r + 0.5) * cm['resolution'] + cm['origin'][1]]).astype(np.float64)
+            pm[i] = _lib.PlanMapT(cm['width'], cm['height'], num_goals, 0, foff, goff, xoff, len(xy),
                                   float(cm['origin'][0]), float(cm['origin'][1]), float(cm['resolution']))
             fl.append(fields.reshape(-1))
             gl.append(goals)
+            xl.append(xy)
             foff += fields.size
             goff += num_goals
-            r, c = np.where(cm['data'] == 0)
-            xy = np.column_stack([(c + 0.5) * cm['resolution'] + cm['origin'][0],
-                                  (r + 0.5) * cm['resolution'] + cm['origin'][1]])
-            self.free_xy.append(xy)
-            self.free_off.append(self.free_off[-1] + len(xy))
+            xoff += len(xy)
         self.plan_maps = torch.from_numpy(np.frombuffer(bytes(pm), dtype=np.uint8).copy()).to(dev)
         self.fields = torch.from_numpy(np.concatenate(fl).view(np.int16)).to(dev)
         self.goals = torch.from_numpy(np.concatenate(gl)).to(dev)
-        self.free_xy = torch.from_numpy(np.concatenate(self.free_xy)).to(dev)
-        self.free_off = torch.tensor(self.free_off, dtype=torch.int64, device=dev)
+        self.free_xy = torch.from_numpy(np.concatenate(xl)).to(dev)
         self.num_goals = int(num_goals)
         # ---- state
         self.pose = torch.zeros(B, P, 3, dtype=f64, device=dev)
@@ -203,104 +209,103 @@ class PedestrianSim(object):
         self.v_pref = torch.zeros(B, P, dtype=f64, device=dev)
         self.has_legs = torch.zeros(B, P, dtype=torch.bool, device=dev)
         self.dist_travelled = torch.zeros(B, P, 3, dtype=f64, device=dev)
-        self.prev_yaw = torch.zeros(B, P, dtype=f64, device=dev)
         self.prev_action = torch.zeros(B, P, 2, dtype=f32, device=dev)
         self.goal_id = torch.zeros(B, P, dtype=i32, device=dev)
         self.waypoint = torch.full((B, P, 2), float('nan'), dtype=f64, device=dev)
         self.goal_local = torch.zeros(B, P, 2, dtype=f32, device=dev)
+        self._all = torch.ones(B, dtype=torch.uint8, device=dev)
+        # ---- geometry for the robot's lidar goes through the env's pedestrian rows
+        env.attach_pedestrians(torch.zeros(B, P, _lib.PED_F, dtype=f32, device=dev), self.nped)
+        env.peds_scripted = False  # the sim moves them; env.step only emits their geometry
         a = _lib.PlanArgs()
         a.num_envs, a.max_ped, a.step, a.seed = B, P, 0, int(seed)
         a.env_offset, a.min_goal_dist = int(env.args.env_offset), float(min_goal_dist)
         a.maps, a.fields, a.goals = _ptr(self.plan_maps), _ptr(self.fields), _ptr(self.goals)
         a.map_id, a.nped, a.pose = _ptr(env.map_id), _ptr(self.nped), _ptr(self.pose)
         a.goal_id, a.waypoint, a.goal_local = _ptr(self.goal_id), _ptr(self.waypoint), _ptr(self.goal_local)
+        a.free_xy, a.robot_state = _ptr(self.free_xy), _ptr(env.state)
+        a.min_robot_dist, a.has_legs_ratio = float(min_robot_dist), float(has_legs_ratio)
+        a.v_pref_lo, a.v_pref_hi = float(v_pref_range[0]), float(v_pref_range[1])
+        a.pose_rw, a.v_pref, a.has_legs = _ptr(self.pose), _ptr(self.v_pref), _ptr(self.has_legs)
+        a.dist_travelled, a.vel, a.prev_action = _ptr(self.dist_travelled), _ptr(self.vel), _ptr(self.prev_action)
         self.plan_args = a
-        # ---- lidar of the pedestrians: segments [robot | ped 0 | ped 1 ...], 4 each
-        self.scanner = AgentScanner(env.pool, B, P, 4 * (P + 1), env.map_id,
+        self._mean = torch.zeros(B, P, 2, dtype=f32, device=dev)
+        mv = _lib.MoveArgs()
+        mv.num_envs, mv.max_ped, mv.dt = B, P, self.dt
+        mv.nped, mv.mean, mv.v_pref, mv.has_legs = _ptr(self.nped), _ptr(self._mean), _ptr(self.v_pref), _ptr(self.has_legs)
+        mv.pose, mv.vel, mv.dist_travelled = _ptr(self.pose), _ptr(self.vel), _ptr(self.dist_travelled)
+        mv.prev_action, mv.rows = _ptr(self.prev_action), _ptr(env.peds)
+        self.move_args = mv
+        # ---- lidar of the pedestrians, crowd mode: footprints built in the kernel
+        self.scanner = AgentScanner(env.pool, B, P, 0, env.map_id,
                                     cell_rule='numpy2' if env.args.cell_rule else 'numpy1')
-        self.segs = torch.zeros(B, 4 * (P + 1), 4, dtype=f32, device=dev)
-        nl = self.nped if self.nped is not None else torch.full((B,), P, dtype=i32, device=dev)
-        self.nseg = (4 * (nl + 1)).to(i32)
-        sk = torch.tensor([[4 * (1 + j), 4] for j in range(P)], dtype=i32, device=dev)
-        self.skip = sk[None].expand(B, P, 2).contiguous()
+        sa = self.scanner.args
+        sa.pose, sa.nagent, sa.robot_state = _ptr(self.pose), _ptr(self.nped), _ptr(env.state)
+        sa.robot_fp = (C.c_double * 8)(*np.asarray(KetiRobot.threshold_footprint, np.float64).reshape(-1))
+        sa.agent_fp = (C.c_double * 8)(*np.asarray(Human.footprint, np.float64).reshape(-1))
         self.scan = self.scanner.ranges
-        # ---- geometry for the robot's lidar goes through the env's pedestrian rows
-        rows = torch.zeros(B, P, _lib.PED_F, dtype=f32, device=dev)
-        env.attach_pedestrians(rows, self.nped)
-        env.peds_scripted = False  # the sim moves them; env.step only emits their geometry
         self.reset()
 
+    def _call(self, fn, args, what):
+        with torch.cuda.device(self.device):
+            _lib.check(fn(C.byref(args), self.env._stream()), what)
+
+    def _plan(self, respawn):
+        a = self.plan_args
+        self._respawn = respawn  # keep the tensor alive while the launch reads it
+        a.respawn = _ptr(respawn)
+        self._call(self.lib.navgym_peds_plan, a, 'peds_plan')
+        a.step += 1
+
+    def _scan(self, env_mask=None):
+        self._mask = env_mask
+        self.scanner.args.env_mask = _ptr(env_mask)
+        self._call(self.lib.navgym_agent_scan_batch, self.scanner.args, 'agent_scan_batch')
+
     # ---- episode start (env.py:785-815) ------------------------------------------------
-    def reset(self, mask=None):
-        """(Re)spawn the pedestrians of the masked environments (all when None): a free cost-map
-        cell at least 4 m from the robot (env.py:369-373), random heading, preferred speed and
-        legs (env.py:793-803), a goal field, zero odometry; then their first scans."""
-        B, P, dev = self.B, self.P, self.device
-        if mask is None:
-            mask = torch.ones(B, dtype=torch.bool, device=dev)
-        m2 = mask[:, None].expand(B, P)
-        mid = self.env.map_id.long()
-        lo, n = self.free_off[mid], (self.free_off[mid + 1] - self.free_off[mid])
-        rob = self.env.state[:2].t()  # [B, 2]
-        xy = torch.zeros(B, P, 2, dtype=torch.float64, device=dev)
-        todo = torch.ones(B, P, dtype=torch.bool, device=dev)
-        for _ in range(6):  # rejection sampling, vectorised; the last draw is kept regardless
-            u = torch.rand(B, P, generator=self.gen, device=dev, dtype=torch.float64)
-            idx = lo[:, None] + torch.clamp((u * n[:, None]).long(), max=(n[:, None] - 1).clamp(min=0))
-            cand = self.free_xy[idx]
-            xy = torch.where(todo[..., None], cand, xy)
-            todo = todo & ((cand - rob[:, None, :]).norm(dim=-1) < self.min_robot_dist)
-        th = torch.rand(B, P, generator=self.gen, device=dev, dtype=torch.float64) * (2 * np.pi)
-        vp = self.v_pref_range[0] + torch.rand(B, P, generator=self.gen, device=dev, dtype=torch.float64) * (
-            self.v_pref_range[1] - self.v_pref_range[0])
-        legs = torch.rand(B, P, generator=self.gen, device=dev) < self.has_legs_ratio
-        gid = torch.randint(self.num_goals, (B, P), generator=self.gen, device=dev, dtype=torch.int32)
-        self.pose = torch.where(m2[..., None], torch.cat((xy, th[..., None]), -1), self.pose).contiguous()
-        self.plan_args.pose = _ptr(self.pose)
-        self.v_pref = torch.where(m2, vp, self.v_pref)
-        self.has_legs = torch.where(m2, legs, self.has_legs)
-        self.goal_id.copy_(torch.where(m2, gid, self.goal_id))
-        self.waypoint.copy_(torch.where(m2[..., None], torch.full_like(self.waypoint, float('nan')), self.waypoint))
-        z3 = torch.zeros_like(self.dist_travelled)
-        self.dist_travelled = torch.where(m2[..., None], z3, self.dist_travelled)
-        self.vel = torch.where(m2[..., None], torch.zeros_like(self.vel), self.vel)
-        self.prev_action = torch.where(m2[..., None], torch.zeros_like(self.prev_action), self.prev_action)
-        self._emit()
+    def reset(self):
+        """Spawn every environment's pedestrians (env.py:785-806) and take their first scans."""
+        self._plan(self._all)
+        rows = self.env.peds
+        rows[..., 0:3] = self.pose.float()
+        rows[..., 9:12] = 0.0
+        rows[..., 12] = self.has_legs.float()
+        self.env._peds_emit(advance=False)
         self.observe()
 
     # ---- env.py:617-662 + 664-681 + 237-255 ---------------------------------------------
     @torch.no_grad()
     def act(self):
-        env, a = self.env, self.plan_args
-        if env.args.auto_reset:  # episodes that ended in the last step start with new pedestrians
-            done = env.done.bool()
-            self.reset(done)
-        with torch.cuda.device(self.device):
-            _lib.check(self.lib.navgym_peds_plan(C.byref(a), env._stream()), 'peds_plan')
-        a.step += 1
+        env = self.env
+        respawn = env.done if env.args.auto_reset else None
+        self._plan(respawn)
+        if respawn is not None:
+            self._scan(respawn)  # first scans of the respawned pedestrians (env.py:808-815)
         x = preprocess_scan(self.scan).reshape(self.B * self.P, 1, -1)
         goal, speed = self.goal_local.reshape(-1, 2), self.prev_action.reshape(-1, 2)
-        if self.fold_frames:
-            mean = self._mean_folded(x, goal, speed)
-        else:
-            mean = self.policy.mean(x.expand(-1, 3, -1).contiguous(), goal, speed)
-        lo = torch.tensor([0.0, -1.0], device=self.device)
-        hi = torch.tensor([1.0, 1.0], device=self.device)
-        act = torch.minimum(torch.maximum(mean, lo), hi).reshape(self.B, self.P, 2)   # env.py:655-657
-        self.prev_action = act
-        action = act.double() * self.v_pref[..., None]                                # env.py:659-661
-        self.prev_yaw = torch.atan2(torch.sin(self.pose[..., 2]), torch.cos(self.pose[..., 2]))
-        pose, vel = human_set_vel(self.pose, action, self.dt)
-        live = self.live[..., None]
-        self.pose.copy_(torch.where(live, pose, self.pose))
-        self.vel = torch.where(live, vel, self.vel)
-        self._update_dist_travelled()
-        self._emit()
+        self._mean.copy_(self._policy_mean(x, goal, speed).reshape(self.B, self.P, 2))
+        self._call(self.lib.navgym_peds_move, self.move_args, 'peds_move')
+        env._peds_emit(advance=False)
 
-    def _mean_folded(self, x, goal, speed):
-        """env.py:647 hands the newest scan to all three input frames, so the first convolution
-        sees three identical channels: sum its weights over them once and convolve one."""
+    def _policy_mean(self, x, goal, speed):
+        if self.precision == 'bf16':
+            with torch.autocast('cuda', dtype=torch.bfloat16):
+                return self._mean_fp(x, goal, speed).float()
+        if self.precision == 'tf32':
+            old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+            torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = True
+            try:
+                return self._mean_fp(x, goal, speed)
+            finally:
+                torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+        return self._mean_fp(x, goal, speed)
+
+    def _mean_fp(self, x, goal, speed):
         p = self.policy
+        if not self.fold_frames:
+            return p.mean(x.expand(-1, 3, -1).contiguous(), goal, speed)
+        # env.py:647 hands the newest scan to all three input frames, so the first convolution
+        # sees three identical channels: sum its weights over them once and convolve one
         w = p.act_fea_cv1.weight.sum(dim=1, keepdim=True)
         h = F.relu(F.conv1d(x, w, p.act_fea_cv1.bias, stride=2, padding=1))
         h = F.relu(p.act_fea_cv2(h))
@@ -308,33 +313,11 @@ class PedestrianSim(object):
         h = F.relu(p.act_fc2(torch.cat((h, goal, speed), dim=-1)))
         return torch.cat((torch.sigmoid(p.actor1(h)), torch.tanh(p.actor2(h))), dim=-1)
 
-    def _update_dist_travelled(self):
-        """env.py:237-255 with pose2d's inverse_pose2d / apply_tf_to_vel written out: the world
-        velocity rotated into the base frame, integrated."""
-        th = self.pose[..., 2]
-        vrot = (th - self.prev_yaw) / self.dt
-        c, s = torch.cos(th), torch.sin(th)
-        vx, vy = self.vel[..., 0], self.vel[..., 1]
-        base = torch.stack((c * vx + s * vy, -s * vx + c * vy, vrot), dim=-1)
-        self.dist_travelled = self.dist_travelled + torch.where(self.live[..., None], base * self.dt, torch.zeros_like(base))
-
-    def _emit(self):
-        """Pedestrian rows of the env (layout include/navgym_b200.h) -> discs / segments."""
-        rows = self.env.peds
-        rows[..., 0:3] = self.pose.float()
-        rows[..., 9:12] = self.dist_travelled.float()
-        rows[..., 12] = self.has_legs.float()
-        self.env._peds_emit(advance=False)
-
     # ---- env.py:683-693 -------------------------------------------------------------------
-    @torch.no_grad()
     def observe(self):
         """Every pedestrian's scan from its current pose: the map, the robot's threshold
         footprint and the other pedestrians' footprints (lidar_legs=False), no noise."""
-        rob = self.env.state[:3].t().contiguous()  # [B, 3] px, py, theta
-        self.segs[:, :4] = footprint_polygons(rob, KetiRobot.threshold_footprint)
-        self.segs[:, 4:] = footprint_polygons(self.pose, Human.footprint).reshape(self.B, -1, 4)
-        self.scanner.scan(self.pose, self.segs, self.nseg, self.skip, self.nped)
+        self._scan(None)
         return self.scan
 
     def step(self, actions):
