@@ -301,6 +301,17 @@ int navgym_sizeof_move_args(void);
 int navgym_sizeof_plan_args(void);
 int navgym_sizeof_plan_map(void);
 
+/* ---- pedestrian policy, convolutional front end (human_policy.py:24-25, 45-47 fed as in
+ * env.py:627-629, 647): scan[n][512] (metres) -> clip to [0, 6], / 6 - 0.5 (float64, then
+ * float32) -> conv1d(1 -> 32, k 5, stride 2, pad 1; env.py:647 feeds the same scan to the
+ * three input frames, so w1 is the reference's act_fea_cv1 weight summed over them) -> relu ->
+ * conv1d(32 -> 32, k 3, stride 2, pad 1) -> relu -> features[n][4096], channel-major like
+ * `.view(N, -1)`.  One launch, activations stay in shared memory (cuDNN writes and re-reads
+ * 2 GB of them for 40 960 pedestrians).  w1 [32][5], b1 [32], w2 [32][32][3] (out, in, tap),
+ * b2 [32]: float32 device pointers in torch's layout. */
+int navgym_policy_features(const float *scan, int n, const float *w1, const float *b1,
+                           const float *w2, const float *b2, float *features, void *stream);
+
 /* ---- inner native boundary: range_libc --------------------------------------------- */
 /* PyOMap(bool[H,W]) + PyRayMarching(omap, max_range) (env.py:337-340): exact Euclidean
  * distance transform of occ_dev (u8, non-zero = occupied, [H][W], row = y) into dist_dev. */

@@ -151,7 +151,7 @@ EXPORTS = [
     'navgym_sizeof_her_args', 'navgym_sizeof_peds_args', 'navgym_compute_rewards', 'navgym_peds_advance',
     'navgym_agent_scan_batch', 'navgym_sizeof_scan_args',
     'navgym_peds_plan', 'navgym_sizeof_plan_args', 'navgym_sizeof_plan_map',
-    'navgym_peds_move', 'navgym_sizeof_move_args',
+    'navgym_peds_move', 'navgym_sizeof_move_args', 'navgym_policy_features',
 ]
 
 _lib = None
@@ -203,6 +203,7 @@ def load():
     lib.navgym_agent_scan_batch.argtypes = [C.POINTER(ScanArgs), _P]
     lib.navgym_peds_plan.argtypes = [C.POINTER(PlanArgs), _P]
     lib.navgym_peds_move.argtypes = [C.POINTER(MoveArgs), _P]
+    lib.navgym_policy_features.argtypes = [_P, C.c_int, _P, _P, _P, _P, _P, _P]
     if (lib.navgym_sizeof_step_args() != C.sizeof(StepArgs) or lib.navgym_sizeof_map() != C.sizeof(MapT)
             or lib.navgym_sizeof_her_args() != C.sizeof(HerArgs)
             or lib.navgym_sizeof_peds_args() != C.sizeof(PedsArgs)

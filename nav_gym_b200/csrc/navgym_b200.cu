@@ -1184,6 +1184,72 @@ __global__ void peds_move_kernel(const navgym_move_args_t a)
     q[12] = a.has_legs[n] ? 1.0f : 0.0f;
 }
 
+// ------------------------------------------------------------------ pedestrian policy front end
+// (include/navgym_b200.h, navgym_policy_features.)  128 threads; a CTA keeps the second
+// convolution's weights in shared memory and walks over pedestrians: conv1 fills h1 in shared
+// memory, then thread p accumulates output position p of all 32 channels of conv2 in registers
+// (weights broadcast as float4 over 4 output channels: one LDS.128 per 4 FMA).
+#define PF_H1 260  // row pitch of h1: [0] = left pad, [1 + q] = conv1 output q (q < 255), [256] = right pad
+__global__ void __launch_bounds__(128) policy_features_kernel(const float *__restrict__ scan, int n,
+                                                              const float *__restrict__ w1, const float *__restrict__ b1,
+                                                              const float *__restrict__ w2, const float *__restrict__ b2,
+                                                              float *__restrict__ out)
+{
+    __shared__ __align__(16) float w2s[32 * 3 * 32];  // [ci][tap][co]
+    __shared__ __align__(16) float h1[32 * PF_H1];
+    __shared__ float xs[516];                          // [0] = left pad, [1 + i] = input i
+    __shared__ float w1s[32 * 5], b1s[32], b2s[32];
+    const int t = threadIdx.x;
+    for (int i = t; i < 32 * 32 * 3; i += 128) {
+        const int co = i / 96, ci = (i / 3) % 32, k = i % 3;
+        w2s[(ci * 3 + k) * 32 + co] = w2[i];
+    }
+    for (int i = t; i < 160; i += 128) w1s[i] = w1[i];
+    if (t < 32) { b1s[t] = b1[t]; b2s[t] = b2[t]; }
+    for (int c = t; c < 32; c += 128) { h1[c * PF_H1] = 0.0f; h1[c * PF_H1 + 256] = 0.0f; }
+    if (t == 0) { xs[0] = 0.0f; xs[513] = 0.0f; xs[514] = 0.0f; xs[515] = 0.0f; }
+    for (int ped = blockIdx.x; ped < n; ped += gridDim.x) {
+        __syncthreads();  // weights ready / previous pedestrian's h1 no longer read
+        for (int i = t; i < 512; i += 128) {
+            const double r = fmin(fmax((double)scan[(size_t)ped * 512 + i], 0.0), 6.0);
+            xs[1 + i] = (float)(r / 6.0 - 0.5);  // env.py:627-629, 648
+        }
+        __syncthreads();
+        for (int i = t; i < 32 * 255; i += 128) {
+            const int c = i / 255, q = i - c * 255;
+            float acc = b1s[c];
+#pragma unroll
+            for (int k = 0; k < 5; k++) acc = fmaf(w1s[c * 5 + k], xs[2 * q + k], acc);  // input 2q - 1 + k
+            h1[c * PF_H1 + 1 + q] = fmaxf(acc, 0.0f);
+        }
+        __syncthreads();
+        float acc[32];
+#pragma unroll
+        for (int co = 0; co < 32; co++) acc[co] = b2s[co];
+#pragma unroll 2
+        for (int ci = 0; ci < 32; ci++) {
+            const float2 a01 = *reinterpret_cast<const float2 *>(h1 + ci * PF_H1 + 2 * t);  // inputs 2p - 1, 2p
+            const float a2 = h1[ci * PF_H1 + 2 * t + 2];                                    // input 2p + 1
+            const float av[3] = {a01.x, a01.y, a2};
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float4 *wr = reinterpret_cast<const float4 *>(w2s + (ci * 3 + k) * 32);
+#pragma unroll
+                for (int c4 = 0; c4 < 8; c4++) {
+                    const float4 w = wr[c4];
+                    acc[4 * c4 + 0] = fmaf(av[k], w.x, acc[4 * c4 + 0]);
+                    acc[4 * c4 + 1] = fmaf(av[k], w.y, acc[4 * c4 + 1]);
+                    acc[4 * c4 + 2] = fmaf(av[k], w.z, acc[4 * c4 + 2]);
+                    acc[4 * c4 + 3] = fmaf(av[k], w.w, acc[4 * c4 + 3]);
+                }
+            }
+        }
+        float *o = out + (size_t)ped * 4096 + t;
+#pragma unroll
+        for (int co = 0; co < 32; co++) o[co * 128] = fmaxf(acc[co], 0.0f);
+    }
+}
+
 // ------------------------------------------------------------------ scripted pedestrians
 // Pedestrian motion + geometry for the batched simulator (scripted stand-in
 // for the reference's CNN-driven humans whose weights are absent): each pedestrian walks
@@ -1618,6 +1684,20 @@ int navgym_sizeof_scan_args(void) { return (int)sizeof(navgym_scan_args_t); }
 int navgym_sizeof_plan_args(void) { return (int)sizeof(navgym_plan_args_t); }
 int navgym_sizeof_plan_map(void) { return (int)sizeof(navgym_plan_map_t); }
 int navgym_sizeof_move_args(void) { return (int)sizeof(navgym_move_args_t); }
+
+int navgym_policy_features(const float *scan, int n, const float *w1, const float *b1, const float *w2,
+                           const float *b2, float *features, void *stream)
+{
+    if (n <= 0) return 0;
+    if (!scan || !w1 || !b1 || !w2 || !b2 || !features) return (int)cudaErrorInvalidValue;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = n < 4 * sms ? n : 4 * sms;  // 4 CTAs of 48 KB shared memory per SM
+    policy_features_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(scan, n, w1, b1, w2, b2, features);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
 
 int navgym_peds_move(const navgym_move_args_t *args, void *stream)
 {

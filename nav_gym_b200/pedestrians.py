@@ -281,13 +281,13 @@ class PedestrianSim(object):
         self._plan(respawn)
         if respawn is not None:
             self._scan(respawn)  # first scans of the respawned pedestrians (env.py:808-815)
-        x = preprocess_scan(self.scan).reshape(self.B * self.P, 1, -1)
         goal, speed = self.goal_local.reshape(-1, 2), self.prev_action.reshape(-1, 2)
-        self._mean.copy_(self._policy_mean(x, goal, speed).reshape(self.B, self.P, 2))
+        self._mean.copy_(self._policy_mean(self.scan.reshape(self.B * self.P, -1), goal, speed).reshape(self.B, self.P, 2))
         self._call(self.lib.navgym_peds_move, self.move_args, 'peds_move')
         env._peds_emit(advance=False)
 
     def _policy_mean(self, x, goal, speed):
+        """x: the raw scans [N, 512] in metres."""
         if self.precision == 'bf16':
             with torch.autocast('cuda', dtype=torch.bfloat16):
                 return self._mean_fp(x, goal, speed).float()
@@ -303,13 +303,22 @@ class PedestrianSim(object):
     def _mean_fp(self, x, goal, speed):
         p = self.policy
         if not self.fold_frames:
-            return p.mean(x.expand(-1, 3, -1).contiguous(), goal, speed)
+            x3 = preprocess_scan(x)[:, None, :].expand(-1, 3, -1).contiguous()
+            return p.mean(x3, goal, speed)
         # env.py:647 hands the newest scan to all three input frames, so the first convolution
-        # sees three identical channels: sum its weights over them once and convolve one
-        w = p.act_fea_cv1.weight.sum(dim=1, keepdim=True)
-        h = F.relu(F.conv1d(x, w, p.act_fea_cv1.bias, stride=2, padding=1))
-        h = F.relu(p.act_fea_cv2(h))
-        h = F.relu(p.act_fc1(h.reshape(h.shape[0], -1)))
+        # sees three identical channels: sum its weights over them once and convolve one.  The
+        # two convolutions run in one kernel of the library (activations never leave shared
+        # memory); the dense layers are torch / cuBLAS.
+        n = x.shape[0]
+        if getattr(self, '_feat', None) is None or self._feat.shape[0] != n:
+            self._feat = torch.empty(n, 4096, dtype=torch.float32, device=self.device)
+        w1 = p.act_fea_cv1.weight.float().sum(dim=1).contiguous()
+        self._w = (w1, p.act_fea_cv1.bias.float().contiguous(), p.act_fea_cv2.weight.float().contiguous(),
+                   p.act_fea_cv2.bias.float().contiguous())
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.navgym_policy_features(_ptr(x), n, *[_ptr(t) for t in self._w], _ptr(self._feat),
+                                                       self.env._stream()), 'policy_features')
+        h = F.relu(p.act_fc1(self._feat))
         h = F.relu(p.act_fc2(torch.cat((h, goal, speed), dim=-1)))
         return torch.cat((torch.sigmoid(p.actor1(h)), torch.tanh(p.actor2(h))), dim=-1)
 
