@@ -1187,9 +1187,11 @@ __global__ void peds_move_kernel(const navgym_move_args_t a)
 // ------------------------------------------------------------------ pedestrian policy front end
 // (include/navgym_b200.h, navgym_policy_features.)  128 threads; a CTA keeps the second
 // convolution's weights in shared memory and walks over pedestrians: conv1 fills h1 in shared
-// memory, then thread p accumulates output position p of all 32 channels of conv2 in registers
-// (weights broadcast as float4 over 4 output channels: one LDS.128 per 4 FMA).
-#define PF_H1 260  // row pitch of h1: [0] = left pad, [1 + q] = conv1 output q (q < 255), [256] = right pad
+// memory, then conv2 is register-tiled: warp w owns output channels 8w .. 8w + 7, lane l output
+// positions 4l .. 4l + 3 (32 accumulators); per input channel a lane reads its 9 inputs with
+// three loads and the warp's 24 weights as six broadcast LDS.128 -- 9 shared-memory loads per
+// 96 FMA, where one position per thread needed 25.
+#define PF_H1 264  // row pitch of h1 (32-byte multiple): [0] = left pad, [1 + q] = conv1 output q (q < 255), [256] = right pad
 __global__ void __launch_bounds__(128) policy_features_kernel(const float *__restrict__ scan, int n,
                                                               const float *__restrict__ w1, const float *__restrict__ b1,
                                                               const float *__restrict__ w2, const float *__restrict__ b2,
@@ -1215,38 +1217,48 @@ __global__ void __launch_bounds__(128) policy_features_kernel(const float *__res
             xs[1 + i] = (float)(r / 6.0 - 0.5);  // env.py:627-629, 648
         }
         __syncthreads();
-        for (int i = t; i < 32 * 255; i += 128) {
-            const int c = i / 255, q = i - c * 255;
-            float acc = b1s[c];
+        {   // conv1: thread t owns output positions t and t + 128 of every channel
+            float xa[5], xb[5];
 #pragma unroll
-            for (int k = 0; k < 5; k++) acc = fmaf(w1s[c * 5 + k], xs[2 * q + k], acc);  // input 2q - 1 + k
-            h1[c * PF_H1 + 1 + q] = fmaxf(acc, 0.0f);
-        }
-        __syncthreads();
-        float acc[32];
+            for (int k = 0; k < 5; k++) { xa[k] = xs[2 * t + k]; xb[k] = t < 127 ? xs[2 * (t + 128) + k] : 0.0f; }  // input 2q - 1 + k
+#pragma unroll 4
+            for (int c = 0; c < 32; c++) {
+                float a0 = b1s[c], a1 = a0;
 #pragma unroll
-        for (int co = 0; co < 32; co++) acc[co] = b2s[co];
-#pragma unroll 2
-        for (int ci = 0; ci < 32; ci++) {
-            const float2 a01 = *reinterpret_cast<const float2 *>(h1 + ci * PF_H1 + 2 * t);  // inputs 2p - 1, 2p
-            const float a2 = h1[ci * PF_H1 + 2 * t + 2];                                    // input 2p + 1
-            const float av[3] = {a01.x, a01.y, a2};
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const float4 *wr = reinterpret_cast<const float4 *>(w2s + (ci * 3 + k) * 32);
-#pragma unroll
-                for (int c4 = 0; c4 < 8; c4++) {
-                    const float4 w = wr[c4];
-                    acc[4 * c4 + 0] = fmaf(av[k], w.x, acc[4 * c4 + 0]);
-                    acc[4 * c4 + 1] = fmaf(av[k], w.y, acc[4 * c4 + 1]);
-                    acc[4 * c4 + 2] = fmaf(av[k], w.z, acc[4 * c4 + 2]);
-                    acc[4 * c4 + 3] = fmaf(av[k], w.w, acc[4 * c4 + 3]);
-                }
+                for (int k = 0; k < 5; k++) { a0 = fmaf(w1s[c * 5 + k], xa[k], a0); a1 = fmaf(w1s[c * 5 + k], xb[k], a1); }
+                h1[c * PF_H1 + 1 + t] = fmaxf(a0, 0.0f);
+                if (t < 127) h1[c * PF_H1 + 129 + t] = fmaxf(a1, 0.0f);
             }
         }
-        float *o = out + (size_t)ped * 4096 + t;
+        __syncthreads();
+        const int wco = (t >> 5) * 8, p0 = (t & 31) * 4;
+        float acc[8][4];
 #pragma unroll
-        for (int co = 0; co < 32; co++) o[co * 128] = fmaxf(acc[co], 0.0f);
+        for (int c = 0; c < 8; c++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[c][j] = b2s[wco + c];
+#pragma unroll 2
+        for (int ci = 0; ci < 32; ci++) {
+            // inputs 2 p0 - 1 .. 2 p0 + 7 = h1 row entries 2 p0 .. 2 p0 + 8
+            const float *row = h1 + ci * PF_H1 + 2 * p0;
+            const float4 i0 = *reinterpret_cast<const float4 *>(row), i1 = *reinterpret_cast<const float4 *>(row + 4);
+            const float in[9] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w, row[8]};
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float4 *wr = reinterpret_cast<const float4 *>(w2s + (ci * 3 + k) * 32 + wco);
+                const float4 wa = wr[0], wb = wr[1];
+                const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                for (int c = 0; c < 8; c++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) acc[c][j] = fmaf(in[2 * j + k], wv[c], acc[c][j]);
+            }
+        }
+        float *o = out + (size_t)ped * 4096 + p0;
+#pragma unroll
+        for (int c = 0; c < 8; c++)
+            *reinterpret_cast<float4 *>(o + (wco + c) * 128) =
+                make_float4(fmaxf(acc[c][0], 0.0f), fmaxf(acc[c][1], 0.0f), fmaxf(acc[c][2], 0.0f), fmaxf(acc[c][3], 0.0f));
     }
 }
 
