@@ -1,5 +1,5 @@
 import os, sys
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import numpy as np, torch, torch.nn.functional as F
 from nav_gym_b200.pedestrians import HumanPolicy
 def t(fn, n=20):

@@ -1,5 +1,5 @@
 import sys, ctypes as C
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import torch
 from nav_gym_b200 import _lib
 from nav_gym_b200.pedestrians import HumanPolicy
