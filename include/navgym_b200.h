@@ -117,6 +117,13 @@ typedef struct {
      * observation rows) instead of three. */
     float *reward_mirror;
     uint8_t *done_mirror;
+    /* optional pedestrian geometry of the NEXT episode (same layouts as discs / ndisc / segs /
+     * nseg; discs_reset == NULL = none): the first scan after an auto-reset is taken against it
+     * instead of the ended episode's pedestrians. */
+    const float *discs_reset;
+    const int32_t *ndisc_reset;
+    const float *segs_reset;
+    const int32_t *nseg_reset;
 } navgym_step_args_t;
 
 /* ---- fused hot path: NavGymEnv.step (env.py:591-728) over num_envs environments ------ */
@@ -261,11 +268,17 @@ typedef struct {
     int32_t *goal_id;         /* [num_envs][max_ped] in/out */
     double *waypoint;         /* [num_envs][max_ped][2] in/out, NaN = none yet */
     float *goal_local;        /* [num_envs][max_ped][2] out */
-    /* respawn (env.py:785-806) of the pedestrians of environments with respawn[e] != 0 (NULL =
-     * none), before the routing: a free cost-map cell at least min_robot_dist from the robot
-     * (robot_state = navgym_step_args_t.state; up to 6 draws), heading U[0, 2 pi), preferred
-     * speed U[v_pref_lo, v_pref_hi], legs with probability has_legs_ratio, a goal field; odometry,
-     * velocity and previous action zeroed.  pose is written, hence not const here. */
+    /* respawn (env.py:785-806).  Every call draws, for every pedestrian slot, the pedestrian of
+     * the environment's NEXT episode into the cand_* arrays: a free cost-map cell at least
+     * min_robot_dist from where the robot will start (up to 6 draws), heading U[0, 2 pi),
+     * preferred speed U[v_pref_lo, v_pref_hi], legs with probability has_legs_ratio, a goal
+     * field.  "Where the robot will start" is the spawn tuple navgym_step_batch draws on auto-reset
+     * (same Philox stream: robot_seed, global env id, episodes[e]; robot_maps / spawn_pool /
+     * num_maps / resample_map as in navgym_step_args_t) when cand_next_spawn != 0, else the
+     * robot's current pose (robot_state = navgym_step_args_t.state).  cand_rows (layout of
+     * navgym_peds_args_t.peds) feed navgym_peds_advance for navgym_step_args_t.discs_reset /
+     * segs_reset.  Environments with respawn[e] != 0 (NULL = none) first ADOPT the candidates
+     * drawn by the previous call: odometry, velocity and previous action zeroed, route reset. */
     const uint8_t *respawn;
     const double *free_xy;
     const double *robot_state;
@@ -276,6 +289,17 @@ typedef struct {
     double *dist_travelled;   /* [num_envs][max_ped][3] */
     double *vel;              /* [num_envs][max_ped][2] */
     float *prev_action;       /* [num_envs][max_ped][2] */
+    double *cand_pose;        /* [num_envs][max_ped][3]; NULL = no candidates, no respawn */
+    double *cand_v_pref;
+    uint8_t *cand_legs;
+    int32_t *cand_goal;
+    float *cand_rows;         /* [num_envs][max_ped][NAVGYM_PED_F] */
+    const navgym_map_t *robot_maps;
+    const double *spawn_pool;
+    const int32_t *episodes;
+    uint64_t robot_seed;
+    int32_t num_maps, resample_map;
+    int32_t cand_next_spawn, _pad2;
 } navgym_plan_args_t;
 int navgym_peds_plan(const navgym_plan_args_t *args, void *stream);
 

@@ -82,6 +82,7 @@ class StepArgs(C.Structure):
         ('done', _P), ('is_success', _P), ('is_crash', _P), ('truncated', _P),
         ('distance', _P), ('hits', _P), ('sched', _P),
         ('reward_mirror', _P), ('done_mirror', _P),
+        ('discs_reset', _P), ('ndisc_reset', _P), ('segs_reset', _P), ('nseg_reset', _P),
     ]
 
 
@@ -121,7 +122,11 @@ class PlanArgs(C.Structure):
                 ('min_robot_dist', C.c_double), ('v_pref_lo', C.c_double), ('v_pref_hi', C.c_double),
                 ('has_legs_ratio', C.c_double),
                 ('pose_rw', _P), ('v_pref', _P), ('has_legs', _P), ('dist_travelled', _P), ('vel', _P),
-                ('prev_action', _P)]
+                ('prev_action', _P),
+                ('cand_pose', _P), ('cand_v_pref', _P), ('cand_legs', _P), ('cand_goal', _P), ('cand_rows', _P),
+                ('robot_maps', _P), ('spawn_pool', _P), ('episodes', _P), ('robot_seed', C.c_uint64),
+                ('num_maps', C.c_int32), ('resample_map', C.c_int32),
+                ('cand_next_spawn', C.c_int32), ('_pad2', C.c_int32)]
 
 
 class MoveArgs(C.Structure):

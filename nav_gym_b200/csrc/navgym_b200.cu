@@ -457,8 +457,8 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
             pass_setup(sm, m0, a, TPB * MARCH_SLOTS);  // first pass: the map descriptor is already here
         }
     }
-    const int nd = a.discs ? min(a.ndisc[e], a.max_disc) : 0;
-    const int ns = a.segs ? min(a.nseg[e], a.max_seg) : 0;
+    int nd = a.discs ? min(a.ndisc[e], a.max_disc) : 0;
+    int ns = a.segs ? min(a.nseg[e], a.max_seg) : 0;
     int pass = IS_RESET_KERNEL ? PASS_RESET : PASS_STEP;
     float *orow = a.obs + (size_t)e * a.obs_stride;
 
@@ -618,8 +618,10 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
         // One warp per obstacle, lanes across the beams of its angular window.
         if (ns + nd > 0) {
             if (WPE > 1) __syncthreads(); else __syncwarp();
-            const float *discs = a.discs + (size_t)e * a.max_disc * 3;
-            const float *segs = a.segs + (size_t)e * a.max_seg * 4;
+            // (the first scan after an auto-reset sees the next episode's pedestrians, if given)
+            const bool nxt = !IS_RESET_KERNEL && pass == PASS_RESET && a.discs_reset != nullptr;
+            const float *discs = (nxt ? a.discs_reset : a.discs) + (size_t)e * a.max_disc * 3;
+            const float *segs = (nxt ? a.segs_reset : a.segs) + (size_t)e * a.max_seg * 4;
             for (int o = warp; o < ns + nd; o += WPE) {
                 int k0, cnt;
                 if (o < ns) {
@@ -788,6 +790,10 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
             }
             if (WPE > 1) __syncthreads(); else __syncwarp();
             pass = sm.next_pass;
+            if (pass == PASS_RESET && a.discs_reset != nullptr) {
+                nd = min(a.ndisc_reset[e], a.max_disc);
+                ns = a.segs_reset ? min(a.nseg_reset[e], a.max_seg) : 0;
+            }
             if (pass != PASS_END) continue;
         }
         break;
@@ -1064,28 +1070,12 @@ __global__ void peds_plan_kernel(const navgym_plan_args_t a)
     const int e = n / a.max_ped, slot = n - e * a.max_ped;
     if (a.nped && slot >= a.nped[e]) return;
     const navgym_plan_map_t m = a.maps[a.map_id[e]];
-    if (a.respawn && a.respawn[e] && m.free_count > 0) {
-        // env.py:785-806: a new pedestrian for the new episode
-        const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-        const uint32_t ge = (uint32_t)(a.env_offset + e);
-        const size_t B = (size_t)a.num_envs;
-        const double rx = a.robot_state[NAVGYM_S_PX * B + e], ry = a.robot_state[NAVGYM_S_PY * B + e];
-        const uint4 r0 = philox4x32_10(make_uint4(ge, (uint32_t)slot, (uint32_t)a.step, 0x5b0au), key);
-        const uint4 r1 = philox4x32_10(make_uint4(ge, (uint32_t)slot, (uint32_t)a.step, 0x5b0bu), key);
-        const uint32_t draws[6] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
-        double sx = 0, sy = 0;
-        for (int i = 0; i < 6; i++) {
-            const long long row = m.free_offset + (long long)(((uint64_t)draws[i] * (uint64_t)m.free_count) >> 32);
-            sx = a.free_xy[2 * row]; sy = a.free_xy[2 * row + 1];
-            if ((sx - rx) * (sx - rx) + (sy - ry) * (sy - ry) >= a.min_robot_dist * a.min_robot_dist) break;
-        }
-        const uint4 r2 = philox4x32_10(make_uint4(ge, (uint32_t)slot, (uint32_t)a.step, 0x5b0cu), key);
-        a.pose_rw[3 * (size_t)n] = sx;
-        a.pose_rw[3 * (size_t)n + 1] = sy;
-        a.pose_rw[3 * (size_t)n + 2] = 6.283185307179586 * (double)u01(r2.x);
-        a.v_pref[n] = a.v_pref_lo + (a.v_pref_hi - a.v_pref_lo) * (double)u01(r2.y);
-        a.has_legs[n] = (double)u01(r2.z) < a.has_legs_ratio;
-        a.goal_id[n] = (int)(((uint64_t)r2.w * (uint64_t)m.num_goals) >> 32);
+    if (a.respawn && a.respawn[e] && a.cand_pose) {
+        // env.py:785-806: the pedestrian drawn for this episode by the previous call
+        for (int i = 0; i < 3; i++) a.pose_rw[3 * (size_t)n + i] = a.cand_pose[3 * (size_t)n + i];
+        a.v_pref[n] = a.cand_v_pref[n];
+        a.has_legs[n] = a.cand_legs[n];
+        a.goal_id[n] = a.cand_goal[n];
         a.waypoint[2 * (size_t)n] = CUDART_NAN;
         a.waypoint[2 * (size_t)n + 1] = CUDART_NAN;
         for (int i = 0; i < 3; i++) a.dist_travelled[3 * (size_t)n + i] = 0.0;
@@ -1137,6 +1127,52 @@ __global__ void peds_plan_kernel(const navgym_plan_args_t a)
     const double c = cos(th), s = sin(th);
     a.goal_local[2 * (size_t)n] = (float)((wx - px) * c + (wy - py) * s);
     a.goal_local[2 * (size_t)n + 1] = (float)(-(wx - px) * s + (wy - py) * c);
+
+    // ---- the pedestrian of this slot in the environment's next episode
+    if (a.cand_pose) {
+        const size_t B = (size_t)a.num_envs;
+        const uint32_t ge = (uint32_t)(a.env_offset + e);
+        double rx = a.robot_state[NAVGYM_S_PX * B + e], ry = a.robot_state[NAVGYM_S_PY * B + e];
+        int nmap = a.map_id[e];
+        if (a.cand_next_spawn && a.robot_maps) {
+            // the spawn tuple step_kernel draws on auto-reset (keep in step with it)
+            const uint4 rnd = philox4x32_10(make_uint4(ge, (uint32_t)(a.episodes ? a.episodes[e] : 0), 0x5eedu, 0xfffffff0u),
+                                            make_uint2((uint32_t)a.robot_seed, (uint32_t)(a.robot_seed >> 32)));
+            int cand_map = nmap;
+            if (a.resample_map && a.num_maps > 1) cand_map = (int)(((uint64_t)rnd.y * (uint64_t)a.num_maps) >> 32);
+            const navgym_map_t m2 = a.robot_maps[cand_map];
+            if (m2.spawn_count > 0) {
+                const long long row = m2.spawn_offset + (long long)(((uint64_t)rnd.x * (uint64_t)m2.spawn_count) >> 32);
+                rx = a.spawn_pool[row * 5];
+                ry = a.spawn_pool[row * 5 + 1];
+                nmap = cand_map;
+            }
+        }
+        const navgym_plan_map_t mc = a.maps[nmap];
+        const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+        const uint4 r0 = philox4x32_10(make_uint4(ge, (uint32_t)slot, (uint32_t)a.step, 0x5b0au), key);
+        const uint4 r1 = philox4x32_10(make_uint4(ge, (uint32_t)slot, (uint32_t)a.step, 0x5b0bu), key);
+        const uint4 r2 = philox4x32_10(make_uint4(ge, (uint32_t)slot, (uint32_t)a.step, 0x5b0cu), key);
+        const uint32_t draws[6] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
+        double sx = rx, sy = ry;
+        for (int i = 0; i < 6 && mc.free_count > 0; i++) {
+            const long long row = mc.free_offset + (long long)(((uint64_t)draws[i] * (uint64_t)mc.free_count) >> 32);
+            sx = a.free_xy[2 * row]; sy = a.free_xy[2 * row + 1];
+            if ((sx - rx) * (sx - rx) + (sy - ry) * (sy - ry) >= a.min_robot_dist * a.min_robot_dist) break;
+        }
+        const double cth = 6.283185307179586 * (double)u01(r2.x);
+        const bool legs = (double)u01(r2.z) < a.has_legs_ratio;
+        a.cand_pose[3 * (size_t)n] = sx;
+        a.cand_pose[3 * (size_t)n + 1] = sy;
+        a.cand_pose[3 * (size_t)n + 2] = cth;
+        a.cand_v_pref[n] = a.v_pref_lo + (a.v_pref_hi - a.v_pref_lo) * (double)u01(r2.y);
+        a.cand_legs[n] = legs;
+        a.cand_goal[n] = (int)(((uint64_t)r2.w * (uint64_t)mc.num_goals) >> 32);
+        float *q = a.cand_rows + (size_t)n * NAVGYM_PED_F;
+        q[0] = (float)sx; q[1] = (float)sy; q[2] = (float)cth;
+        q[9] = 0.0f; q[10] = 0.0f; q[11] = 0.0f;
+        q[12] = legs ? 1.0f : 0.0f;
+    }
 }
 
 // ------------------------------------------------------------------ pedestrian motion
@@ -1729,8 +1765,9 @@ int navgym_peds_plan(const navgym_plan_args_t *args, void *stream)
     if (n <= 0) return 0;
     if (!args->maps || !args->fields || !args->goals || !args->pose || !args->goal_id || !args->waypoint || !args->goal_local)
         return (int)cudaErrorInvalidValue;
-    if (args->respawn && (!args->free_xy || !args->robot_state || !args->pose_rw || !args->v_pref || !args->has_legs ||
-                          !args->dist_travelled || !args->vel || !args->prev_action))
+    if (args->cand_pose && (!args->free_xy || !args->robot_state || !args->pose_rw || !args->v_pref || !args->has_legs ||
+                            !args->dist_travelled || !args->vel || !args->prev_action || !args->cand_v_pref ||
+                            !args->cand_legs || !args->cand_goal || !args->cand_rows))
         return (int)cudaErrorInvalidValue;
     peds_plan_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*args);
     g_launches++;

@@ -158,9 +158,11 @@ class PedestrianSim(object):
     'tf32' or 'bf16' (tensor cores; means move by ~1e-3, the pedestrians' paths are not
     comparable step by step any more).
 
-    Known deviation: with auto_reset the first observation of a new episode is taken inside the
-    robot's fused step, against the previous episode's pedestrians; they respawn (at least 4 m
-    from the new robot pose) before the first action of the episode.
+    Auto-reset: every act() also draws the pedestrians of each environment's NEXT episode (at
+    least 4 m from where the robot's auto-reset will put it -- the same Philox draw the step
+    kernel makes) and hands their geometry to the robot's step as discs_reset / segs_reset, so the
+    first observation of a new episode already sees the new pedestrians; the next act() adopts
+    them for the environments whose episode ended.
     """
 
     def __init__(self, env, max_ped, nped=None, policy=None, v_pref_range=(0.0, 0.6), has_legs_ratio=0.5,
@@ -228,6 +230,31 @@ class PedestrianSim(object):
         a.v_pref_lo, a.v_pref_hi = float(v_pref_range[0]), float(v_pref_range[1])
         a.pose_rw, a.v_pref, a.has_legs = _ptr(self.pose), _ptr(self.v_pref), _ptr(self.has_legs)
         a.dist_travelled, a.vel, a.prev_action = _ptr(self.dist_travelled), _ptr(self.vel), _ptr(self.prev_action)
+        # ---- the next episode's pedestrians (candidates) and their geometry
+        self.cand_pose = torch.zeros(B, P, 3, dtype=f64, device=dev)
+        self.cand_v_pref = torch.zeros(B, P, dtype=f64, device=dev)
+        self.cand_legs = torch.zeros(B, P, dtype=torch.bool, device=dev)
+        self.cand_goal = torch.zeros(B, P, dtype=i32, device=dev)
+        self.cand_rows = torch.zeros(B, P, _lib.PED_F, dtype=f32, device=dev)
+        a.cand_pose, a.cand_v_pref, a.cand_legs = _ptr(self.cand_pose), _ptr(self.cand_v_pref), _ptr(self.cand_legs)
+        a.cand_goal, a.cand_rows = _ptr(self.cand_goal), _ptr(self.cand_rows)
+        ea = env.args
+        a.robot_maps, a.spawn_pool, a.episodes = ea.maps, ea.spawn_pool, ea.episodes
+        a.robot_seed, a.num_maps, a.resample_map = ea.seed, ea.num_maps, ea.resample_map
+        self.cand_discs = torch.zeros_like(env._pdiscs)
+        self.cand_segs = torch.zeros_like(env._psegs)
+        self.cand_nd = torch.zeros_like(env._pnd)
+        self.cand_ns = torch.zeros_like(env._pns)
+        cp = _lib.PedsArgs()
+        for f, _t in _lib.PedsArgs._fields_:
+            setattr(cp, f, getattr(env._pargs, f))
+        cp.advance = 0
+        cp.peds, cp.discs, cp.ndisc = _ptr(self.cand_rows), _ptr(self.cand_discs), _ptr(self.cand_nd)
+        cp.segs, cp.nseg = _ptr(self.cand_segs), _ptr(self.cand_ns)
+        self.cand_pargs = cp
+        if ea.auto_reset:
+            ea.discs_reset, ea.ndisc_reset = _ptr(self.cand_discs), _ptr(self.cand_nd)
+            ea.segs_reset, ea.nseg_reset = _ptr(self.cand_segs), _ptr(self.cand_ns)
         self.plan_args = a
         self._mean = torch.zeros(B, P, 2, dtype=f32, device=dev)
         mv = _lib.MoveArgs()
@@ -250,12 +277,14 @@ class PedestrianSim(object):
         with torch.cuda.device(self.device):
             _lib.check(fn(C.byref(args), self.env._stream()), what)
 
-    def _plan(self, respawn):
+    def _plan(self, respawn, next_spawn=True):
         a = self.plan_args
         self._respawn = respawn  # keep the tensor alive while the launch reads it
         a.respawn = _ptr(respawn)
+        a.cand_next_spawn = int(bool(next_spawn) and bool(self.env.args.auto_reset))
         self._call(self.lib.navgym_peds_plan, a, 'peds_plan')
         a.step += 1
+        self._call(self.lib.navgym_peds_advance, self.cand_pargs, 'peds_advance')  # candidates' geometry
 
     def _scan(self, env_mask=None):
         self._mask = env_mask
@@ -264,8 +293,10 @@ class PedestrianSim(object):
 
     # ---- episode start (env.py:785-815) ------------------------------------------------
     def reset(self):
-        """Spawn every environment's pedestrians (env.py:785-806) and take their first scans."""
-        self._plan(self._all)
+        """Spawn every environment's pedestrians (env.py:785-806) around the robots' current poses
+        and take their first scans."""
+        self._plan(None, next_spawn=False)  # draw them ...
+        self._plan(self._all)               # ... adopt them, and draw the next episode's
         rows = self.env.peds
         rows[..., 0:3] = self.pose.float()
         rows[..., 9:12] = 0.0

@@ -224,3 +224,48 @@ def test_pedestrian_sim_scans_match_oracle_and_routes_descend():
         d_prev, gid_prev = d_now, gid.copy()
         sim.pose[..., :2] = torch.from_numpy(wp).cuda()
     assert changes >= 8  # 32 pedestrians walking 2 m a call for 300 calls: many arrivals
+
+
+def test_auto_reset_first_scan_sees_the_next_episodes_pedestrians():
+    """When an episode ends inside the fused step, the new episode's first observation is taken
+    against the pedestrians drawn for it (candidates of the preceding act()), which the next
+    act() then adopts: at least 4 m from the robot's new start, and the scan equals the
+    oracle's scan of the new pose with exactly that geometry."""
+    from oracle import oracle as orc
+    m, env, sim = _crowd(B=256, P=4, seed=4)
+    env.args.noise_lo = env.args.noise_hi = 0.0
+    env.noise_std.zero_()
+    g = torch.Generator(device='cuda'); g.manual_seed(1)
+    checked = 0
+    dist = orc.edt(np.asarray(m['data']) >= 0.1)
+    for t in range(60):
+        act = torch.rand(256, 2, device='cuda', generator=g) * torch.tensor([0.5, 1.28], device='cuda') + torch.tensor([0, -0.64], device='cuda')
+        sim.act()
+        cand_pose = sim.cand_pose.clone()
+        cd, cnd = sim.cand_discs.clone(), sim.cand_nd.clone()
+        cs, cns = sim.cand_segs.clone(), sim.cand_ns.clone()
+        env.step(act)
+        sim.observe()
+        torch.cuda.synchronize()
+        done = env.done.bool().cpu().numpy()
+        if t < 3:
+            continue  # (noise of the episodes that started before it was switched off)
+        for e in np.where(done)[0][:4]:
+            st = env.state[:, e].cpu().numpy()
+            rob = st[:3]
+            d = np.hypot(*(cand_pose[e, :, :2].cpu().numpy() - rob[:2]).T)
+            assert (d >= 4.0 - 1e-9).all()
+            ob = orc.OracleBatch([m], np.zeros(1, np.int32), rob[None, :2], st[None, 3:5], rob[None, 2:3],
+                                 max_disc=env.max_disc, max_seg=env.max_seg)
+            ob.reset_obs(cd[e][None].cpu().numpy(), cnd[e][None].cpu().numpy(), cs[e][None].cpu().numpy(),
+                         cns[e][None].cpu().numpy())
+            assert np.array_equal(ob.obs[0, :512], env.obs[e, :512].cpu().numpy())
+            checked += 1
+        # the next act() adopts exactly those pedestrians
+        if done.any() and checked >= 3:
+            sim._plan(env.done)
+            torch.cuda.synchronize()
+            for e in np.where(done)[0]:
+                assert torch.equal(sim.pose[e], cand_pose[e])
+            break
+    assert checked >= 3
