@@ -350,7 +350,18 @@ class BatchedNavGym(object):
         robot.v, robot.r = float(st[_lib.S_PV]), float(st[_lib.S_PW])
         robot.vx, robot.vy = robot.v * np.cos(robot.theta), robot.v * np.sin(robot.theta)
         humans = []
-        if self.peds is not None:
+        crowd = getattr(self, 'crowd', None)
+        if crowd is not None:  # policy-driven pedestrians: float64 state of the PedestrianSim
+            n = int(crowd.nped[i].item()) if crowd.nped is not None else crowd.P
+            pose, vel = crowd.pose[i, :n].cpu().numpy(), crowd.vel[i, :n].cpu().numpy()
+            wp, legs = crowd.waypoint[i, :n].cpu().numpy(), crowd.has_legs[i, :n].cpu().numpy()
+            act, vp = crowd.prev_action[i, :n].cpu().numpy(), crowd.v_pref[i, :n].cpu().numpy()
+            for j in range(n):
+                h = Human(float(pose[j, 0]), float(pose[j, 1]), float(pose[j, 2]), float(wp[j, 0]), float(wp[j, 1]), self.args.dt)
+                h.vx, h.vy, h.has_legs, h.v_pref = float(vel[j, 0]), float(vel[j, 1]), bool(legs[j]), float(vp[j])
+                h.v, h.r = float(act[j, 0] * vp[j]), float(act[j, 1] * vp[j])
+                humans.append(h)
+        elif self.peds is not None:
             n = int(self.nped[i].item()) if getattr(self, 'nped', None) is not None else self.peds.shape[1]
             for row in self.peds[i, :n].cpu().numpy():
                 tgt = row[6:8] if row[8] > 0.5 else row[4:6]

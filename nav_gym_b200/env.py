@@ -199,8 +199,6 @@ class NavGymEnv(gym.Env, EzPickle):
         sx, sy, gx, gy, th = pool[np.random.randint(len(pool))]
         self.robot = KetiRobot(sx, sy, th, gx, gy, self.time_step)
         n_h = int(self.env_param['num_humans'])
-        peds = maps.spawn_pedestrians(self.map_info, (sx, sy), n_h, v_pref_range=self.human_v_pref_range,
-                                      has_legs_ratio=self.human_has_legs_ratio)
         self._sim = BatchedNavGym(1, mp, device=self.device, time_step=self.time_step,
                                   distance_threshold=self.distance_threshold,
                                   min_turning_radius=self.min_turning_radius, early_stop=True,
@@ -208,29 +206,42 @@ class NavGymEnv(gym.Env, EzPickle):
                                   num_scan_stack=self.num_scan_stack, **self._reward_kwargs())
         self._sim.set_state([[sx, sy]], [[gx, gy]], [th],
                             noise_std=[self.env_param['scan_noise_std']])
+        self._crowd = None
         if n_h:
-            self._sim.attach_pedestrians(peds[None])
+            # the reference's pedestrians (env.py:617-693, 785-815): CNN policy on their own scans
+            from .pedestrians import PedestrianSim
+            self._crowd = PedestrianSim(self._sim, n_h, policy=self._human_policy(),
+                                        v_pref_range=self.human_v_pref_range,
+                                        has_legs_ratio=self.human_has_legs_ratio,
+                                        seed=int(np.random.randint(2 ** 31)))
         self._sim.reset()
         torch.cuda.synchronize(self._sim.device)
         obs = self._obs()
         self.prev_obs = obs
         return obs
 
+    _policy_cache = None
+
+    def _human_policy(self):
+        """The pedestrian policy network (env.py:112-118).  The reference loads
+        nav_gym_env/human_policy.pth, a blob its repository does not distribute: set
+        NAVGYM_HUMAN_POLICY to such a state_dict to use it, else the weights are random-init."""
+        if NavGymEnv._policy_cache is None:
+            import os
+            import torch
+            from .pedestrians import HumanPolicy
+            pol = HumanPolicy()
+            path = os.environ.get('NAVGYM_HUMAN_POLICY')
+            if path:
+                pol.load_state_dict(torch.load(path, map_location='cpu'))
+            NavGymEnv._policy_cache = pol
+        return NavGymEnv._policy_cache
+
     def _obs(self):
-        sim = self._sim
-        scan = sim.obs[0, :self.num_scan_stack * KetiRobot.n_angles].double().cpu().numpy()
-        tail = sim.tail64[0].cpu().numpy()
-        st = sim.state[:, 0].cpu().numpy()
-        self.robot.px, self.robot.py, self.robot.theta = float(st[0]), float(st[1]), float(st[2])
-        self.humans = []
-        if sim.peds is not None:
-            for row in sim.peds[0].cpu().numpy():
-                h = Human(float(row[0]), float(row[1]), float(row[2]), float(row[6]), float(row[7]), self.time_step)
-                h.v, h.has_legs = float(row[3]), bool(row[12] > 0.5)
-                h.vx, h.vy = h.v * np.cos(h.theta), h.v * np.sin(h.theta)
-                self.humans.append(h)
-        return {'observation': np.concatenate([scan, tail]), 'achieved_goal': tail[2:4].copy(),
-                'desired_goal': np.array([self.robot.gx, self.robot.gy])}
+        view = self._sim.export_env(0)
+        self.robot.px, self.robot.py, self.robot.theta = view.robot.px, view.robot.py, view.robot.theta
+        self.humans = view.humans
+        return view.prev_obs
 
     def step(self, action):
         import torch
@@ -241,7 +252,10 @@ class NavGymEnv(gym.Env, EzPickle):
         if action[1] < self.rotvel_range[0] or action[0] > self.rotvel_range[1]:  # sic, env.py:608
             print('rotvel {} is out of range {}'.format(action[1], self.rotvel_range))
         sim = self._sim
-        sim.step(torch.from_numpy(action[None].astype(np.float32)))
+        if self._crowd is not None:
+            self._crowd.step(torch.from_numpy(action[None].astype(np.float32)))
+        else:
+            sim.step(torch.from_numpy(action[None].astype(np.float32)))
         torch.cuda.synchronize(sim.device)
         obs = self._obs()
         self.robot.v, self.robot.r = float(action[0]), float(action[1])

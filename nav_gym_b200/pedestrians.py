@@ -219,6 +219,7 @@ class PedestrianSim(object):
         # ---- geometry for the robot's lidar goes through the env's pedestrian rows
         env.attach_pedestrians(torch.zeros(B, P, _lib.PED_F, dtype=f32, device=dev), self.nped)
         env.peds_scripted = False  # the sim moves them; env.step only emits their geometry
+        env.crowd = self           # export_env reads the float64 state from here
         a = _lib.PlanArgs()
         a.num_envs, a.max_ped, a.step, a.seed = B, P, 0, int(seed)
         a.env_offset, a.min_goal_dist = int(env.args.env_offset), float(min_goal_dist)
