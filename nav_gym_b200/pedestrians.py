@@ -154,9 +154,10 @@ class PedestrianSim(object):
     (the clipped policy mean, the policy's `speed` input), scan f32 [.., 512], goal_id i32,
     waypoint f64, goal_local f32.
 
-    precision: 'fp32' (default; the policy mean matches the reference's CPU forward to ~1e-5),
-    'tf32' or 'bf16' (tensor cores; means move by ~1e-3, the pedestrians' paths are not
-    comparable step by step any more).
+    precision of the dense layers: 'fp32' (default; the policy mean matches the reference's CPU
+    forward to ~1e-5), 'tf32x3' (the 4096 x 256 layer as three TF32 tensor-core products of the
+    operands' high and low halves: float32-grade results, same tolerance), 'tf32' or 'bf16'
+    (means move by ~1e-3, the pedestrians' paths are not comparable step by step any more).
 
     Auto-reset: every act() also draws the pedestrians of each environment's NEXT episode (at
     least 4 m from where the robot's auto-reset will put it -- the same Philox draw the step
@@ -169,7 +170,7 @@ class PedestrianSim(object):
                  num_goals=32, min_goal_dist=10.0, min_robot_dist=4.0, seed=0, fold_frames=True,
                  precision='fp32'):
         from . import maps as M
-        assert precision in ('fp32', 'tf32', 'bf16')
+        assert precision in ('fp32', 'tf32x3', 'tf32', 'bf16')
         self.env, self.device = env, env.device
         self.B, self.P = env.B, int(max_ped)
         self.dt = float(env.args.dt)
@@ -350,7 +351,23 @@ class PedestrianSim(object):
         with torch.cuda.device(self.device):
             _lib.check(self.lib.navgym_policy_features(_ptr(x), n, *[_ptr(t) for t in self._w], _ptr(self._feat),
                                                        self.env._stream()), 'policy_features')
-        h = F.relu(p.act_fc1(self._feat))
+        if self.precision == 'tf32x3':
+            # x = xh + xl, w = wh + wl with xh, wh exactly representable in TF32 (low 13 mantissa
+            # bits cleared): x w^T = xh wh^T + xl wh^T + xh wl^T up to the dropped xl wl^T (2^-22)
+            def split(t):
+                hi = (t.contiguous().view(torch.int32) & -8192).view(torch.float32)
+                return hi, t - hi
+            xh, xl = split(self._feat)
+            wh, wl = split(p.act_fc1.weight.float())
+            old = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = True   # for these three products only
+            try:
+                h = xh @ wh.t() + (xl @ wh.t() + xh @ wl.t())
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = old
+            h = F.relu(h + p.act_fc1.bias)
+        else:
+            h = F.relu(p.act_fc1(self._feat))
         h = F.relu(p.act_fc2(torch.cat((h, goal, speed), dim=-1)))
         return torch.cat((torch.sigmoid(p.actor1(h)), torch.tanh(p.actor2(h))), dim=-1)
 

@@ -125,6 +125,25 @@ def _crowd(B=64, P=6, seed=0, **kw):
     return m, env, PedestrianSim(env, P, seed=seed, **kw)
 
 
+@pytest.mark.parametrize('precision,tol', [('fp32', 1e-5), ('tf32x3', 1e-5), ('tf32', 5e-3), ('bf16', 2e-2)])
+def test_policy_precisions(precision, tol):
+    """PedestrianSim's policy forward in each precision mode against torch's float32 forward."""
+    m, env, sim = _crowd(B=32, P=8, seed=3, precision=precision)
+    from nav_gym_b200.pedestrians import preprocess_scan
+    x = sim.scan.reshape(-1, 512)
+    goal, speed = sim.goal_local.reshape(-1, 2), torch.rand(32 * 8, 2, device='cuda')
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            want = sim.policy.mean(preprocess_scan(x)[:, None, :].expand(-1, 3, -1).contiguous(), goal, speed)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    with torch.no_grad():
+        got = sim._policy_mean(x, goal, speed)
+    assert float((got - want).abs().max()) < tol
+
+
 def test_pedestrian_sim_follows_the_reference_step_order():
     """One PedestrianSim step against a by-hand evaluation of env.py:617-693 on the same state:
     policy mean from the previous scan / local goal / previous action, Human.set_vel with the
