@@ -259,7 +259,7 @@ def main():
     obs_h = torch.empty(B, NB + 7, dtype=torch.float32).pin_memory()
     rew_h = torch.empty(B, dtype=torch.float32).pin_memory()
     done_h = torch.empty(B, dtype=torch.uint8).pin_memory()
-    Ke = min(K, 200)
+    Ke = min(K, 1000)
     for i in range(30):
         env.step_host(act_h[i % n_bank], obs_h, rew_h, done_h)
     barrier()
@@ -285,12 +285,23 @@ def main():
                 if i + 1 < n:
                     cur_np[b0:b1] = nxt[b0:b1]        # "policy": the group's next actions
                     env.submit_host(g)
-    pipelined(30)
+    pipelined(60)
     barrier()
     t_s = time.perf_counter()
     pipelined(Ke)
     barrier()
     e2e_ms = (time.perf_counter() - t_s) * 1e3
+
+    # the same bytes with no simulation at all: what this box's PCIe allows for the copy pattern
+    streams = [torch.cuda.Stream(device=dev) for _ in bounds]
+    torch.cuda.synchronize(dev)
+    t_s = time.perf_counter()
+    for i in range(Ke):
+        for s_, (b0, b1) in zip(streams, bounds):
+            with torch.cuda.stream(s_):
+                obs_h[b0:b1].copy_(env.obs[b0:b1], non_blocking=True)
+    torch.cuda.synchronize(dev)
+    copy_only_ms = (time.perf_counter() - t_s) * 1e3
 
     t = torch.tensor([total_ms, e2e_ms, e2e_sync_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -336,6 +347,8 @@ def main():
                         "groups in flight; a group's next actions are submitted only after its "
                         "previous results landed") % n_groups,
                 "sync_value": world * B * Ke / (e2e_sync_ms * 1e-3),
+                "copy_only_value": B * Ke / (copy_only_ms * 1e-3),
+                "copy_only_note": "rank 0's observation rows copied D2H in the same chunks with no stepping: the PCIe ceiling of the e2e figure, per GPU",
                 "sync_api": "BatchedNavGym.step_host (navgym_step_batch_host), one blocking call per step"},
         "gpu_launches": launches,
         "clocks": clocks,

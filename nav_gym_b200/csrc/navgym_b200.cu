@@ -1550,7 +1550,8 @@ navgym_host_pipe_t *navgym_host_pipe_create(int chunks, int num_envs, int longes
     cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi is the numerically lowest = highest priority
     for (int c = 0; c <= chunks; c++) p->b0[c] = (int)((long long)num_envs * c / chunks);
     for (int c = 0; c < chunks; c++) {
-        int prio = hi + c;
+        static const int spread = env_int("NAVGYM_PIPE_PRIO", 1);
+        int prio = spread ? hi + c : lo;
         if (prio > lo) prio = lo;
         if (cudaStreamCreateWithPriority(&p->streams[c], cudaStreamNonBlocking, prio) != cudaSuccess) { delete p; return nullptr; }
         p->sched[c] = nullptr;
