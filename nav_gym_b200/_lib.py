@@ -39,7 +39,8 @@ def _nvcc():
 def build(force=False, verbose=False):
     """Compile the CUDA library for sm_100a (cross-compiles without a GPU)."""
     if not force and os.path.exists(SO):
-        newest = max(os.path.getmtime(SRC), os.path.getmtime(HDR))
+        csrc = os.path.dirname(SRC)  # navgym_b200.cu includes the other files of csrc/
+        newest = max([os.path.getmtime(HDR)] + [os.path.getmtime(os.path.join(csrc, f)) for f in os.listdir(csrc)])
         if os.path.getmtime(SO) >= newest:
             return SO
     nvcc = _nvcc()

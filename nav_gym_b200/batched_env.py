@@ -3,7 +3,7 @@
 Host-side mirror of the reference's NavGymEnv.step contract (env.py:591-728) for a batch:
 ``step(actions[B,2]) -> obs[B,519], reward[B], done[B], info`` with every tensor resident on
 the device.  All arithmetic happens in the hand-written sm_100a kernels of
-csrc/navgym_b200.cu, reached through the C ABI of include/navgym_b200.h via ctypes; torch is
+csrc/ (navgym_b200.cu and the kernels it includes), reached through the C ABI of include/navgym_b200.h via ctypes; torch is
 used only for device memory and streams.  There is no CPU fallback.
 """
 import ctypes as C

@@ -1,0 +1,438 @@
+// pedestrian_kernels.cuh -- part of navgym_b200.cu (included there; one translation unit).
+// The pedestrians of env.py:617-693 on the device: their lidar, route following, motion, the
+// policy network's convolutional front end, and the geometry the robot's lidar sees.
+// ------------------------------------------------------------------ pedestrian lidar
+// The scan every simulated pedestrian takes of its surroundings (env.py:683-693): map raycast
+// from its own pose + the closed footprints of the robot and the other pedestrians, clipped,
+// no noise.  One CTA per agent, threads across beams; the same canonical march / segment
+// arithmetic as the robot's scan.
+// World-frame closed footprint of an agent at (x, y, th) as 4 segments (env.py:408-414):
+// float64 rotation + translation, vertices rounded to float32.
+__device__ __forceinline__ void footprint_segments(double x, double y, double th, const double *fp, float4 *out)
+{
+    const double c = cos(th), s = sin(th);
+    float wx[4], wy[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        wx[i] = (float)(c * fp[2 * i] - s * fp[2 * i + 1] + x);
+        wy[i] = (float)(s * fp[2 * i] + c * fp[2 * i + 1] + y);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[i] = make_float4(wx[i], wy[i], wx[(i + 1) & 3], wy[(i + 1) & 3]);
+}
+
+#define NAVGYM_SCAN_SEGS 128  // nearby-footprint segments kept per agent in crowd mode
+__global__ void __launch_bounds__(128) agent_scan_kernel(const navgym_scan_args_t a)
+{
+    __shared__ float4 near_segs[NAVGYM_SCAN_SEGS];
+    __shared__ int n_near;
+    const int n = blockIdx.x;
+    const int e = n / a.agents_per_env, slot = n - e * a.agents_per_env;
+    if (a.env_mask && !a.env_mask[e]) return;
+    const int live = a.nagent ? min(a.nagent[e], a.agents_per_env) : a.agents_per_env;
+    if (slot >= live) return;
+    const double *p = a.pose + (size_t)n * 3;
+    const float lx = (float)p[0], ly = (float)p[1], lt = (float)p[2];  // env.py:386
+    const navgym_map_t m = a.maps[a.map_id[e]];
+    const float *dist = a.edt_pool + m.edt_offset;
+    const int ci = xy_to_cell(lx, m.ox, m.res, m.H, a.cell_rule);
+    const int cj = xy_to_cell(ly, m.oy, m.res, m.W, a.cell_rule);
+    const float max_range = (float)((double)m.W * (double)m.H);
+    const float t_stop = a.t_stop > 0.0f ? fminf(a.t_stop, max_range) : max_range;
+    const float res32 = (float)m.res;
+    int ns = 0, s0 = -1, s1 = -1;
+    const float4 *segs = nullptr;
+    if (a.segs) {
+        ns = a.nseg ? min(a.nseg[e], a.max_seg) : 0;
+        segs = reinterpret_cast<const float4 *>(a.segs) + (size_t)e * a.max_seg;
+        if (a.skip) { s0 = a.skip[2 * (size_t)n]; s1 = s0 + a.skip[2 * (size_t)n + 1]; }
+    } else if (a.robot_state) {
+        // crowd mode: thread 0 = the robot, thread 1 + j = agent j of this environment
+        if (threadIdx.x == 0) n_near = 0;
+        __syncthreads();
+        const int o = threadIdx.x;
+        if (o <= live && o != slot + 1 && 4 * (live + 1) <= NAVGYM_SCAN_SEGS) {
+            double ox, oy, oth;
+            const double *fp;
+            if (o == 0) {
+                const size_t B = (size_t)a.num_envs;
+                ox = a.robot_state[NAVGYM_S_PX * B + e]; oy = a.robot_state[NAVGYM_S_PY * B + e];
+                oth = a.robot_state[NAVGYM_S_TH * B + e];
+                fp = a.robot_fp;
+            } else {
+                const double *q = a.pose + ((size_t)e * a.agents_per_env + (o - 1)) * 3;
+                ox = q[0]; oy = q[1]; oth = q[2];
+                fp = a.agent_fp;
+            }
+            float reach = 0.0f;  // farthest footprint vertex from the body origin
+#pragma unroll
+            for (int i = 0; i < 4; i++) reach = fmaxf(reach, hypotf((float)fp[2 * i], (float)fp[2 * i + 1]));
+            const float dc = hypotf((float)ox - lx, (float)oy - ly);
+            if (dc <= a.range_max + reach + 0.01f) {
+                const int at = atomicAdd(&n_near, 4);
+                footprint_segments(ox, oy, oth, fp, near_segs + at);
+            }
+        }
+        __syncthreads();
+        ns = n_near;
+        segs = near_segs;
+    }
+    for (int k = threadIdx.x; k < a.num_beams; k += blockDim.x) {
+        const float h = (float)__dadd_rn(a.lin[k], (double)lt);
+        double sd, cd;
+        dir_sincos((double)h, sd, cd);
+        const float dx = (float)cd, dy = (float)sd;
+        int hx, hy;
+        float r = __fmul_rn(march(dist, m.W, m.H, (float)ci, (float)cj, dx, dy, max_range, t_stop, hx, hy), res32);
+        for (int s = 0; s < ns; s++) {
+            if (s >= s0 && s < s1) continue;
+            const float4 sg = segs[s];
+            r = fminf(r, seg_hit(lx, ly, dx, dy, sg.x, sg.y, sg.z, sg.w));
+        }
+        a.ranges[(size_t)n * a.num_beams + k] = fminf(fmaxf(r, 0.0f), a.range_max);
+    }
+}
+
+// ------------------------------------------------------------------ pedestrian routes
+// (include/navgym_b200.h, navgym_plan_args_t.)  One thread per pedestrian.
+__device__ __forceinline__ int plan_cell(double v, double origin, double res, int dim)
+{
+    int c = (int)floor((v - origin) / res);
+    return c < 0 ? 0 : (c >= dim ? dim - 1 : c);
+}
+
+// From cell (cx, cy) walk the field downhill until the cell centre is more than 2 m from the
+// starting point (sx, sy) or the goal cell is reached.  Returns false on an unreachable cell.
+__device__ __forceinline__ bool plan_advance(const uint16_t *f, const navgym_plan_map_t &m, int cx, int cy,
+                                             double sx, double sy, double &wx, double &wy, bool &is_goal)
+{
+    unsigned d = f[cy * m.W + cx];
+    is_goal = false;
+    if (d == 65535u) return false;
+    for (int it = 0; it < 64; it++) {
+        if (d == 0u) { is_goal = true; break; }
+        int bx = cx, by = cy;
+        unsigned bd = d;
+        if (cx > 0 && f[cy * m.W + cx - 1] < bd) { bd = f[cy * m.W + cx - 1]; bx = cx - 1; by = cy; }
+        if (cx + 1 < m.W && f[cy * m.W + cx + 1] < bd) { bd = f[cy * m.W + cx + 1]; bx = cx + 1; by = cy; }
+        if (cy > 0 && f[(cy - 1) * m.W + cx] < bd) { bd = f[(cy - 1) * m.W + cx]; bx = cx; by = cy - 1; }
+        if (cy + 1 < m.H && f[(cy + 1) * m.W + cx] < bd) { bd = f[(cy + 1) * m.W + cx]; bx = cx; by = cy + 1; }
+        if (bd >= d) break;  // local minimum that is not the goal: cannot happen on a BFS field
+        cx = bx; cy = by; d = bd;
+        wx = m.ox + (cx + 0.5) * m.res;
+        wy = m.oy + (cy + 0.5) * m.res;
+        if ((wx - sx) * (wx - sx) + (wy - sy) * (wy - sy) > 4.0) return true;
+    }
+    wx = m.ox + (cx + 0.5) * m.res;
+    wy = m.oy + (cy + 0.5) * m.res;
+    return true;
+}
+
+__global__ void peds_plan_kernel(const navgym_plan_args_t a)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= a.num_envs * a.max_ped) return;
+    const int e = n / a.max_ped, slot = n - e * a.max_ped;
+    if (a.nped && slot >= a.nped[e]) return;
+    const navgym_plan_map_t m = a.maps[a.map_id[e]];
+    if (a.respawn && a.respawn[e] && a.cand_pose) {
+        // env.py:785-806: the pedestrian drawn for this episode by the previous call
+        for (int i = 0; i < 3; i++) a.pose_rw[3 * (size_t)n + i] = a.cand_pose[3 * (size_t)n + i];
+        a.v_pref[n] = a.cand_v_pref[n];
+        a.has_legs[n] = a.cand_legs[n];
+        a.goal_id[n] = a.cand_goal[n];
+        a.waypoint[2 * (size_t)n] = CUDART_NAN;
+        a.waypoint[2 * (size_t)n + 1] = CUDART_NAN;
+        for (int i = 0; i < 3; i++) a.dist_travelled[3 * (size_t)n + i] = 0.0;
+        a.vel[2 * (size_t)n] = a.vel[2 * (size_t)n + 1] = 0.0;
+        a.prev_action[2 * (size_t)n] = a.prev_action[2 * (size_t)n + 1] = 0.0f;
+    }
+    const double px = a.pose[3 * (size_t)n], py = a.pose[3 * (size_t)n + 1], th = a.pose[3 * (size_t)n + 2];
+    const int cx = plan_cell(px, m.ox, m.res, m.W), cy = plan_cell(py, m.oy, m.res, m.H);
+    const size_t fsz = (size_t)m.W * m.H;
+    int g = a.goal_id[n];
+    const double *goals = a.goals + 2 * m.goal_offset;
+    double gx = goals[2 * g], gy = goals[2 * g + 1];
+    double wx = a.waypoint[2 * (size_t)n], wy = a.waypoint[2 * (size_t)n + 1];
+    // 1. arrived (env.py:666-668): a new goal, if one qualifies
+    if ((px - gx) * (px - gx) + (py - gy) * (py - gy) < 0.25) {
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)(a.env_offset + e), (uint32_t)slot, (uint32_t)a.step, 0x9ed5u),
+                                      make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+        const uint32_t draws[4] = {r.x, r.y, r.z, r.w};
+        for (int i = 0; i < 4; i++) {
+            const int c = (int)(((uint64_t)draws[i] * (uint64_t)m.num_goals) >> 32);
+            const double qx = goals[2 * c], qy = goals[2 * c + 1];
+            const double dd = (qx - px) * (qx - px) + (qy - py) * (qy - py);
+            if (c != g && dd > a.min_goal_dist * a.min_goal_dist &&
+                a.fields[m.field_offset + c * fsz + (size_t)cy * m.W + cx] != 65535u) {
+                g = c; gx = qx; gy = qy;
+                wx = CUDART_NAN;
+                break;
+            }
+        }
+        a.goal_id[n] = g;
+    }
+    const uint16_t *f = a.fields + m.field_offset + g * fsz;
+    // 2. / 3. the waypoint: first one from here, later ones from the previous waypoint
+    bool is_goal = (wx == gx) & (wy == gy);
+    if (wx != wx) {
+        if (!plan_advance(f, m, cx, cy, px, py, wx, wy, is_goal)) { wx = gx; wy = gy; is_goal = true; }
+        if (is_goal) { wx = gx; wy = gy; }
+    }
+    for (int it = 0; it < 8 && !is_goal && (px - wx) * (px - wx) + (py - wy) * (py - wy) < 1.0; it++) {
+        const double sx = wx, sy = wy;
+        if (!plan_advance(f, m, plan_cell(sx, m.ox, m.res, m.W), plan_cell(sy, m.oy, m.res, m.H), sx, sy, wx, wy, is_goal)) {
+            is_goal = true;
+        }
+        if (is_goal) { wx = gx; wy = gy; }
+    }
+    a.waypoint[2 * (size_t)n] = wx;
+    a.waypoint[2 * (size_t)n + 1] = wy;
+    // env.py:641-645: the goal in the pedestrian's frame
+    const double c = cos(th), s = sin(th);
+    a.goal_local[2 * (size_t)n] = (float)((wx - px) * c + (wy - py) * s);
+    a.goal_local[2 * (size_t)n + 1] = (float)(-(wx - px) * s + (wy - py) * c);
+
+    // ---- the pedestrian of this slot in the environment's next episode
+    if (a.cand_pose) {
+        const size_t B = (size_t)a.num_envs;
+        const uint32_t ge = (uint32_t)(a.env_offset + e);
+        double rx = a.robot_state[NAVGYM_S_PX * B + e], ry = a.robot_state[NAVGYM_S_PY * B + e];
+        int nmap = a.map_id[e];
+        if (a.cand_next_spawn && a.robot_maps) {
+            // the spawn tuple step_kernel draws on auto-reset (keep in step with it)
+            const uint4 rnd = philox4x32_10(make_uint4(ge, (uint32_t)(a.episodes ? a.episodes[e] : 0), 0x5eedu, 0xfffffff0u),
+                                            make_uint2((uint32_t)a.robot_seed, (uint32_t)(a.robot_seed >> 32)));
+            int cand_map = nmap;
+            if (a.resample_map && a.num_maps > 1) cand_map = (int)(((uint64_t)rnd.y * (uint64_t)a.num_maps) >> 32);
+            const navgym_map_t m2 = a.robot_maps[cand_map];
+            if (m2.spawn_count > 0) {
+                const long long row = m2.spawn_offset + (long long)(((uint64_t)rnd.x * (uint64_t)m2.spawn_count) >> 32);
+                rx = a.spawn_pool[row * 5];
+                ry = a.spawn_pool[row * 5 + 1];
+                nmap = cand_map;
+            }
+        }
+        const navgym_plan_map_t mc = a.maps[nmap];
+        const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+        const uint4 r0 = philox4x32_10(make_uint4(ge, (uint32_t)slot, (uint32_t)a.step, 0x5b0au), key);
+        const uint4 r1 = philox4x32_10(make_uint4(ge, (uint32_t)slot, (uint32_t)a.step, 0x5b0bu), key);
+        const uint4 r2 = philox4x32_10(make_uint4(ge, (uint32_t)slot, (uint32_t)a.step, 0x5b0cu), key);
+        const uint32_t draws[6] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
+        double sx = rx, sy = ry;
+        for (int i = 0; i < 6 && mc.free_count > 0; i++) {
+            const long long row = mc.free_offset + (long long)(((uint64_t)draws[i] * (uint64_t)mc.free_count) >> 32);
+            sx = a.free_xy[2 * row]; sy = a.free_xy[2 * row + 1];
+            if ((sx - rx) * (sx - rx) + (sy - ry) * (sy - ry) >= a.min_robot_dist * a.min_robot_dist) break;
+        }
+        const double cth = 6.283185307179586 * (double)u01(r2.x);
+        const bool legs = (double)u01(r2.z) < a.has_legs_ratio;
+        a.cand_pose[3 * (size_t)n] = sx;
+        a.cand_pose[3 * (size_t)n + 1] = sy;
+        a.cand_pose[3 * (size_t)n + 2] = cth;
+        a.cand_v_pref[n] = a.v_pref_lo + (a.v_pref_hi - a.v_pref_lo) * (double)u01(r2.y);
+        a.cand_legs[n] = legs;
+        a.cand_goal[n] = (int)(((uint64_t)r2.w * (uint64_t)mc.num_goals) >> 32);
+        float *q = a.cand_rows + (size_t)n * NAVGYM_PED_F;
+        q[0] = (float)sx; q[1] = (float)sy; q[2] = (float)cth;
+        q[9] = 0.0f; q[10] = 0.0f; q[11] = 0.0f;
+        q[12] = legs ? 1.0f : 0.0f;
+    }
+}
+
+// ------------------------------------------------------------------ pedestrian motion
+// (include/navgym_b200.h, navgym_move_args_t.)  One thread per pedestrian.
+__global__ void peds_move_kernel(const navgym_move_args_t a)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= a.num_envs * a.max_ped) return;
+    const int e = n / a.max_ped, slot = n - e * a.max_ped;
+    if (a.nped && slot >= a.nped[e]) return;
+    // env.py:655-661
+    const float m0 = fminf(fmaxf(a.mean[2 * (size_t)n], 0.0f), 1.0f);
+    const float m1 = fminf(fmaxf(a.mean[2 * (size_t)n + 1], -1.0f), 1.0f);
+    a.prev_action[2 * (size_t)n] = m0;
+    a.prev_action[2 * (size_t)n + 1] = m1;
+    const double factor = a.v_pref[n];
+    const double v = (double)m0 * factor, w = (double)m1 * factor;
+    // human.py:32-41
+    double x = a.pose[3 * (size_t)n], y = a.pose[3 * (size_t)n + 1];
+    const double th0 = a.pose[3 * (size_t)n + 2];
+    const double vx = v * cos(th0), vy = v * sin(th0);
+    const double th1 = th0 + w * a.dt;
+    x = x + cos(th1) * v * a.dt;
+    y = y + sin(th1) * v * a.dt;
+    const double twopi = 6.283185307179586;
+    double th = fmod(th1, twopi);
+    if (th != 0 && th < 0) th += twopi;
+    a.pose[3 * (size_t)n] = x;
+    a.pose[3 * (size_t)n + 1] = y;
+    a.pose[3 * (size_t)n + 2] = th;
+    a.vel[2 * (size_t)n] = vx;
+    a.vel[2 * (size_t)n + 1] = vy;
+    // env.py:237-255: rotation rate from the previous observation's yaw, world velocity into
+    // the base frame (pose2d inverse_pose2d / apply_tf_to_vel written out), integrated
+    const double prev_yaw = atan2(sin(th0), cos(th0));
+    const double vrot = (th - prev_yaw) / a.dt;
+    const double c = cos(th), s = sin(th);
+    double *d = a.dist_travelled + 3 * (size_t)n;
+    d[0] += (c * vx + s * vy) * a.dt;
+    d[1] += (-s * vx + c * vy) * a.dt;
+    d[2] += vrot * a.dt;
+    float *q = a.rows + (size_t)n * NAVGYM_PED_F;
+    q[0] = (float)x; q[1] = (float)y; q[2] = (float)th;
+    q[9] = (float)d[0]; q[10] = (float)d[1]; q[11] = (float)d[2];
+    q[12] = a.has_legs[n] ? 1.0f : 0.0f;
+}
+
+// ------------------------------------------------------------------ pedestrian policy front end
+// (include/navgym_b200.h, navgym_policy_features.)  128 threads; a CTA keeps the second
+// convolution's weights in shared memory and walks over pedestrians: conv1 fills h1 in shared
+// memory, then conv2 is register-tiled: warp w owns output channels 8w .. 8w + 7, lane l output
+// positions 4l .. 4l + 3 (32 accumulators); per input channel a lane reads its 9 inputs with
+// three loads and the warp's 24 weights as six broadcast LDS.128 -- 9 shared-memory loads per
+// 96 FMA, where one position per thread needed 25.
+#define PF_H1 264  // row pitch of h1 (32-byte multiple): [0] = left pad, [1 + q] = conv1 output q (q < 255), [256] = right pad
+__global__ void __launch_bounds__(128) policy_features_kernel(const float *__restrict__ scan, int n,
+                                                              const float *__restrict__ w1, const float *__restrict__ b1,
+                                                              const float *__restrict__ w2, const float *__restrict__ b2,
+                                                              float *__restrict__ out)
+{
+    __shared__ __align__(16) float w2s[32 * 3 * 32];  // [ci][tap][co]
+    __shared__ __align__(16) float h1[32 * PF_H1];
+    __shared__ float xs[516];                          // [0] = left pad, [1 + i] = input i
+    __shared__ float w1s[32 * 5], b1s[32], b2s[32];
+    const int t = threadIdx.x;
+    for (int i = t; i < 32 * 32 * 3; i += 128) {
+        const int co = i / 96, ci = (i / 3) % 32, k = i % 3;
+        w2s[(ci * 3 + k) * 32 + co] = w2[i];
+    }
+    for (int i = t; i < 160; i += 128) w1s[i] = w1[i];
+    if (t < 32) { b1s[t] = b1[t]; b2s[t] = b2[t]; }
+    for (int c = t; c < 32; c += 128) { h1[c * PF_H1] = 0.0f; h1[c * PF_H1 + 256] = 0.0f; }
+    if (t == 0) { xs[0] = 0.0f; xs[513] = 0.0f; xs[514] = 0.0f; xs[515] = 0.0f; }
+    for (int ped = blockIdx.x; ped < n; ped += gridDim.x) {
+        __syncthreads();  // weights ready / previous pedestrian's h1 no longer read
+        for (int i = t; i < 512; i += 128) {
+            const double r = fmin(fmax((double)scan[(size_t)ped * 512 + i], 0.0), 6.0);
+            xs[1 + i] = (float)(r / 6.0 - 0.5);  // env.py:627-629, 648
+        }
+        __syncthreads();
+        {   // conv1: thread t owns output positions t and t + 128 of every channel
+            float xa[5], xb[5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) { xa[k] = xs[2 * t + k]; xb[k] = t < 127 ? xs[2 * (t + 128) + k] : 0.0f; }  // input 2q - 1 + k
+#pragma unroll 4
+            for (int c = 0; c < 32; c++) {
+                float a0 = b1s[c], a1 = a0;
+#pragma unroll
+                for (int k = 0; k < 5; k++) { a0 = fmaf(w1s[c * 5 + k], xa[k], a0); a1 = fmaf(w1s[c * 5 + k], xb[k], a1); }
+                h1[c * PF_H1 + 1 + t] = fmaxf(a0, 0.0f);
+                if (t < 127) h1[c * PF_H1 + 129 + t] = fmaxf(a1, 0.0f);
+            }
+        }
+        __syncthreads();
+        const int wco = (t >> 5) * 8, p0 = (t & 31) * 4;
+        float acc[8][4];
+#pragma unroll
+        for (int c = 0; c < 8; c++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[c][j] = b2s[wco + c];
+#pragma unroll 2
+        for (int ci = 0; ci < 32; ci++) {
+            // inputs 2 p0 - 1 .. 2 p0 + 7 = h1 row entries 2 p0 .. 2 p0 + 8
+            const float *row = h1 + ci * PF_H1 + 2 * p0;
+            const float4 i0 = *reinterpret_cast<const float4 *>(row), i1 = *reinterpret_cast<const float4 *>(row + 4);
+            const float in[9] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w, row[8]};
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float4 *wr = reinterpret_cast<const float4 *>(w2s + (ci * 3 + k) * 32 + wco);
+                const float4 wa = wr[0], wb = wr[1];
+                const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                for (int c = 0; c < 8; c++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) acc[c][j] = fmaf(in[2 * j + k], wv[c], acc[c][j]);
+            }
+        }
+        float *o = out + (size_t)ped * 4096 + p0;
+#pragma unroll
+        for (int c = 0; c < 8; c++)
+            *reinterpret_cast<float4 *>(o + (wco + c) * 128) =
+                make_float4(fmaxf(acc[c][0], 0.0f), fmaxf(acc[c][1], 0.0f), fmaxf(acc[c][2], 0.0f), fmaxf(acc[c][3], 0.0f));
+    }
+}
+
+// ------------------------------------------------------------------ scripted pedestrians
+// Pedestrian motion + geometry for the batched simulator (scripted stand-in
+// for the reference's CNN-driven humans whose weights are absent): each pedestrian walks
+// between two waypoints at its preferred speed with Human.set_vel's unicycle update
+// (human.py:32-41), turning at <= 1 rad/s toward the current target, and its leg-gait odometry
+// advances as in _update_dist_travelled (env.py:237-255).  Emits what the robot's lidar sees:
+// two leg discs (pymap2d CSimAgent "legs") for legged pedestrians, the 0.44 x 0.38 m box
+// footprint (human.py:5-10) as four segments otherwise (env.py:398-414), or one trunk disc
+// per pedestrian in trunk mode.  One thread per environment.
+__global__ void peds_advance_kernel(const navgym_peds_args_t a)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.num_envs) return;
+    const int P = a.nped ? min(a.nped[e], a.max_ped) : a.max_ped;
+    float *pp = a.peds + (size_t)e * a.max_ped * NAVGYM_PED_F;
+    float *discs = a.discs + (size_t)e * a.max_disc * 3;
+    float *segs = a.segs ? a.segs + (size_t)e * a.max_seg * 4 : nullptr;
+    int nd = 0, ns = 0;
+    for (int p = 0; p < P; p++) {
+        float *q = pp + p * NAVGYM_PED_F;
+        float x = q[0], y = q[1], th = q[2];
+        const float v = q[3];
+        float tgt = q[8];
+        if (a.advance) {
+            float gx = tgt > 0.5f ? q[6] : q[4], gy = tgt > 0.5f ? q[7] : q[5];
+            if ((gx - x) * (gx - x) + (gy - y) * (gy - y) < 0.25f) {  // reached: turn back
+                tgt = 1.0f - tgt;
+                gx = tgt > 0.5f ? q[6] : q[4];
+                gy = tgt > 0.5f ? q[7] : q[5];
+            }
+            float err = atan2f(gy - y, gx - x) - th;
+            err -= 6.2831853f * rintf(err * 0.15915494f);
+            const float w = fminf(fmaxf(err / a.dt, -1.0f), 1.0f);
+            const float vx = v * cosf(th), vy = v * sinf(th);  // human.py:35-36 (old heading)
+            const float thn = th + w * a.dt;
+            x += cosf(thn) * v * a.dt;
+            y += sinf(thn) * v * a.dt;
+            // leg gait odometry in the base frame (env.py:251-255)
+            const float c = cosf(thn), s_ = sinf(thn);
+            q[9] += (c * vx + s_ * vy) * a.dt;
+            q[10] += (-s_ * vx + c * vy) * a.dt;
+            q[11] += w * a.dt;
+            th = thn - 6.2831853f * floorf(thn * 0.15915494f);
+            q[0] = x; q[1] = y; q[2] = th; q[8] = tgt;
+        }
+        const float c = cosf(th), s_ = sinf(th);
+        if (a.trunk_mode) {
+            if (nd < a.max_disc) { discs[3 * nd] = x; discs[3 * nd + 1] = y; discs[3 * nd + 2] = q[13]; nd++; }
+        } else if (q[12] > 0.5f) {  // legs
+            const float front = 0.3f * cosf(q[9] * (2.0f / 0.3f) + q[11]);
+            const float side = 0.1f * cosf(q[10] * (2.0f / 0.1f) + q[11]) + 0.1f;
+            if (nd + 1 < a.max_disc) {
+                discs[3 * nd] = x + c * front - s_ * side; discs[3 * nd + 1] = y + s_ * front + c * side;
+                discs[3 * nd + 2] = 0.03f; nd++;
+                discs[3 * nd] = x - c * front + s_ * side; discs[3 * nd + 1] = y - s_ * front - c * side;
+                discs[3 * nd + 2] = 0.03f; nd++;
+            }
+        } else if (segs && ns + 3 < a.max_seg) {  // box footprint, closed
+            const float fx[4] = {0.22f, -0.22f, -0.22f, 0.22f}, fy[4] = {0.19f, 0.19f, -0.19f, -0.19f};
+            float wx[4], wy[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { wx[i] = c * fx[i] - s_ * fy[i] + x; wy[i] = s_ * fx[i] + c * fy[i] + y; }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                float *sg = segs + 4 * (ns + i);
+                sg[0] = wx[i]; sg[1] = wy[i]; sg[2] = wx[(i + 1) & 3]; sg[3] = wy[(i + 1) & 3];
+            }
+            ns += 4;
+        }
+    }
+    a.ndisc[e] = nd;
+    if (a.nseg) a.nseg[e] = ns;
+}

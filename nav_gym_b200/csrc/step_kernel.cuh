@@ -1,0 +1,724 @@
+// step_kernel.cuh -- part of navgym_b200.cu (included there; one translation unit).
+// The fused step kernel: NavGymEnv.step (env.py:591-728) for one environment per CTA.
+// ------------------------------------------------------------------ fused step kernel
+// Optional per-phase cycle accounting (tools/phase_prof.py builds with -DNAVGYM_PROFILE).
+#ifdef NAVGYM_PROFILE
+__device__ unsigned long long g_prof[16];
+#define PROF_DECL long long _pt = clock64(); unsigned long long _g_begin; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_g_begin));
+#define PROF_MARK(i) do { if (tid == 0) { long long _n = clock64(); atomicAdd(&g_prof[i], (unsigned long long)(_n - _pt)); _pt = _n; } } while (0)
+#else
+#define PROF_DECL
+#define PROF_MARK(i)
+#endif
+
+struct EnvSmem {
+    int scan[NB];          // float bits of the ranges [m] (non-negative floats order like ints)
+    float2 dir[NB];        // beam directions (cos, sin) of the current pass
+    double red[16];
+    // per-environment scalars parked here between the phases that need them, so the march
+    // loop runs with a small register footprint
+    double px, py, th, gx, gy, ppx, ppy, pyaw, pv, pw, act_v, act_w;
+    double th_spec, yaw_spec;  // heading warp 1 assumed for the final pose, and its yaw
+    int map, steps, episode, next_pass;
+    int next_beam;         // next undealt entry of the survivor list
+    int n_alive;           // beams still marching after the head phase
+    short alive[NB];       // their indices
+    float noise_std;
+    // per-pass scan setup
+    float lx, ly, lt, res32, max_range, t_stop;
+    int ci, cj, W, H;
+    long long edt_off;
+};
+
+enum { PASS_STEP = 0, PASS_RESCAN = 1, PASS_RESET = 2, PASS_END = 3 };
+
+// Angular window of beams that can see an obstacle spanning bearings [phi0, phi0 + width].
+// Beam k looks along lin[k] + theta with lin[k] = ANGLE_MIN + k * step (env.py:388-390).
+__device__ __forceinline__ void beam_window(float phi0, float width, float theta, int &k0, int &cnt)
+{
+    const float step = 0.012271843f, amin = -3.141592f;
+    float rel = phi0 - theta - amin;
+    rel -= 6.2831853f * floorf(rel * 0.15915494f);
+    k0 = (int)floorf(rel / step) - 2;
+    cnt = (int)ceilf(width / step) + 5;
+    if (cnt > NB) cnt = NB;
+}
+
+// float -> cell index with C truncation semantics for x > -1, without the conversion pipe:
+// 2^23 + x rounded toward zero leaves trunc(x) in the mantissa (x in [0, 2^23)).
+__device__ __forceinline__ int trunc_cell(float x)
+{
+    return __float_as_int(__fadd_rz(fmaxf(x, 0.0f), 8388608.0f)) & 0x007fffff;
+}
+
+__device__ __forceinline__ void normal4(uint64_t seed, uint32_t env, uint32_t episode, uint32_t step,
+                                        uint32_t slot, uint32_t group, float (&z)[4])
+{
+    uint4 r = philox4x32_10(make_uint4(env, episode, step, (slot << 16) | group),
+                            make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    float r0 = sqrtf(-2.0f * __logf(u01(r.x))), r1 = sqrtf(-2.0f * __logf(u01(r.z)));
+    float s0, c0, s1, c1;
+    __sincosf(6.283185307179586f * u01(r.y), &s0, &c0);
+    __sincosf(6.283185307179586f * u01(r.w), &s1, &c1);
+    z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
+}
+
+// theta mod 2 pi with the sign of the divisor (numpy's float64 `%`, keti_robot.py:93).  One step
+// turns by far less than 2 pi, so |x| < 4 pi in practice: there fmod is the identity or one
+// exact subtraction (Sterbenz), bit-identical to the library call kept for anything larger.
+__device__ __forceinline__ double wrap_2pi(double x)
+{
+    const double twopi = 6.283185307179586;
+    double r;
+    const double ax = fabs(x);
+    if (ax < twopi) r = x;
+    else if (ax < 2.0 * twopi) r = x < 0 ? __dadd_rn(x, twopi) : __dsub_rn(x, twopi);
+    else r = fmod(x, twopi);
+    if (r != 0 && r < 0) r = __dadd_rn(r, twopi);
+    return r;
+}
+
+// Heading after this step's action (keti_robot.py:86-93); warps 0 and 1 both evaluate it.
+__device__ __forceinline__ double turned_heading(double th0, double w, double dt, double &th1)
+{
+    th1 = __dadd_rn(th0, __dmul_rn(w, dt));
+    return wrap_2pi(th1);
+}
+
+// Per-pass scan setup from the pose in shared memory: float32 lidar pose, origin cell
+// (env.py:386, 419), map geometry.  Run by one thread.
+__device__ __forceinline__ void pass_setup(EnvSmem &sm, const navgym_map_t &m, const navgym_step_args_t &a, int next_beam)
+{
+    sm.lx = (float)sm.px; sm.ly = (float)sm.py; sm.lt = (float)sm.th;
+    sm.ci = xy_to_cell(sm.lx, m.ox, m.res, m.H, a.cell_rule);
+    sm.cj = xy_to_cell(sm.ly, m.oy, m.res, m.W, a.cell_rule);
+    sm.W = m.W; sm.H = m.H; sm.edt_off = m.edt_offset;
+    sm.res32 = (float)m.res;
+    sm.max_range = (float)((double)m.W * (double)m.H);
+    sm.t_stop = fminf(fminf(a.t_stop, sm.max_range), 8.0e6f);
+    sm.n_alive = 0;
+    sm.next_beam = next_beam;
+}
+
+// Tail phase with S survivors per lane in flight, dealt from a shared counter (sm.next_beam
+// starts at S * TPB): a slot whose beam ends takes the next undealt survivor.
+template <int S, int TPB>
+__device__ __forceinline__ void march_tail_slots(EnvSmem &sm, const float *__restrict__ dist, float x0, float y0,
+                                                 int W, int H, float t_stop, int n_alive, int tid)
+{
+    const unsigned FULL = 0xffffffffu;
+    int kb[S];  // the slot's current beam, -1 = none left
+    float t[S], dx[S], dy[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        const int i = s * TPB + tid;
+        kb[s] = i < n_alive ? (int)sm.alive[i] : -1;
+        const int kk = kb[s] >= 0 ? kb[s] : 0;
+        t[s] = __int_as_float(sm.scan[kk]);
+        const float2 dd = sm.dir[kk];
+        dx[s] = dd.x;
+        dy[s] = dd.y;
+    }
+    if (n_alive <= 0) return;
+    for (;;) {
+        float d[S];
+        int cx[S], cy[S];
+        bool inb[S];
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            cx[s] = __float2int_rz(__fmaf_rn(dx[s], t[s], x0));
+            cy[s] = __float2int_rz(__fmaf_rn(dy[s], t[s], y0));
+            inb[s] = ((unsigned)cx[s] < (unsigned)W) & ((unsigned)cy[s] < (unsigned)H);
+            const unsigned idx = (inb[s] & (kb[s] >= 0)) ? (unsigned)(cy[s] * W + cx[s]) : 0u;
+            d[s] = __ldg(dist + idx);
+        }
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            const bool hit = inb[s] & (d[s] <= 0.0f);
+            float tn = __fadd_rn(t[s], fmaxf(__fmul_rn(d[s], 0.999f), 1.0f));
+            const bool fin = !inb[s] | hit | !(tn < t_stop);
+            if (fin & (kb[s] >= 0)) {
+                // absolute hit cell, (y << 16 | x), or -1 for "no hit"
+                sm.scan[kb[s]] = hit ? (cy[s] << 16 | cx[s]) : -1;
+                const int i = atomicAdd(&sm.next_beam, 1);
+                kb[s] = -1;
+                if (i < n_alive) {
+                    const int k = sm.alive[i];
+                    kb[s] = k;
+                    tn = __int_as_float(sm.scan[k]);
+                    const float2 dd = sm.dir[k];
+                    dx[s] = dd.x;
+                    dy[s] = dd.y;
+                }
+            }
+            t[s] = tn;
+        }
+        bool live = false;
+#pragma unroll
+        for (int s = 0; s < S; s++) live |= kb[s] >= 0;
+        if (!__any_sync(FULL, live)) break;
+    }
+}
+
+// One CTA = one environment, WPE warps.  Lane l of warp w owns beams l + 32 (w + WPE i),
+// i = 0 .. 16/WPE - 1: at any moment the lanes of a warp work on neighbouring beams, whose
+// EDT gathers share sectors.  Each lane walks its beams through MARCH_SLOTS independent march
+// slots; a slot that finishes a beam immediately starts the lane's next one, so lanes stay
+// busy instead of idling until the slowest beam of a lockstep group ends, and MARCH_SLOTS
+// gathers per lane are in flight.  The three scans a step may need (the step's scan, the
+// crash re-scan env.py:718, the auto-reset first scan) run through ONE copy of the scan code
+// inside a CTA-uniform pass loop.
+#ifndef NAVGYM_HEAD_STEPS
+#define NAVGYM_HEAD_STEPS 4  // samples every beam marches in the lockstep head phase
+#endif
+#ifndef NAVGYM_RISK_MARGIN
+#define NAVGYM_RISK_MARGIN 0.25f  // [m] clearance under which the next step may end the episode
+#endif
+#ifndef NAVGYM_THREADS_PER_SM
+#define NAVGYM_THREADS_PER_SM 1024  // resident threads the register budget is tuned for
+#endif
+template <bool IS_RESET_KERNEL, int WPE, int MARCH_SLOTS>
+__global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) step_kernel(const navgym_step_args_t a)
+{
+    constexpr int BPL = NB / (32 * WPE);  // beams per lane
+    constexpr int TPB = WPE * 32;
+    static_assert(BPL >= MARCH_SLOTS && BPL % MARCH_SLOTS == 0, "beams per lane vs slots");
+    __shared__ EnvSmem sm;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int B = a.num_envs;
+    const long long t_begin = clock64();
+    // Which environment this CTA steps.  With a schedule buffer, CTAs take environments in
+    // descending order of the cycles they cost in the previous step (they change slowly from
+    // step to step), so the longest ones start first and the launch does not end on a lone
+    // straggler; NAVGYM_SCHED_BUCKETS cost classes, bucket 0 = most expensive.
+    int e = a.env_begin + blockIdx.x;
+    int *sched_cnt = nullptr, *sched_list = nullptr;
+    if (!IS_RESET_KERNEL && a.sched) {
+        const int cur = a.sched_phase, nxt = (a.sched_phase + 1) % 3, clr = (a.sched_phase + 2) % 3;
+        int *cnt = a.sched;                                   // [3][NBK]
+        int *lst = a.sched + 3 * NAVGYM_SCHED_BUCKETS;        // [3][NBK][B]
+        const int c = cnt[cur * NAVGYM_SCHED_BUCKETS + (threadIdx.x & 31)];
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += v;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, (int)blockIdx.x < incl);
+        const int b = m ? __ffs(m) - 1 : 31;
+        const int excl = __shfl_sync(0xffffffffu, incl - c, b);
+        e = lst[((size_t)cur * NAVGYM_SCHED_BUCKETS + b) * B + ((int)blockIdx.x - excl)];
+        sched_cnt = cnt + nxt * NAVGYM_SCHED_BUCKETS;
+        sched_list = lst + (size_t)nxt * NAVGYM_SCHED_BUCKETS * B;
+        if (blockIdx.x == 0 && threadIdx.x < NAVGYM_SCHED_BUCKETS) cnt[clr * NAVGYM_SCHED_BUCKETS + threadIdx.x] = 0;
+    }
+    const unsigned FULL = 0xffffffffu;
+    double *S = a.state;
+#define ST(f) S[(size_t)(f) * B + e]
+#define BEAM(i) (tid + TPB * (i))
+
+    PROF_DECL
+    // ---------------- prologue (warp 0): state (lane f holds row f), kinematics ----------
+    // Every global load the prologue needs is issued up front (they only depend on e), the map
+    // descriptor as soon as the map id is back, so one L2 round trip overlaps the next and the
+    // float64 kinematics.  Warp 1 meanwhile evaluates the yaw the epilogue will need (the same
+    // heading arithmetic as warp 0): for every environment that neither rolls back nor resets,
+    // the float64 sincos + atan2 of the final heading leave the critical path.
+    if (WPE > 1 && warp == 1) {
+        double th = ST(NAVGYM_S_TH);
+        if (!IS_RESET_KERNEL) {
+            double th1;
+            th = turned_heading(th, (double)a.actions[2 * (size_t)e + 1], a.dt, th1);
+        }
+        double sn, cn;
+        sincos(th, &sn, &cn);
+        const double yaw = atan2(sn, cn);  // utils.py:5-9
+        if (lane == 0) { sm.th_spec = th; sm.yaw_spec = yaw; }
+    }
+    if (warp == 0) {
+        double sv = lane < NAVGYM_NS ? ST(lane) : 0.0;
+        int steps = a.steps[e];
+        const int map0 = a.map_id[e];
+        const int episode0 = a.episodes ? a.episodes[e] : 0;
+        const float noise_std0 = a.noise_std ? a.noise_std[e] : 0.0f;
+        float2 av = make_float2(0.f, 0.f);
+        if (!IS_RESET_KERNEL) av = *reinterpret_cast<const float2 *>(a.actions + 2 * (size_t)e);
+        const navgym_map_t m0 = a.maps[map0];
+        double px = __shfl_sync(FULL, sv, NAVGYM_S_PX), py = __shfl_sync(FULL, sv, NAVGYM_S_PY);
+        double th0 = __shfl_sync(FULL, sv, NAVGYM_S_TH), th = th0;
+        double act_v = 0, act_w = 0;
+        if (!IS_RESET_KERNEL) {
+            double v = (double)av.x, w = (double)av.y;
+            if (a.min_turn_radius > 0) {  // env.py:595-600
+                double lim = __dmul_rn(fabs(w), a.min_turn_radius);
+                if (v >= 0) v = v > lim ? v : lim;
+                else v = v < -lim ? v : -lim;
+            }
+            act_v = a.min_turn_radius > 0 ? v : (double)av.x;  // env.py:725 (the clamp edits `action`)
+            act_w = (double)av.y;
+            double th1;
+            th = turned_heading(th0, w, a.dt, th1);
+            double s_, c_;
+            sincos(lane == 0 ? th0 : th1, &s_, &c_);  // lanes 0 / 1 in parallel
+            double s0 = __shfl_sync(FULL, s_, 0), c0 = __shfl_sync(FULL, c_, 0);
+            double s1 = __shfl_sync(FULL, s_, 1), c1 = __shfl_sync(FULL, c_, 1);
+            // keti_robot.py:64-93
+            double rx = __dadd_rn(__dmul_rn(0.14474, c0), px);
+            double ry = __dadd_rn(__dmul_rn(0.14474, s0), py);
+            rx = __dadd_rn(rx, __dmul_rn(__dmul_rn(c1, v), a.dt));
+            ry = __dadd_rn(ry, __dmul_rn(__dmul_rn(s1, v), a.dt));
+            px = __dadd_rn(__dmul_rn(-0.14474, c1), rx);
+            py = __dadd_rn(__dmul_rn(-0.14474, s1), ry);
+            steps += 1;  // env.py:592
+        } else {
+            steps = 0;
+        }
+        if (lane == NAVGYM_S_GX) sm.gx = sv;
+        if (lane == NAVGYM_S_GY) sm.gy = sv;
+        if (!IS_RESET_KERNEL) {
+            if (lane == NAVGYM_S_PPX) sm.ppx = sv;
+            if (lane == NAVGYM_S_PPY) sm.ppy = sv;
+            if (lane == NAVGYM_S_PYAW) sm.pyaw = sv;
+            if (lane == NAVGYM_S_PV) sm.pv = sv;
+            if (lane == NAVGYM_S_PW) sm.pw = sv;
+        }
+        if (lane == 0) {
+            sm.px = px; sm.py = py; sm.th = th;
+            sm.act_v = act_v; sm.act_w = act_w;
+            sm.map = map0;
+            sm.steps = steps;
+            sm.episode = episode0;
+            sm.noise_std = noise_std0;
+            if (IS_RESET_KERNEL) { sm.ppx = px; sm.ppy = py; sm.pyaw = 0; sm.pv = 0; sm.pw = 0; }
+            if (WPE == 1) sm.th_spec = CUDART_NAN;
+            pass_setup(sm, m0, a, TPB * MARCH_SLOTS);  // first pass: the map descriptor is already here
+        }
+    }
+    int nd = a.discs ? min(a.ndisc[e], a.max_disc) : 0;
+    int ns = a.segs ? min(a.nseg[e], a.max_seg) : 0;
+    int pass = IS_RESET_KERNEL ? PASS_RESET : PASS_STEP;
+    float *orow = a.obs + (size_t)e * a.obs_stride;
+
+    long long t_pass = t_begin;  // start of the pass that produces the returned observation
+    float margin = CUDART_INF_F; // its smallest clearance over the crash thresholds [m]
+    for (bool first = true;; first = false) {
+        // ---- per-pass setup; the first pass was set up by the prologue
+        if (WPE > 1) __syncthreads(); else __syncwarp();
+        if (!first) {
+            t_pass = clock64();
+            if (tid == 0) pass_setup(sm, a.maps[sm.map], a, TPB * MARCH_SLOTS);
+            if (WPE > 1) __syncthreads(); else __syncwarp();
+        }
+        margin = CUDART_INF_F;
+        PROF_MARK(0);
+        const float lx = sm.lx, ly = sm.ly, lt = sm.lt;
+        PROF_MARK(1);
+        // ---- occupancy-grid march (env.py:425-426).
+        // Every beam of a scan starts on the origin cell, so that first sample (t = 0) is taken
+        // once per environment: either the origin is occupied (all beams end there) or all
+        // beams advance by the same first step.  The march then runs in two phases:
+        //  head: every thread marches its own beams NAVGYM_HEAD_STEPS samples, HB beams at a
+        //        time in lockstep — almost every beam is still alive that early, and the HB
+        //        independent EDT gathers per thread hide the L2 latency by ILP;
+        //  tail: the surviving beams are compacted into a list and dealt out dynamically (a
+        //        lane takes the next survivor whenever its beam ends), so lanes stay busy on
+        //        the long-tailed remainder instead of idling until the slowest beam ends.
+        // The loops only find each beam's hit cell (packed into sm.scan); ranges are computed
+        // afterwards with all lanes active.
+        {
+            const int W = sm.W, H = sm.H, ci = sm.ci, cj = sm.cj;
+            const float x0 = (float)ci, y0 = (float)cj;
+            const float t_stop = sm.t_stop;
+            const float *dist = a.edt_pool + sm.edt_off;
+            asm volatile("" : "+l"(dist));  // keep base + offset folded into one register pair
+            const float d0 = __ldg(dist + cj * W + ci);   // origin cell is clipped into the map
+            const float t1 = fmaxf(__fmul_rn(d0, 0.999f), 1.0f);  // == 0.0f + first step
+            const bool degenerate = (d0 <= 0.0f) | !(t1 < t_stop);
+            constexpr int HB = BPL >= 4 ? 4 : BPL;   // beams in flight per thread in the head phase
+#pragma unroll 1
+            for (int r = 0; r < BPL / HB; r++) {
+                float th_[HB], dxh[HB], dyh[HB];
+                // beam directions (env.py:388-390, 420-424)
+#pragma unroll
+                for (int j = 0; j < HB; j++) {
+                    const int k = BEAM(r * HB + j);
+                    const float h = (float)__dadd_rn(a.lin[k], (double)lt);
+                    double sd, cd;
+                    dir_sincos((double)h, sd, cd);
+                    dxh[j] = (float)cd;
+                    dyh[j] = (float)sd;
+                    sm.dir[k] = make_float2(dxh[j], dyh[j]);
+                    th_[j] = t1;
+                    if (degenerate) { sm.scan[k] = d0 <= 0.0f ? (cj << 16 | ci) : -1; th_[j] = -1.0f; }
+                }
+#pragma unroll 1
+                for (int st = 0; st < NAVGYM_HEAD_STEPS; st++) {
+                    float dv[HB];
+                    int cx[HB], cy[HB];
+                    bool inb[HB];
+#pragma unroll
+                    for (int j = 0; j < HB; j++) {
+                        cx[j] = __float2int_rz(__fmaf_rn(dxh[j], th_[j], x0));
+                        cy[j] = __float2int_rz(__fmaf_rn(dyh[j], th_[j], y0));
+                        inb[j] = ((unsigned)cx[j] < (unsigned)W) & ((unsigned)cy[j] < (unsigned)H);
+                        const unsigned idx = (inb[j] & (th_[j] >= 0.0f)) ? (unsigned)(cy[j] * W + cx[j]) : 0u;
+                        dv[j] = __ldg(dist + idx);
+                    }
+#pragma unroll
+                    for (int j = 0; j < HB; j++) {
+                        const bool alive = th_[j] >= 0.0f;
+                        const bool hit = inb[j] & (dv[j] <= 0.0f);
+                        const float tn = __fadd_rn(th_[j], fmaxf(__fmul_rn(dv[j], 0.999f), 1.0f));
+                        const bool fin = !inb[j] | hit | !(tn < t_stop);
+                        if (alive & fin) sm.scan[BEAM(r * HB + j)] = hit ? (cy[j] << 16 | cx[j]) : -1;
+                        th_[j] = (alive & !fin) ? tn : -1.0f;
+                    }
+                }
+                // survivors: park t in the scan slot and append the beam to the compact list
+#pragma unroll
+                for (int j = 0; j < HB; j++) {
+                    const int k = BEAM(r * HB + j);
+                    const bool alive = th_[j] >= 0.0f;
+                    if (alive) sm.scan[k] = __float_as_int(th_[j]);
+                    const unsigned mk = __ballot_sync(FULL, alive);
+                    int base = 0;
+                    if (lane == 0 && mk) base = atomicAdd(&sm.n_alive, __popc(mk));
+                    base = __shfl_sync(FULL, base, 0);
+                    if (alive) sm.alive[base + __popc(mk & ((1u << lane) - 1u))] = (short)k;
+                }
+            }
+            if (WPE > 1) __syncthreads(); else __syncwarp();  // any lane may be dealt any survivor
+            PROF_MARK(2);
+            {
+                const int n_alive = sm.n_alive;
+                if (MARCH_SLOTS == 1) {
+                    // Warp w owns list entries w, w + WPE, w + 2 WPE, ...; they are dealt to its
+                    // lanes with ballot ranks (no atomics, no cross-warp traffic): a lane whose
+                    // beam ends takes the warp's next undealt entry.
+                    int next_j = 32;                       // warp-uniform: entries dealt so far
+                    int idx = warp + WPE * lane;
+                    int kb = idx < n_alive ? (int)sm.alive[idx] : -1;
+                    float t = __int_as_float(sm.scan[kb >= 0 ? kb : 0]);
+                    float2 dd = sm.dir[kb >= 0 ? kb : 0];
+                    if (__any_sync(FULL, kb >= 0)) {
+                        for (;;) {
+                            const int cx = __float2int_rz(__fmaf_rn(dd.x, t, x0));
+                            const int cy = __float2int_rz(__fmaf_rn(dd.y, t, y0));
+                            const bool inb = ((unsigned)cx < (unsigned)W) & ((unsigned)cy < (unsigned)H);
+                            const unsigned ci_ = (inb & (kb >= 0)) ? (unsigned)(cy * W + cx) : 0u;
+                            const float d = __ldg(dist + ci_);
+                            const bool hit = inb & (d <= 0.0f);
+                            t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+                            const bool fin = (kb >= 0) & (!inb | hit | !(t < t_stop));
+                            const unsigned fm = __ballot_sync(FULL, fin);
+                            if (fin) {
+                                // absolute hit cell, (y << 16 | x), or -1 for "no hit"
+                                sm.scan[kb] = hit ? (cy << 16 | cx) : -1;
+                                idx = warp + WPE * (next_j + __popc(fm & ((1u << lane) - 1u)));
+                                kb = -1;
+                                if (idx < n_alive) {
+                                    kb = sm.alive[idx];
+                                    t = __int_as_float(sm.scan[kb]);
+                                    dd = sm.dir[kb];
+                                }
+                            }
+                            next_j += __popc(fm);
+                            if (!__any_sync(FULL, kb >= 0)) break;
+                        }
+                    }
+                } else {
+                    march_tail_slots<MARCH_SLOTS, TPB>(sm, dist, x0, y0, W, H, t_stop, n_alive, tid);
+                }
+            }
+            if (WPE > 1) __syncthreads(); else __syncwarp();
+            // ranges (env.py:426), all lanes active: sqrt(di^2 + dj^2) * resolution
+            const bool rec = pass == (IS_RESET_KERNEL ? PASS_RESET : PASS_STEP) && a.hits;
+            const float max_range = sm.max_range, res32 = sm.res32;
+#pragma unroll
+            for (int i = 0; i < BPL; i++) {
+                const int k = BEAM(i);
+                const int cell = sm.scan[k];
+                float rc = max_range;
+                int rel = (int)0x80008000;
+                if (cell != -1) {
+                    const int hx = (cell & 0xffff) - ci, hy = (cell >> 16) - cj;
+                    const float xd = (float)hx, yd = (float)hy;
+                    rc = __fsqrt_rn(__fadd_rn(__fmul_rn(xd, xd), __fmul_rn(yd, yd)));
+                    rel = (hx & 0xffff) | (hy << 16);
+                }
+                sm.scan[k] = __float_as_int(__fmul_rn(rc, res32));
+                if (rec) reinterpret_cast<int *>(a.hits)[(size_t)e * NB + k] = rel;
+            }
+        }
+        PROF_MARK(3);
+        // ---- pedestrians: segments (env.py:430-431) and discs (env.py:432), min-merged.
+        // One warp per obstacle, lanes across the beams of its angular window.
+        if (ns + nd > 0) {
+            if (WPE > 1) __syncthreads(); else __syncwarp();
+            // (the first scan after an auto-reset sees the next episode's pedestrians, if given)
+            const bool nxt = !IS_RESET_KERNEL && pass == PASS_RESET && a.discs_reset != nullptr;
+            const float *discs = (nxt ? a.discs_reset : a.discs) + (size_t)e * a.max_disc * 3;
+            const float *segs = (nxt ? a.segs_reset : a.segs) + (size_t)e * a.max_seg * 4;
+            for (int o = warp; o < ns + nd; o += WPE) {
+                int k0, cnt;
+                if (o < ns) {
+                    const float4 sg = *reinterpret_cast<const float4 *>(segs + 4 * o);
+                    const float ax = sg.x, ay = sg.y, bx = sg.z, by = sg.w;
+                    float pa = atan2f(ay - ly, ax - lx), pb = atan2f(by - ly, bx - lx);
+                    float dl = pb - pa;
+                    dl -= 6.2831853f * rintf(dl * 0.15915494f);
+                    float da2 = (ax - lx) * (ax - lx) + (ay - ly) * (ay - ly);
+                    float db2 = (bx - lx) * (bx - lx) + (by - ly) * (by - ly);
+                    if (fabsf(dl) > 3.0f || da2 < 1e-6f || db2 < 1e-6f) { k0 = 0; cnt = NB; }
+                    else beam_window(dl >= 0 ? pa : pb, fabsf(dl), lt, k0, cnt);
+                    for (int i = lane; i < cnt; i += 32) {
+                        const int k = (k0 + i) & (NB - 1);
+                        const float tt = seg_hit(lx, ly, sm.dir[k].x, sm.dir[k].y, ax, ay, bx, by);
+                        if (tt < CUDART_INF_F) atomicMin(&sm.scan[k], __float_as_int(tt));
+                    }
+                } else {
+                    const int q = o - ns;
+                    const float X = discs[3 * q], Y = discs[3 * q + 1], Rd = discs[3 * q + 2];
+                    const float cx = X - lx, cy = Y - ly;
+                    const float dc = sqrtf(cx * cx + cy * cy);
+                    if (dc <= Rd * 1.05f + 1e-3f) { k0 = 0; cnt = NB; }
+                    else {
+                        const float half = asinf(fminf(Rd / dc, 1.0f)) * 1.01f + 1e-4f;
+                        beam_window(atan2f(cy, cx) - half, 2.0f * half, lt, k0, cnt);
+                    }
+                    for (int i = lane; i < cnt; i += 32) {
+                        const int k = (k0 + i) & (NB - 1);
+                        const float tt = disc_hit(lx, ly, sm.dir[k].x, sm.dir[k].y, X, Y, Rd);
+                        if (tt < CUDART_INF_F) atomicMin(&sm.scan[k], __float_as_int(tt));
+                    }
+                }
+            }
+            if (WPE > 1) __syncthreads(); else __syncwarp();
+        }
+        PROF_MARK(4);
+        // ---- clip + noise (env.py:435-440), thresholds, observation row
+        bool c_any = false, d_any = false;
+        {
+            const int nslot = pass == PASS_RESCAN ? 1 : 0;
+            const float noise_std = sm.noise_std;
+            const int steps = sm.steps, episode = sm.episode;
+            const int SS = a.num_scan_stack > 1 ? a.num_scan_stack : 1;
+            constexpr int G = BPL >= 4 ? 4 : BPL;
+#pragma unroll 1
+            for (int g = 0; g < BPL / G; g++) {
+                float z[4] = {0.f, 0.f, 0.f, 0.f};
+                if (!a.noise && noise_std > 0.0f)
+                    normal4(a.seed, (uint32_t)(a.env_offset + e), (uint32_t)episode, (uint32_t)steps,
+                            (uint32_t)pass, (uint32_t)(tid + TPB * g), z);
+#pragma unroll
+                for (int j = 0; j < G; j++) {
+                    const int k = BEAM(G * g + j);
+                    float v = fminf(fmaxf(__int_as_float(sm.scan[k]), 0.0f), a.range_max);
+                    if (v != a.range_max) {
+                        if (a.noise) v = __fadd_rn(v, a.noise[((size_t)e * 2 + nslot) * NB + k]);
+                        else if (noise_std > 0.0f) v = __fadd_rn(v, noise_std * z[j]);
+                    }
+                    sm.scan[k] = __float_as_int(v);
+                    if (SS == 1) {
+                        orow[k] = v;
+                    } else {
+                        // _stack_scan (env.py:257-279): [pads = current scan | previous scans,
+                        // oldest first | current scan]; the previous observation row still holds
+                        // them one slot to the right
+                        const int hist = pass == PASS_RESET ? 0 : min(steps, SS - 1);
+                        for (int j = 0; j < SS - 1; j++) {
+                            if (j < SS - 1 - hist) orow[j * NB + k] = v;
+                            else if (pass == PASS_STEP) orow[j * NB + k] = orow[(j + 1) * NB + k];
+                        }
+                        orow[(SS - 1) * NB + k] = v;
+                    }
+                    const float thr_k = a.thr[k];
+                    c_any |= v < thr_k;
+                    d_any |= v < a.dthr[k];
+                    margin = fminf(margin, v - thr_k);
+                }
+            }
+        }
+
+        PROF_MARK(5);
+        if (pass == PASS_STEP) {
+            // ---- reward / done / info on this observation (env.py:464-589)
+            int crash, discomf;
+            if (WPE > 1) {
+                crash = __syncthreads_or(c_any);
+                discomf = __syncthreads_or(d_any) && !crash;
+            } else {
+                crash = __any_sync(FULL, c_any);
+                discomf = __any_sync(FULL, d_any) && !crash;
+            }
+            double mn = CUDART_INF;
+            if (discomf) {
+                for (int i = 0; i < BPL; i++) {
+                    const int k = BEAM(i);
+                    const float thr_k = a.thr[k], dthr_k = a.dthr[k];
+                    const float den = __fadd_rn(__fsub_rn(dthr_k, thr_k), 1e-6f);
+                    mn = fmin(mn, __ddiv_rn(__dsub_rn((double)__int_as_float(sm.scan[k]), (double)thr_k), (double)den));
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(FULL, mn, o));
+                if (WPE > 1) {
+                    if (lane == 0) sm.red[warp] = mn;
+                    __syncthreads();
+                }
+            }
+            if (warp == 0) {
+                if (WPE > 1 && discomf)
+                    for (int i = 0; i < WPE; i++) mn = fmin(mn, sm.red[i]);
+                // lanes 0 / 1: distance to goal from pose / prev_pose
+                const double gx = sm.gx, gy = sm.gy;
+                const double qx = lane == 0 ? sm.px : sm.ppx, qy = lane == 0 ? sm.py : sm.ppy;
+                const double ddx = __dsub_rn(gx, qx), ddy = __dsub_rn(gy, qy);
+                const double dq = sqrt(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)));
+                const double dist_g = __shfl_sync(FULL, dq, 0), pdist = __shfl_sync(FULL, dq, 1);
+                __syncwarp();  // lane 1 has read sm.ppx / sm.ppy before lane 0 may rewrite the pose below
+                const int success = dist_g < a.dist_thresh;
+                const int trunc = a.max_episode_steps > 0 && sm.steps >= a.max_episode_steps && !(success || crash);
+                const int done = success || crash || trunc;
+                if (lane == 0) {
+                    const double pv = sm.pv, pw = sm.pw;
+                    double r_s = success ? __dmul_rn(__dmul_rn(1.0, a.r_success), a.r_scale) : 0.0;
+                    double r_c = crash ? __dmul_rn(__dmul_rn(-1.0, a.r_crash), a.r_scale) : 0.0;
+                    double r_p = __dmul_rn(__dmul_rn(__dsub_rn(pdist, dist_g), a.r_progress), a.r_scale);
+                    double r_f = __dmul_rn(__dmul_rn(pv, a.r_forward), a.r_scale);
+                    double r_r = __dmul_rn(__dmul_rn(__dmul_rn(-1.0, __dmul_rn(pw, pw)), a.r_rotation), a.r_scale);
+                    double r_d = 0.0;
+                    if (discomf) r_d = __dmul_rn(__dmul_rn(-__dsub_rn(1.0, mn), a.r_discomfort), a.r_scale);
+                    double rew = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(r_s, r_c), r_p), r_f), r_r), r_d);
+                    a.reward[e] = (float)rew;
+                    a.done[e] = (uint8_t)done;
+                    if (a.reward_mirror) a.reward_mirror[e] = (float)rew;
+                    if (a.done_mirror) a.done_mirror[e] = (uint8_t)done;
+                    a.is_success[e] = (uint8_t)success;
+                    a.is_crash[e] = (uint8_t)crash;
+                    if (a.truncated) a.truncated[e] = (uint8_t)trunc;
+                    a.distance[e] = (float)dist_g;
+                    int next = PASS_END;
+                    if (done && a.auto_reset) {
+                        // auto-reset: draw a spawn tuple (and a map) for the next episode
+                        uint4 rnd = philox4x32_10(make_uint4((uint32_t)(a.env_offset + e), (uint32_t)sm.episode, 0x5eedu, 0xfffffff0u),
+                                                  make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+                        int nmap = sm.map;
+                        if (a.resample_map && a.num_maps > 1) nmap = (int)(((uint64_t)rnd.y * (uint64_t)a.num_maps) >> 32);
+                        const navgym_map_t m2 = a.maps[nmap];
+                        if (m2.spawn_count > 0) {
+                            const long long row = m2.spawn_offset + (long long)(((uint64_t)rnd.x * (uint64_t)m2.spawn_count) >> 32);
+                            const double *sp = a.spawn_pool + row * 5;
+                            sm.px = sp[0]; sm.py = sp[1]; sm.gx = sp[2]; sm.gy = sp[3]; sm.th = sp[4];
+                            sm.map = nmap;
+                        } else {  // no pool: restart from the rolled-back pose
+                            sm.px = sm.ppx; sm.py = sm.ppy; sm.th = sm.pyaw;
+                        }
+                        sm.noise_std = a.noise_lo + (a.noise_hi - a.noise_lo) * u01(rnd.z);
+                        sm.episode += 1;
+                        sm.steps = 0;
+                        sm.ppx = sm.px; sm.ppy = sm.py; sm.pv = 0; sm.pw = 0; sm.act_v = 0; sm.act_w = 0;
+                        next = PASS_RESET;
+                    } else if (crash) {  // env.py:707-717: back to the pose / yaw of prev_obs
+                        sm.px = sm.ppx; sm.py = sm.ppy; sm.th = sm.pyaw;
+                        next = PASS_RESCAN;
+                    }
+                    sm.next_pass = next;
+                }
+            }
+            if (WPE > 1) __syncthreads(); else __syncwarp();
+            pass = sm.next_pass;
+            if (pass == PASS_RESET && a.discs_reset != nullptr) {
+                nd = min(a.ndisc_reset[e], a.max_disc);
+                ns = a.segs_reset ? min(a.nseg_reset[e], a.max_seg) : 0;
+            }
+            if (pass != PASS_END) continue;
+        }
+        break;
+    }
+
+    PROF_MARK(6);
+    // File this environment under its cost class for the next step: the cycles its last scan
+    // took (an auto-reset first scan is taken at the pose the next step starts from), doubled
+    // when the next step is likely to end the episode and run a second scan -- the robot is
+    // within one step of a crash threshold, of the goal, or of the step limit.  Such
+    // environments then start first instead of stretching the end of the launch.  The slot in
+    // the class list is claimed here and filled in at the very end, so the atomic's round trip
+    // overlaps the epilogue.
+    int sched_pos = 0, sched_b = 0;
+    if (sched_cnt) {
+        bool risky = margin < NAVGYM_RISK_MARGIN;
+        if (tid == 0) {
+            const double gx = sm.gx - sm.px, gy = sm.gy - sm.py;
+            risky |= gx * gx + gy * gy < (a.dist_thresh + NAVGYM_RISK_MARGIN) * (a.dist_thresh + NAVGYM_RISK_MARGIN);
+            risky |= a.max_episode_steps > 0 && sm.steps + 1 >= a.max_episode_steps;
+        }
+        risky = (WPE > 1 ? __syncthreads_or(risky) : __any_sync(FULL, risky)) && a.auto_reset;
+        if (tid == 0) {
+            const long long kc = ((clock64() - t_pass) << (risky ? 1 : 0)) >> 13;
+            sched_b = NAVGYM_SCHED_BUCKETS - 1 - (int)(kc > NAVGYM_SCHED_BUCKETS - 1 ? NAVGYM_SCHED_BUCKETS - 1 : kc);
+            sched_pos = atomicAdd(&sched_cnt[sched_b], 1);
+        }
+    }
+    // ---------------- epilogue (warp 0): observation tail + state (env.py:455, 725-727) ---
+    if (warp == 0) {
+        double yaw;
+        if (WPE > 1 && sm.th_spec == sm.th) {
+            yaw = sm.yaw_spec;  // warp 1 had the final heading right
+        } else {
+            double sn, cn;
+            sincos(sm.th, &sn, &cn);
+            yaw = atan2(sn, cn);  // utils.py:5-9
+        }
+        double tv = 0.0;
+        switch (lane) {
+        case 0: tv = sm.ppx; break;
+        case 1: tv = sm.ppy; break;
+        case 2: tv = sm.px; break;
+        case 3: tv = sm.py; break;
+        case 4: tv = sm.pv; break;
+        case 5: tv = sm.pw; break;
+        case 6: tv = yaw; break;
+        }
+        if (lane < 7) {
+            orow[(a.num_scan_stack > 1 ? a.num_scan_stack : 1) * NB + lane] = (float)tv;
+            if (a.tail64) a.tail64[(size_t)e * 7 + lane] = tv;
+        }
+        double nv = 0.0;
+        switch (lane) {
+        case NAVGYM_S_PX: nv = sm.px; break;
+        case NAVGYM_S_PY: nv = sm.py; break;
+        case NAVGYM_S_TH: nv = sm.th; break;
+        case NAVGYM_S_GX: nv = sm.gx; break;
+        case NAVGYM_S_GY: nv = sm.gy; break;
+        case NAVGYM_S_PPX: nv = sm.px; break;
+        case NAVGYM_S_PPY: nv = sm.py; break;
+        case NAVGYM_S_PYAW: nv = yaw; break;
+        case NAVGYM_S_PV: nv = sm.act_v; break;
+        case NAVGYM_S_PW: nv = sm.act_w; break;
+        }
+        if (lane < NAVGYM_NS) ST(lane) = nv;
+        if (lane == 0) {
+            a.steps[e] = sm.steps;
+            a.map_id[e] = sm.map;
+            if (a.episodes) a.episodes[e] = sm.episode;
+            if (a.noise_std) a.noise_std[e] = sm.noise_std;
+        }
+    }
+    if (sched_cnt && tid == 0) sched_list[(size_t)sched_b * B + sched_pos] = e;
+    PROF_MARK(7);
+#ifdef NAVGYM_PROFILE
+    if (tid == 0 && a.tail64) {  // CTA timeline (global ns clock, SM id) for tail analysis
+        unsigned long long t_end;
+        unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        a.tail64[(size_t)e * 7 + 0] = (double)_g_begin;
+        a.tail64[(size_t)e * 7 + 1] = (double)t_end;
+        a.tail64[(size_t)e * 7 + 2] = (double)smid;
+        a.tail64[(size_t)e * 7 + 3] = (double)blockIdx.x;
+    }
+#endif
+#undef ST
+#undef BEAM
+}
