@@ -160,14 +160,14 @@ __device__ __forceinline__ void march_tail_slots(EnvSmem &sm, const float *__res
     }
 }
 
-// One CTA = one environment, WPE warps.  Lane l of warp w owns beams l + 32 (w + WPE i),
-// i = 0 .. 16/WPE - 1: at any moment the lanes of a warp work on neighbouring beams, whose
-// EDT gathers share sectors.  Each lane walks its beams through MARCH_SLOTS independent march
-// slots; a slot that finishes a beam immediately starts the lane's next one, so lanes stay
-// busy instead of idling until the slowest beam of a lockstep group ends, and MARCH_SLOTS
-// gathers per lane are in flight.  The three scans a step may need (the step's scan, the
-// crash re-scan env.py:718, the auto-reset first scan) run through ONE copy of the scan code
-// inside a CTA-uniform pass loop.
+// One CTA = one environment, WPE warps (default 2).  Thread t owns beams t + 32 WPE i, i = 0 ..
+// 16 / WPE - 1: the lanes of a warp work on neighbouring beams, whose EDT gathers share sectors.
+// A scan marches in two phases (see the march section below): a lockstep head phase, four
+// samples per beam with four beams per thread in flight, then a tail phase in which the beams
+// still alive are dealt to lanes as lanes fall free (MARCH_SLOTS = 1: ballot-rank dealing, one
+// beam per lane at a time; > 1: several per lane from a shared counter).  The three scans a step
+// may need (the step's scan, the crash re-scan env.py:718, the auto-reset first scan) run
+// through ONE copy of the scan code inside a CTA-uniform pass loop.
 #ifndef NAVGYM_HEAD_STEPS
 #define NAVGYM_HEAD_STEPS 4  // samples every beam marches in the lockstep head phase
 #endif
