@@ -61,12 +61,25 @@ rows = pool[rng.randint(len(pool), size=N)]
 bt = orc.beam_table()
 res = {}
 rem = np.zeros(512, np.int64); ls = np.zeros(512, np.float32)
+rem0 = np.zeros(512, np.int64); ls0 = np.zeros(512, np.float32)
+INC = 0.0122718437
 for r in rows:
     ox = np.float32(int(r[0] / 0.05)); oy = np.float32(int(r[1] / 0.05))
     heads = (bt + np.float32(r[4])).astype(np.float32)
     beam_profile(dist, m['width'], m['height'], ox, oy, heads, np.float32(502), 4, rem, ls)
     surv = np.where(rem > 0)[0]
+    # the previous step's scan: the robot came from 0.1 m behind, turned by up to 0.128 rad
+    v, w = rng.uniform(0, 0.5), rng.uniform(-0.64, 0.64)
+    th0 = r[4] - w * 0.2
+    ox0 = np.float32(int((r[0] - v * 0.2 * np.cos(r[4])) / 0.05)); oy0 = np.float32(int((r[1] - v * 0.2 * np.sin(r[4])) / 0.05))
+    beam_profile(dist, m['width'], m['height'], ox0, oy0, (bt + np.float32(th0)).astype(np.float32), np.float32(502), 4, rem0, ls0)
+    shift = int(np.rint((r[4] - th0) / INC))
+    pred = rem0[(np.arange(512) + shift) % 512]          # beam k now looked along old beam k + shift
     orders = {
+        'history: longest predicted first': surv[np.argsort(-pred[surv], kind='stable')],
+        'history: predicted >= 16 first': np.concatenate([surv[pred[surv] >= 16], surv[pred[surv] < 16]]),
+        'history: predicted >= 8 first': np.concatenate([surv[pred[surv] >= 8], surv[pred[surv] < 8]]),
+        'history, no shift: >= 16 first': np.concatenate([surv[rem0[surv] >= 16], surv[rem0[surv] < 16]]),
         'beam order (today)': surv,
         'longest first (ideal)': surv[np.argsort(-rem[surv], kind='stable')],
         'last step < 4 cells first': np.concatenate([surv[ls[surv] < 4], surv[ls[surv] >= 4]]),
