@@ -53,3 +53,24 @@ def test_no_cpu_fallback(lib):
 def test_sass_is_sm100a():
     out = os.popen('cuobjdump -lelf %s 2>/dev/null' % _lib.SO).read()
     assert 'sm_100a' in out
+
+
+def test_plain_c_client_links_and_runs(lib, tmp_path):
+    """include/navgym_b200.h is valid C99 and a C program linked against the shared library
+    sees the same ABI (struct sizes, no-op empty batch, host helper) -- the view a cgo / JNI /
+    FFI host has of the boundary."""
+    import shutil
+    import subprocess
+    from nav_gym_b200 import _lib
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('no gcc')
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = str(tmp_path / 'abi_client')
+    subprocess.check_call([gcc, '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror',
+                           '-I', os.path.dirname(_lib.HDR), os.path.join(here, 'abi_client.c'),
+                           '-o', exe, '-L', os.path.dirname(_lib.SO), '-lnavgym_b200',
+                           '-Wl,-rpath,' + os.path.dirname(_lib.SO)])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert 'abi ok' in out.stdout
