@@ -173,9 +173,62 @@ class CMap2D(object):
         _render(ranges, angles, None, np.ascontiguousarray(discs, np.float32), lidar_xy)
 
 
+# ---- pose2d / pyastar2d: host-side helpers of the reset path and the leg odometry ----------
+def inverse_pose2d(pose):
+    """pose2d.inverse_pose2d (call site env.py:252): the transform that undoes (x, y, theta)."""
+    x, y, th = (float(v) for v in pose)
+    c, s = np.cos(th), np.sin(th)
+    return np.array([-(c * x + s * y), s * x - c * y, -th])
+
+
+def apply_tf_to_vel(vel, tf):
+    """pose2d.apply_tf_to_vel (call site env.py:254): rotate (vx, vy) by the transform's angle,
+    the rotation rate is frame-independent."""
+    c, s = np.cos(tf[2]), np.sin(tf[2])
+    return np.array([c * vel[0] - s * vel[1], s * vel[0] + c * vel[1], vel[2]])
+
+
+def astar_path(weights, start, goal, allow_diagonal=False):
+    """pyastar2d.astar_path on the reference's planning grid (env.py:343-351: inf where blocked,
+    one uniform cost elsewhere, 4-connected): with uniform costs every 4-connected shortest path
+    is optimal, so one is read off the library's BFS distance field from the goal.  Returns int
+    [L, 2] cells from start to goal inclusive, or None when there is no path."""
+    if allow_diagonal:
+        raise NotImplementedError('the reference plans 4-connected (env.py:351)')
+    w = np.asarray(weights)
+    si, sj, gi, gj = int(start[0]), int(start[1]), int(goal[0]), int(goal[1])
+    blocked = ~np.isfinite(w)
+    if blocked[si, sj] or blocked[gi, gj]:
+        return None
+    from .maps import grid_bfs
+    d = grid_bfs(blocked, (gi, gj))
+    if d[si, sj] < 0:
+        return None
+    path = [(si, sj)]
+    i, j = si, sj
+    H, W = d.shape
+    while (i, j) != (gi, gj):
+        for di, dj in ((1, 0), (-1, 0), (0, 1), (0, -1)):
+            ni, nj = i + di, j + dj
+            if 0 <= ni < H and 0 <= nj < W and d[ni, nj] == d[i, j] - 1:
+                i, j = ni, nj
+                break
+        path.append((i, j))
+    return np.array(path, dtype=np.int64)
+
+
 def install_as_reference_natives():
     """Expose these classes as ``range_libc`` and ``CMap2D`` so the reference's env.py picks
-    them up unchanged."""
+    them up unchanged; ``pose2d`` and ``pyastar2d`` (the other two un-vendored imports of
+    env.py:13-17) are registered too when the real packages are not installed."""
+    import importlib.util
+    for name, attrs in (('pose2d', dict(inverse_pose2d=inverse_pose2d, apply_tf_to_vel=apply_tf_to_vel)),
+                        ('pyastar2d', dict(astar_path=astar_path))):
+        if name not in sys.modules and importlib.util.find_spec(name) is None:
+            m = types.ModuleType(name)
+            for k, v in attrs.items():
+                setattr(m, k, v)
+            sys.modules[name] = m
     m = types.ModuleType('range_libc')
     m.PyOMap, m.PyRayMarching = PyOMap, PyRayMarching
     sys.modules['range_libc'] = m

@@ -102,3 +102,33 @@ def test_render_draws_the_attribute_surface():
     assert tuple(img[int(6.0 / 0.05), int(5.0 / 0.05)]) == (1.0, 0.0, 0.0)  # robot arrow base
     out = render(view, 'rgb_array')
     assert out.shape == (800, 800, 3) and out.dtype == np.uint8
+
+
+def test_pose2d_and_astar_stand_ins():
+    """The host-side stand-ins for pose2d / pyastar2d (env.py:252-254, 350) against the ones the
+    golden harness ran the reference with."""
+    from nav_gym_b200 import natives
+    from oracle import ref_harness as rh
+    rng = np.random.RandomState(2)
+    for _ in range(20):
+        p = rng.uniform(-5, 5, 3)
+        v = rng.uniform(-1, 1, 3)
+        inv = natives.inverse_pose2d(p)
+        assert np.allclose(inv, rh.inverse_pose2d(p), atol=1e-12)
+        assert np.allclose(natives.apply_tf_to_vel(v, inv), rh.apply_tf_to_vel(v, inv), atol=1e-12)
+        # composing a pose with its inverse is the identity
+        c, s = np.cos(p[2]), np.sin(p[2])
+        assert np.allclose([c * inv[0] - s * inv[1] + p[0], s * inv[0] + c * inv[1] + p[1]], 0, atol=1e-12)
+    grid = np.full((30, 40), 255.0, np.float32)
+    grid[10, 5:38] = np.inf
+    grid[20, 0:30] = np.inf
+    for s_, g_ in (((2, 3), (28, 35)), ((15, 2), (25, 39)), ((0, 0), (29, 39))):
+        mine = natives.astar_path(grid, s_, g_, allow_diagonal=False)
+        ref = rh.astar_path(grid, s_, g_, allow_diagonal=False)
+        assert mine is not None and len(mine) == len(ref)              # both shortest
+        assert tuple(mine[0]) == s_ and tuple(mine[-1]) == g_
+        assert (np.abs(np.diff(mine, axis=0)).sum(1) == 1).all()         # 4-connected steps
+        assert np.isfinite(grid[mine[:, 0], mine[:, 1]]).all()
+    grid[:, 20] = np.inf
+    assert natives.astar_path(grid, (2, 3), (28, 35)) is None
+    assert natives.astar_path(grid, (10, 6), (2, 3)) is None            # start on a blocked cell
