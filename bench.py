@@ -295,18 +295,20 @@ def main():
     # the same bytes with no simulation at all: what this box's PCIe allows for the copy pattern
     streams = [torch.cuda.Stream(device=dev) for _ in bounds]
     torch.cuda.synchronize(dev)
+    barrier()  # all ranks copy at the same time, as in the e2e legs
     t_s = time.perf_counter()
     for i in range(Ke):
         for s_, (b0, b1) in zip(streams, bounds):
             with torch.cuda.stream(s_):
                 obs_h[b0:b1].copy_(env.obs[b0:b1], non_blocking=True)
     torch.cuda.synchronize(dev)
+    barrier()
     copy_only_ms = (time.perf_counter() - t_s) * 1e3
 
-    t = torch.tensor([total_ms, e2e_ms, e2e_sync_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, e2e_ms, e2e_sync_ms, copy_only_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, e2e_sync_ms = float(t[0]), float(t[1]), float(t[2])
+    total_ms, e2e_ms, e2e_sync_ms, copy_only_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -347,8 +349,8 @@ def main():
                         "groups in flight; a group's next actions are submitted only after its "
                         "previous results landed") % n_groups,
                 "sync_value": world * B * Ke / (e2e_sync_ms * 1e-3),
-                "copy_only_value": B * Ke / (copy_only_ms * 1e-3),
-                "copy_only_note": "rank 0's observation rows copied D2H in the same chunks with no stepping: the PCIe ceiling of the e2e figure, per GPU",
+                "copy_only_value": world * B * Ke / (copy_only_ms * 1e-3),
+                "copy_only_note": "every rank's observation rows copied D2H in the same chunks, all ranks at once, with no stepping: the PCIe / host-memory ceiling of the e2e figure on this box",
                 "sync_api": "BatchedNavGym.step_host (navgym_step_batch_host), one blocking call per step"},
         "gpu_launches": launches,
         "clocks": clocks,
