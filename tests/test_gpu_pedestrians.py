@@ -288,3 +288,51 @@ def test_auto_reset_first_scan_sees_the_next_episodes_pedestrians():
                 assert torch.equal(sim.pose[e], cand_pose[e])
             break
     assert checked >= 3
+
+
+def test_respawn_follows_the_map_drawn_at_auto_reset():
+    """Two different maps, resample_map: when an episode ends the robot may move to the other map,
+    and the pedestrians adopted for the new episode stand on free cost-map cells of THAT map, at
+    least 4 m from the robot's new start."""
+    from nav_gym_b200 import maps
+    from nav_gym_b200.batched_env import BatchedNavGym, MapPool, filter_spawn_pool
+    from nav_gym_b200.pedestrians import PedestrianSim
+    rng = np.random.RandomState(8)
+    ms = [maps.create_indoor_map(3, 100, rng), maps.create_outdoor_map(10, 0.7, rng)]
+    pools = [filter_spawn_pool(ms[0], maps.spawn_pool(ms[0], 1024, rng), 'cuda:0'),
+             filter_spawn_pool(ms[1], maps.spawn_pool(ms[1], 1024, rng, min_goal_dist=5, max_goal_dist=15), 'cuda:0')]
+    mp = MapPool(ms, 'cuda:0', spawn_pools=pools)
+    B, P = 256, 3
+    env = BatchedNavGym(B, mp, seed=3, auto_reset=True, resample_map=True,
+                        map_id=rng.randint(0, 2, B).astype(np.int32))
+    env.reset_from_spawn_pool(np.random.RandomState(1))
+    sim = PedestrianSim(env, P, seed=3)
+    cms = [maps.cost_map(m) for m in ms]
+    g = torch.Generator(device='cuda'); g.manual_seed(2)
+    moved = checked = 0
+    for t in range(50):
+        act = torch.rand(B, 2, device='cuda', generator=g) * torch.tensor([0.5, 1.28], device='cuda') + torch.tensor([0, -0.64], device='cuda')
+        map_before = env.map_id.clone()
+        sim.act()
+        env.step(act)
+        sim.observe()
+        torch.cuda.synchronize()
+        done = env.done.bool()
+        if not done.any():
+            continue
+        sim._plan(env.done)            # what the next act() does first: adopt the new pedestrians
+        torch.cuda.synchronize()
+        pose = sim.pose.cpu().numpy()
+        rob = env.state[:2].t().cpu().numpy()
+        mid = env.map_id.cpu().numpy()
+        moved += int((env.map_id != map_before)[done].sum())
+        for e in np.where(done.cpu().numpy())[0]:
+            cm = cms[mid[e]]
+            c = (pose[e, :, 0] / cm['resolution']).astype(int)
+            r = (pose[e, :, 1] / cm['resolution']).astype(int)
+            assert (c < cm['width']).all() and (r < cm['height']).all()
+            assert (cm['data'][r, c] == 0).all(), (t, e)
+            assert (np.hypot(*(pose[e, :, :2] - rob[e]).T) >= 4.0 - 1e-9).all()
+            checked += 1
+        env.done.zero_()               # consumed: the loop's next act() must not adopt again
+    assert checked > 20 and moved > 5
