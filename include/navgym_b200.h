@@ -153,8 +153,40 @@ int navgym_step_batch_host_submit(navgym_host_pipe_t *pipe, const navgym_step_ar
                                   const float *actions_host, float *obs_host, float *reward_host,
                                   uint8_t *done_host);
 int navgym_step_batch_host_wait(navgym_host_pipe_t *pipe, int group);
+int navgym_host_pipe_groups(const navgym_host_pipe_t *pipe);
+int navgym_host_pipe_group_bounds(const navgym_host_pipe_t *pipe, int group, int *begin, int *end);
+/* The whole host-side rollout loop in C (the reference's `while True: obs, r, d, info =
+ * env.step(policy(obs))` smoke loop, env.py:1318-1355, for a batch): every group is primed with
+ * the policy's step-0 actions, then `steps` times round each group is waited for, `policy` is
+ * called with the group's env range -- its rows of obs_host / reward_host / done_host hold the
+ * results of step `step - 1` -- to write the group's next actions into actions_host, and the
+ * group is submitted again.  No per-group work in the caller's language; the PCIe transfers of
+ * one group hide behind the raycast of the others.  Returns when all `steps` steps of every
+ * group have landed (also on error: nothing stays in flight). */
+typedef void (*navgym_policy_fn)(void *user, int group, int env_begin, int env_end, int64_t step,
+                                 const float *obs_host, const float *reward_host,
+                                 const uint8_t *done_host, float *actions_host);
+int navgym_host_rollout(navgym_host_pipe_t *pipe, const navgym_step_args_t *args, int64_t steps,
+                        navgym_policy_fn policy, void *user, float *actions_host, float *obs_host,
+                        float *reward_host, uint8_t *done_host);
+/* built-in policy: step s plays row (s mod rows) of a host action bank f32 [rows][num_envs][2] */
+typedef struct {
+    const float *actions;
+    int32_t rows, num_envs;
+} navgym_action_bank_t;
+void navgym_policy_action_bank(void *user, int group, int env_begin, int env_end, int64_t step,
+                               const float *obs_host, const float *reward_host,
+                               const uint8_t *done_host, float *actions_host);
 /* first observation of an episode, NavGymEnv.reset's tail (env.py:822-831) */
 int navgym_reset_obs_batch(const navgym_step_args_t *args, void *stream);
+
+/* ---- host export of one environment (ros_env.py:69-176 reads a NavGymEnv's attributes; the
+ * single-env drop-in returns numpy per step, env.py:728): everything it needs from environment
+ * `env`, packed into one float64 row out_dev[navgym_export_env_len(S)] so that ONE device-to-host
+ * copy fetches it: state[NAVGYM_NS] | tail64[7] | reward done is_success is_crash truncated
+ * distance steps map_id episode noise_std | the S*512 scan columns of its observation row. */
+int navgym_export_env_len(int num_scan_stack);
+int navgym_export_env(const navgym_step_args_t *args, int env, double *out_dev, void *stream);
 
 /* ---- HER batch API: compute_rewards / compute_terminals / compute_info (env.py:464-589) on
  * `count` stored observation rows obs[count][obs_stride] (float32, the layout of env.py:455)

@@ -139,6 +139,15 @@ class MoveArgs(C.Structure):
 PED_F = 16
 
 
+class ActionBank(C.Structure):
+    _fields_ = [('actions', _P), ('rows', C.c_int32), ('num_envs', C.c_int32)]
+
+
+# navgym_policy_fn (include/navgym_b200.h): user, group, env_begin, env_end, step, obs, reward,
+# done, actions
+POLICY_FN = C.CFUNCTYPE(None, _P, C.c_int, C.c_int, C.c_int, C.c_int64, _P, _P, _P, _P)
+
+
 class PedsArgs(C.Structure):
     _fields_ = [('num_envs', C.c_int32), ('max_ped', C.c_int32), ('max_disc', C.c_int32),
                 ('max_seg', C.c_int32), ('advance', C.c_int32), ('trunk_mode', C.c_int32),
@@ -158,6 +167,8 @@ EXPORTS = [
     'navgym_agent_scan_batch', 'navgym_sizeof_scan_args',
     'navgym_peds_plan', 'navgym_sizeof_plan_args', 'navgym_sizeof_plan_map',
     'navgym_peds_move', 'navgym_sizeof_move_args', 'navgym_policy_features',
+    'navgym_host_pipe_groups', 'navgym_host_pipe_group_bounds', 'navgym_host_rollout',
+    'navgym_policy_action_bank', 'navgym_export_env', 'navgym_export_env_len',
 ]
 
 _lib = None
@@ -182,6 +193,11 @@ def load():
     lib.navgym_step_batch_host.argtypes = [_P, C.POINTER(StepArgs), _P, _P, _P, _P, _P]
     lib.navgym_step_batch_host_submit.argtypes = [_P, C.POINTER(StepArgs), C.c_int, _P, _P, _P, _P]
     lib.navgym_step_batch_host_wait.argtypes = [_P, C.c_int]
+    lib.navgym_host_pipe_groups.argtypes = [_P]
+    lib.navgym_host_pipe_group_bounds.argtypes = [_P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.navgym_host_rollout.argtypes = [_P, C.POINTER(StepArgs), C.c_int64, _P, _P, _P, _P, _P, _P]
+    lib.navgym_export_env.argtypes = [C.POINTER(StepArgs), C.c_int, _P, _P]
+    lib.navgym_export_env_len.argtypes = [C.c_int]
     lib.navgym_edt_build.argtypes = [_P, C.c_int, C.c_int, _P, _P, _P]
     lib.navgym_calc_range_many.argtypes = [_P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_float,
                                            C.c_float, _P, _P]

@@ -24,19 +24,27 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+_THRESHOLDS = {}
+
+
 def scan_thresholds(device):
     """_make_scan_threshold / _make_scan_discomfort_threshold (env.py:162-180): the inflated
     footprints rendered into a 25 m scan from the origin at heading 0, on the GPU."""
     lib = _lib.require_device()
+    key = str(torch.device(device))
+    if key in _THRESHOLDS:  # constants of the robot model: rendered once per device
+        return [t.copy() for t in _THRESHOLDS[key]]
     head = beam_table().astype(np.float32)  # float32(lin + float32(0))
     out = []
     for fp in (KetiRobot.threshold_footprint, KetiRobot.discomfort_threshold_footprint):
         ranges = np.full(NB, KetiRobot.range_max, np.float32)
         segs = np.ascontiguousarray(closed_segments(fp))
-        _lib.check(lib.navgym_render_in_lidar_host(
-            ranges.ctypes.data_as(C.c_void_p), head.ctypes.data_as(C.c_void_p), NB,
-            segs.ctypes.data_as(C.c_void_p), len(segs), None, 0, 0.0, 0.0), 'render_in_lidar_host')
+        with torch.cuda.device(torch.device(device)):
+            _lib.check(lib.navgym_render_in_lidar_host(
+                ranges.ctypes.data_as(C.c_void_p), head.ctypes.data_as(C.c_void_p), NB,
+                segs.ctypes.data_as(C.c_void_p), len(segs), None, 0, 0.0, 0.0), 'render_in_lidar_host')
         out.append(np.clip(ranges, 0, KetiRobot.range_max))
+    _THRESHOLDS[key] = [t.copy() for t in out]
     return out
 
 
@@ -272,15 +280,7 @@ class BatchedNavGym(object):
             self._geom(self._pdiscs, self._pnd, self._psegs, self._pns, None)
         else:
             self._geom(None, None, None, None, None)
-        if self._pipe is None or self._pipe[1] != chunks:
-            if self._pipe is not None:
-                self.lib.navgym_host_pipe_destroy(self._pipe[0])
-            h = self.lib.navgym_host_pipe_create(chunks, self.B, int(self.sched is not None))
-            if not h:
-                raise RuntimeError('navgym_host_pipe_create failed')
-            self._pipe = (C.c_void_p(h), chunks)
-            self._act_dev = torch.empty(self.B, 2, dtype=torch.float32, device=self.device)
-        self.args.actions = _ptr(self._act_dev)
+        self._make_pipe(chunks)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.navgym_step_batch_host(
                 self._pipe[0], C.byref(self.args), self._stream(), _ptr(actions_host), _ptr(obs_host),
@@ -300,20 +300,29 @@ class BatchedNavGym(object):
         assert obs_host.dtype == torch.float32 and tuple(obs_host.shape) == (self.B, self.obs_dim)
         assert actions_host.dtype == torch.float32 and actions_host.numel() == 2 * self.B
         assert reward_host.dtype == torch.float32 and done_host.dtype == torch.uint8
-        if self._pipe is not None:
-            self.lib.navgym_host_pipe_destroy(self._pipe[0])
-        h = self.lib.navgym_host_pipe_create(groups, self.B, int(self.sched is not None))
-        if not h:
-            raise RuntimeError('navgym_host_pipe_create failed')
-        self._pipe = (C.c_void_p(h), groups)
-        self._act_dev = torch.empty(self.B, 2, dtype=torch.float32, device=self.device)
-        self.args.actions = _ptr(self._act_dev)
+        self._make_pipe(groups, fresh=True)
         self._geom(None, None, None, None, None)
         self._host_bufs = (actions_host, obs_host, reward_host, done_host)
         self._host_ptrs = tuple(_ptr(t) for t in self._host_bufs)
         self._args_ref = C.byref(self.args)
         torch.cuda.synchronize(self.device)
         return [(self.B * g // groups, self.B * (g + 1) // groups) for g in range(groups)]
+
+    def _make_pipe(self, groups, fresh=False):
+        """(Re)create the host pipe -- its streams, events and schedule buffers live on the env's
+        device (the C side switches to it on every call; here the device is made current so that
+        the creation itself lands there)."""
+        if self._pipe is None or self._pipe[1] != groups or fresh:
+            with torch.cuda.device(self.device):
+                if self._pipe is not None:
+                    self.lib.navgym_host_pipe_destroy(self._pipe[0])
+                    self._pipe = None
+                h = self.lib.navgym_host_pipe_create(groups, self.B, int(self.sched is not None))
+            if not h:
+                raise RuntimeError('navgym_host_pipe_create failed')
+            self._pipe = (C.c_void_p(h), groups)
+            self._act_dev = torch.empty(self.B, 2, dtype=torch.float32, device=self.device)
+        self.args.actions = _ptr(self._act_dev)
 
     def submit_host(self, group):
         """Enqueue one step of env group `group` (its rows of the bound host tensors are read /
@@ -329,6 +338,27 @@ class BatchedNavGym(object):
         if err:
             _lib.check(err, 'step_host_wait')
 
+    def rollout_host(self, steps, policy, user=None):
+        """`steps` lockstep steps of every env group bound by host_groups(), the group rotation
+        done in C (navgym_host_rollout): per group and step the results land in the bound host
+        tensors, `policy` writes the group's next actions into the bound actions tensor, and the
+        group is resubmitted while the others are stepping / copying.
+
+        policy: a C function pointer of type _lib.POLICY_FN (e.g. the library's
+        navgym_policy_action_bank with `user` = a _lib.ActionBank), or a Python callable
+        policy(group, env_begin, env_end, step) that reads / writes the bound tensors' rows
+        [env_begin:env_end] (called with the GIL held: convenient, not fast)."""
+        if callable(policy) and not isinstance(policy, (C._CFuncPtr,)):
+            fn = policy
+            policy = _lib.POLICY_FN(lambda u, g, b0, b1, s, o, r, d, a: fn(g, b0, b1, s))
+        self._policy_keep = (policy, user)
+        p = self._host_ptrs
+        uptr = None if user is None else C.cast(C.pointer(user), C.c_void_p)
+        err = self.lib.navgym_host_rollout(self._pipe[0], self._args_ref, int(steps),
+                                           C.cast(policy, C.c_void_p), uptr, p[0], p[1], p[2], p[3])
+        if err:
+            _lib.check(err, 'host_rollout')
+
     def __del__(self):
         p, self._pipe = getattr(self, '_pipe', None), None
         if p is not None:
@@ -338,44 +368,71 @@ class BatchedNavGym(object):
     def export_env(self, i):
         """Copy environment `i` back to the attribute surface ros_env.py and render read from a
         NavGymEnv (ros_env.py:69-176): map_info, robot.{px,py,theta,gx,gy,...}, humans[...],
-        prev_obs (the dict form of its last observation row), num_scan_stack, steps_since_reset.
-        Synchronises the device; a debugging aid, not part of the step path."""
+        prev_obs (the dict form of its last observation row), num_scan_stack, steps_since_reset,
+        plus the step's reward / done / info scalars.  One kernel packs the robot's side into a
+        float64 row (navgym_export_env) and ONE device-to-host copy fetches it (a second one for
+        the pedestrians, if any); synchronises the device -- a debugging / single-env aid, not
+        part of the batched step path."""
         from types import SimpleNamespace
         from .robot import Human
-        torch.cuda.synchronize(self.device)
-        st = self.state[:, i].cpu().numpy()
-        m = self.pool.maps[int(self.map_id[i].item())]
+        n_out = self.lib.navgym_export_env_len(self.num_scan_stack)
+        if getattr(self, '_export_dev', None) is None:
+            self._export_dev = torch.empty(n_out, dtype=torch.float64, device=self.device)
+            self._export_host = torch.empty(n_out, dtype=torch.float64).pin_memory()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.navgym_export_env(C.byref(self.args), int(i), _ptr(self._export_dev),
+                                                  self._stream()), 'export_env')
+            self._export_host.copy_(self._export_dev, non_blocking=True)
+            ped_host = None
+            crowd = getattr(self, 'crowd', None)
+            if crowd is not None:  # policy-driven pedestrians: float64 state of the PedestrianSim
+                P = crowd.P
+                packed = torch.cat([crowd.pose[i].reshape(-1), crowd.vel[i].reshape(-1),
+                                    crowd.waypoint[i].reshape(-1), crowd.has_legs[i].double(),
+                                    crowd.prev_action[i].reshape(-1).double(), crowd.v_pref[i],
+                                    (crowd.nped[i:i + 1] if crowd.nped is not None else
+                                     torch.full((1,), P, device=self.device)).double()])
+                ped_host = packed.cpu()
+            elif self.peds is not None:
+                P = self.peds.shape[1]
+                nn_ = self.nped[i:i + 1] if getattr(self, 'nped', None) is not None else torch.full((1,), P, device=self.device)
+                ped_host = torch.cat([self.peds[i].reshape(-1).double(), nn_.double()]).cpu()
+            torch.cuda.current_stream(self.device).synchronize()
+        x = self._export_host.numpy().copy()
+        st, tail = x[:NS], x[NS:NS + 7].copy()
+        sc = x[NS + 7:NS + 17]
+        m = self.pool.maps[int(sc[7])]
         robot = KetiRobot(float(st[_lib.S_PX]), float(st[_lib.S_PY]), float(st[_lib.S_TH]),
                           float(st[_lib.S_GX]), float(st[_lib.S_GY]), self.args.dt)
         robot.v, robot.r = float(st[_lib.S_PV]), float(st[_lib.S_PW])
         robot.vx, robot.vy = robot.v * np.cos(robot.theta), robot.v * np.sin(robot.theta)
         humans = []
-        crowd = getattr(self, 'crowd', None)
-        if crowd is not None:  # policy-driven pedestrians: float64 state of the PedestrianSim
-            n = int(crowd.nped[i].item()) if crowd.nped is not None else crowd.P
-            pose, vel = crowd.pose[i, :n].cpu().numpy(), crowd.vel[i, :n].cpu().numpy()
-            wp, legs = crowd.waypoint[i, :n].cpu().numpy(), crowd.has_legs[i, :n].cpu().numpy()
-            act, vp = crowd.prev_action[i, :n].cpu().numpy(), crowd.v_pref[i, :n].cpu().numpy()
+        if ped_host is not None and crowd is not None:
+            q = ped_host.numpy()
+            n = int(q[-1])
+            pose, vel, wp = q[:3 * P].reshape(P, 3), q[3 * P:5 * P].reshape(P, 2), q[5 * P:7 * P].reshape(P, 2)
+            legs, act, vp = q[7 * P:8 * P], q[8 * P:10 * P].reshape(P, 2), q[10 * P:11 * P]
             for j in range(n):
                 h = Human(float(pose[j, 0]), float(pose[j, 1]), float(pose[j, 2]), float(wp[j, 0]), float(wp[j, 1]), self.args.dt)
                 h.vx, h.vy, h.has_legs, h.v_pref = float(vel[j, 0]), float(vel[j, 1]), bool(legs[j]), float(vp[j])
                 h.v, h.r = float(act[j, 0] * vp[j]), float(act[j, 1] * vp[j])
                 humans.append(h)
-        elif self.peds is not None:
-            n = int(self.nped[i].item()) if getattr(self, 'nped', None) is not None else self.peds.shape[1]
-            for row in self.peds[i, :n].cpu().numpy():
+        elif ped_host is not None:
+            q = ped_host.numpy()
+            n = int(q[-1])
+            for row in q[:-1].reshape(P, _lib.PED_F)[:n]:
                 tgt = row[6:8] if row[8] > 0.5 else row[4:6]
                 h = Human(float(row[0]), float(row[1]), float(row[2]), float(tgt[0]), float(tgt[1]), self.args.dt)
                 h.v, h.has_legs = float(row[3]), bool(row[12] > 0.5)
                 h.vx, h.vy = h.v * np.cos(h.theta), h.v * np.sin(h.theta)
                 humans.append(h)
-        nscan = self.num_scan_stack * NB
-        tail = self.tail64[i].cpu().numpy()
-        obs = {'observation': np.concatenate([self.obs[i, :nscan].double().cpu().numpy(), tail]),
+        obs = {'observation': np.concatenate([x[NS + 17:], tail]),
                'achieved_goal': tail[2:4].copy(), 'desired_goal': np.array([robot.gx, robot.gy])}
         return SimpleNamespace(map_info=m, robot=robot, humans=humans, prev_obs=obs,
-                               num_scan_stack=self.num_scan_stack,
-                               steps_since_reset=int(self.steps[i].item()))
+                               num_scan_stack=self.num_scan_stack, steps_since_reset=int(sc[6]),
+                               reward=float(np.float32(sc[0])), done=bool(sc[1]), is_success=bool(sc[2]),
+                               is_crash=bool(sc[3]), truncated=bool(sc[4]), distance=float(np.float32(sc[5])),
+                               episode=int(sc[8]), noise_std=float(np.float32(sc[9])))
 
     # ---- HER batch API (env.py:491-589) on device tensors ---------------------------------
     def compute_rewards(self, obs, goals, **reward):

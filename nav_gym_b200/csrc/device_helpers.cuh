@@ -113,16 +113,3 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
 }
 
 __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
-
-// standard normal for (env, episode, step, slot, beam): Philox4x32-10 + Box-Muller
-__device__ __forceinline__ float beam_normal(uint64_t seed, uint32_t env, uint32_t episode,
-                                             uint32_t step, uint32_t slot, uint32_t beam)
-{
-    uint4 r = philox4x32_10(make_uint4(env, episode, step, (slot << 16) | (beam >> 2)),
-                            make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-    uint32_t a = (beam & 2) ? r.z : r.x, b = (beam & 2) ? r.w : r.y;
-    float rad = sqrtf(-2.0f * __logf(u01(a)));
-    float s, c;
-    __sincosf(6.283185307179586f * u01(b), &s, &c);
-    return rad * ((beam & 1) ? s : c);
-}

@@ -71,3 +71,35 @@ __global__ void render_in_lidar_kernel(float *__restrict__ ranges, const float *
         r = fminf(r, disc_hit(ox, oy, dx, dy, discs[3 * i], discs[3 * i + 1], discs[3 * i + 2]));
     ranges[k] = r;
 }
+
+// ------------------------------------------------------------------ host export of one env
+// Everything the single-environment drop-in reads back per step, packed into
+// one float64 row so that the host needs ONE device-to-host copy:
+//   [0..NS) state rows | [NS..NS+7) tail64 | reward done is_success is_crash truncated distance
+//   steps map_id episode noise_std | S*512 scan values (float32 -> float64, exact)
+#define NAVGYM_EXPORT_HEAD (NAVGYM_NS + NAVGYM_OBS_TAIL + 10)
+__global__ void export_env_kernel(const navgym_step_args_t a, int e, double *out)
+{
+    const int B = a.num_envs;
+    const int SS = a.num_scan_stack > 1 ? a.num_scan_stack : 1;
+    for (int i = threadIdx.x; i < NAVGYM_EXPORT_HEAD + SS * NB; i += blockDim.x) {
+        double v = 0.0;
+        if (i < NAVGYM_NS) v = a.state[(size_t)i * B + e];
+        else if (i < NAVGYM_NS + NAVGYM_OBS_TAIL) v = a.tail64 ? a.tail64[(size_t)e * 7 + (i - NAVGYM_NS)] : 0.0;
+        else if (i < NAVGYM_EXPORT_HEAD) {
+            switch (i - NAVGYM_NS - NAVGYM_OBS_TAIL) {
+            case 0: v = (double)a.reward[e]; break;
+            case 1: v = (double)a.done[e]; break;
+            case 2: v = (double)a.is_success[e]; break;
+            case 3: v = (double)a.is_crash[e]; break;
+            case 4: v = a.truncated ? (double)a.truncated[e] : 0.0; break;
+            case 5: v = (double)a.distance[e]; break;
+            case 6: v = (double)a.steps[e]; break;
+            case 7: v = (double)a.map_id[e]; break;
+            case 8: v = a.episodes ? (double)a.episodes[e] : 0.0; break;
+            case 9: v = a.noise_std ? (double)a.noise_std[e] : 0.0; break;
+            }
+        } else v = (double)a.obs[(size_t)e * a.obs_stride + (i - NAVGYM_EXPORT_HEAD)];
+        out[i] = v;
+    }
+}

@@ -130,6 +130,19 @@ int navgym_reset_obs_batch(const navgym_step_args_t *args, void *stream)
     return (int)cudaGetLastError();
 }
 
+int navgym_export_env_len(int num_scan_stack)
+{
+    return NAVGYM_EXPORT_HEAD + (num_scan_stack > 1 ? num_scan_stack : 1) * NB;
+}
+
+int navgym_export_env(const navgym_step_args_t *args, int env, double *out_dev, void *stream)
+{
+    if (env < 0 || env >= args->num_envs || !out_dev) return (int)cudaErrorInvalidValue;
+    export_env_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*args, env, out_dev);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
+
 int navgym_compute_rewards(const navgym_her_args_t *args, void *stream)
 {
     if (args->count <= 0) return 0;
@@ -198,7 +211,8 @@ int navgym_agent_scan_batch(const navgym_scan_args_t *args, void *stream)
 {
     if (args->num_envs <= 0 || args->agents_per_env <= 0) return 0;
     if (args->num_beams <= 0 || !args->pose || !args->lin || !args->ranges) return (int)cudaErrorInvalidValue;
-    if (!args->segs && args->robot_state && args->agents_per_env + 1 > 128) return (int)cudaErrorInvalidValue;
+    // crowd mode: one thread per other agent builds its footprint into a fixed shared-memory list
+    if (!args->segs && args->robot_state && args->agents_per_env > NAVGYM_SCAN_AGENTS) return (int)cudaErrorInvalidValue;
     agent_scan_kernel<<<args->num_envs * args->agents_per_env, 128, 0, (cudaStream_t)stream>>>(*args);
     g_launches++;
     return (int)cudaGetLastError();

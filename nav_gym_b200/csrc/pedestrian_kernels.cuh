@@ -21,7 +21,8 @@ __device__ __forceinline__ void footprint_segments(double x, double y, double th
     for (int i = 0; i < 4; i++) out[i] = make_float4(wx[i], wy[i], wx[(i + 1) & 3], wy[(i + 1) & 3]);
 }
 
-#define NAVGYM_SCAN_SEGS 128  // nearby-footprint segments kept per agent in crowd mode
+#define NAVGYM_SCAN_AGENTS 127  // crowd mode: agents per environment (+ the robot = one thread each)
+#define NAVGYM_SCAN_SEGS (4 * NAVGYM_SCAN_AGENTS)  // every other agent + the robot, 4 segments each
 __global__ void __launch_bounds__(128) agent_scan_kernel(const navgym_scan_args_t a)
 {
     __shared__ float4 near_segs[NAVGYM_SCAN_SEGS];
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(128) agent_scan_kernel(const navgym_scan_args_
         if (threadIdx.x == 0) n_near = 0;
         __syncthreads();
         const int o = threadIdx.x;
-        if (o <= live && o != slot + 1 && 4 * (live + 1) <= NAVGYM_SCAN_SEGS) {
+        if (o <= live && o != slot + 1) {  // host: agents_per_env <= NAVGYM_SCAN_AGENTS
             double ox, oy, oth;
             const double *fp;
             if (o == 0) {
@@ -218,21 +219,47 @@ __global__ void peds_plan_kernel(const navgym_plan_args_t a)
         const uint4 r0 = philox4x32_10(make_uint4(ge, (uint32_t)slot, (uint32_t)a.step, 0x5b0au), key);
         const uint4 r1 = philox4x32_10(make_uint4(ge, (uint32_t)slot, (uint32_t)a.step, 0x5b0bu), key);
         const uint4 r2 = philox4x32_10(make_uint4(ge, (uint32_t)slot, (uint32_t)a.step, 0x5b0cu), key);
-        const uint32_t draws[6] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
-        double sx = rx, sy = ry;
-        for (int i = 0; i < 6 && mc.free_count > 0; i++) {
+        // spawn (env.py:786-797): a free, goal-connected cost-map cell at least min_robot_dist
+        // from the robot's start; of 8 draws the first that qualifies, else the farthest -- and
+        // if even that one is too close (or the map has no free cell) the slot sits the episode
+        // out, parked outside the map with zero preferred speed where no lidar sees it
+        const uint32_t draws[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        double sx = mc.ox - 1000.0, sy = mc.oy - 1000.0, best = -1.0;
+        for (int i = 0; i < 8 && mc.free_count > 0; i++) {
             const long long row = mc.free_offset + (long long)(((uint64_t)draws[i] * (uint64_t)mc.free_count) >> 32);
-            sx = a.free_xy[2 * row]; sy = a.free_xy[2 * row + 1];
-            if ((sx - rx) * (sx - rx) + (sy - ry) * (sy - ry) >= a.min_robot_dist * a.min_robot_dist) break;
+            const double qx = a.free_xy[2 * row], qy = a.free_xy[2 * row + 1];
+            const double dd = (qx - rx) * (qx - rx) + (qy - ry) * (qy - ry);
+            if (dd > best) { best = dd; sx = qx; sy = qy; }
+            if (dd >= a.min_robot_dist * a.min_robot_dist) break;
         }
+        const bool parked = best < a.min_robot_dist * a.min_robot_dist;
+        if (parked) { sx = mc.ox - 1000.0; sy = mc.oy - 1000.0; }
         const double cth = 6.283185307179586 * (double)u01(r2.x);
         const bool legs = (double)u01(r2.z) < a.has_legs_ratio;
+        // goal (env.py:370-381): a goal field that reaches the spawn cell, farther than
+        // min_goal_dist; up to 5 draws, else the farthest reachable one drawn
+        int cgoal = (int)(((uint64_t)r2.w * (uint64_t)mc.num_goals) >> 32);
+        if (!parked) {
+            const uint4 r3 = philox4x32_10(make_uint4(ge, (uint32_t)slot, (uint32_t)a.step, 0x5b0du), key);
+            const uint32_t gd[5] = {r2.w, r3.x, r3.y, r3.z, r3.w};
+            const int scx = plan_cell(sx, mc.ox, mc.res, mc.W), scy = plan_cell(sy, mc.oy, mc.res, mc.H);
+            const size_t csz = (size_t)mc.W * mc.H;
+            const double *cg = a.goals + 2 * mc.goal_offset;
+            double gbest = -1.0;
+            for (int i = 0; i < 5; i++) {
+                const int c = (int)(((uint64_t)gd[i] * (uint64_t)mc.num_goals) >> 32);
+                if (a.fields[mc.field_offset + c * csz + (size_t)scy * mc.W + scx] == 65535u) continue;
+                const double dd = (cg[2 * c] - sx) * (cg[2 * c] - sx) + (cg[2 * c + 1] - sy) * (cg[2 * c + 1] - sy);
+                if (dd > gbest) { gbest = dd; cgoal = c; }
+                if (dd > a.min_goal_dist * a.min_goal_dist) break;
+            }
+        }
         a.cand_pose[3 * (size_t)n] = sx;
         a.cand_pose[3 * (size_t)n + 1] = sy;
         a.cand_pose[3 * (size_t)n + 2] = cth;
-        a.cand_v_pref[n] = a.v_pref_lo + (a.v_pref_hi - a.v_pref_lo) * (double)u01(r2.y);
+        a.cand_v_pref[n] = parked ? 0.0 : a.v_pref_lo + (a.v_pref_hi - a.v_pref_lo) * (double)u01(r2.y);
         a.cand_legs[n] = legs;
-        a.cand_goal[n] = (int)(((uint64_t)r2.w * (uint64_t)mc.num_goals) >> 32);
+        a.cand_goal[n] = cgoal;
         float *q = a.cand_rows + (size_t)n * NAVGYM_PED_F;
         q[0] = (float)sx; q[1] = (float)sy; q[2] = (float)cth;
         q[9] = 0.0f; q[10] = 0.0f; q[11] = 0.0f;

@@ -44,13 +44,6 @@ __device__ __forceinline__ void beam_window(float phi0, float width, float theta
     if (cnt > NB) cnt = NB;
 }
 
-// float -> cell index with C truncation semantics for x > -1, without the conversion pipe:
-// 2^23 + x rounded toward zero leaves trunc(x) in the mantissa (x in [0, 2^23)).
-__device__ __forceinline__ int trunc_cell(float x)
-{
-    return __float_as_int(__fadd_rz(fmaxf(x, 0.0f), 8388608.0f)) & 0x007fffff;
-}
-
 __device__ __forceinline__ void normal4(uint64_t seed, uint32_t env, uint32_t episode, uint32_t step,
                                         uint32_t slot, uint32_t group, float (&z)[4])
 {
@@ -274,6 +267,9 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
         } else {
             steps = 0;
         }
+        // a host-side reset starts a new episode: a new noise / spawn stream (the in-kernel
+        // auto-reset advances the same counter)
+        const int episode1 = episode0 + (IS_RESET_KERNEL ? 1 : 0);
         if (lane == NAVGYM_S_GX) sm.gx = sv;
         if (lane == NAVGYM_S_GY) sm.gy = sv;
         if (!IS_RESET_KERNEL) {
@@ -288,7 +284,7 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
             sm.act_v = act_v; sm.act_w = act_w;
             sm.map = map0;
             sm.steps = steps;
-            sm.episode = episode0;
+            sm.episode = episode1;
             sm.noise_std = noise_std0;
             if (IS_RESET_KERNEL) { sm.ppx = px; sm.ppy = py; sm.pyaw = 0; sm.pv = 0; sm.pw = 0; }
             if (WPE == 1) sm.th_spec = CUDART_NAN;
@@ -332,9 +328,13 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
             const float t_stop = sm.t_stop;
             const float *dist = a.edt_pool + sm.edt_off;
             asm volatile("" : "+l"(dist));  // keep base + offset folded into one register pair
-            const float d0 = __ldg(dist + cj * W + ci);   // origin cell is clipped into the map
+            // xy_to_cell clips ci against H and cj against W (the reference's quirk, env.py:1245-1248):
+            // on a non-square map the origin can still lie outside [0, W) x [0, H), where
+            // calc_range's first sample returns "no hit" for every beam
+            const bool o_in = ((unsigned)ci < (unsigned)W) & ((unsigned)cj < (unsigned)H);
+            const float d0 = o_in ? __ldg(dist + cj * W + ci) : 1.0f;
             const float t1 = fmaxf(__fmul_rn(d0, 0.999f), 1.0f);  // == 0.0f + first step
-            const bool degenerate = (d0 <= 0.0f) | !(t1 < t_stop);
+            const bool degenerate = !o_in | (d0 <= 0.0f) | !(t1 < t_stop);
             constexpr int HB = BPL >= 4 ? 4 : BPL;   // beams in flight per thread in the head phase
 #pragma unroll 1
             for (int r = 0; r < BPL / HB; r++) {
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
                     dyh[j] = (float)sd;
                     sm.dir[k] = make_float2(dxh[j], dyh[j]);
                     th_[j] = t1;
-                    if (degenerate) { sm.scan[k] = d0 <= 0.0f ? (cj << 16 | ci) : -1; th_[j] = -1.0f; }
+                    if (degenerate) { sm.scan[k] = (o_in & (d0 <= 0.0f)) ? (cj << 16 | ci) : -1; th_[j] = -1.0f; }
                 }
 #pragma unroll 1
                 for (int st = 0; st < NAVGYM_HEAD_STEPS; st++) {
@@ -505,19 +505,30 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
             const int steps = sm.steps, episode = sm.episode;
             const int SS = a.num_scan_stack > 1 ? a.num_scan_stack : 1;
             constexpr int G = BPL >= 4 ? 4 : BPL;
+            // Production noise: one Philox4x32-10 call + two Box-Muller pairs per group of four
+            // CONSECUTIVE beams 4q .. 4q + 3, keyed (seed; global env, episode, step, scan slot,
+            // q) -- a function of the beam index alone, whatever the launch shape.  The unit
+            // normals are staged in sm.dir (the beam directions are not needed any more).
+            const bool philox = !a.noise && noise_std > 0.0f;   // CTA-uniform
+            float *zs = reinterpret_cast<float *>(sm.dir);
+            if (philox) {
+                for (int q = tid; q < NB / 4; q += TPB) {
+                    float z[4];
+                    normal4(a.seed, (uint32_t)(a.env_offset + e), (uint32_t)episode, (uint32_t)steps,
+                            (uint32_t)pass, (uint32_t)q, z);
+                    *reinterpret_cast<float4 *>(zs + 4 * q) = make_float4(z[0], z[1], z[2], z[3]);
+                }
+                if (WPE > 1) __syncthreads(); else __syncwarp();
+            }
 #pragma unroll 1
             for (int g = 0; g < BPL / G; g++) {
-                float z[4] = {0.f, 0.f, 0.f, 0.f};
-                if (!a.noise && noise_std > 0.0f)
-                    normal4(a.seed, (uint32_t)(a.env_offset + e), (uint32_t)episode, (uint32_t)steps,
-                            (uint32_t)pass, (uint32_t)(tid + TPB * g), z);
 #pragma unroll
                 for (int j = 0; j < G; j++) {
                     const int k = BEAM(G * g + j);
                     float v = fminf(fmaxf(__int_as_float(sm.scan[k]), 0.0f), a.range_max);
                     if (v != a.range_max) {
                         if (a.noise) v = __fadd_rn(v, a.noise[((size_t)e * 2 + nslot) * NB + k]);
-                        else if (noise_std > 0.0f) v = __fadd_rn(v, noise_std * z[j]);
+                        else if (philox) v = __fadd_rn(v, noise_std * zs[k]);
                     }
                     sm.scan[k] = __float_as_int(v);
                     if (SS == 1) {

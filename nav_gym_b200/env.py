@@ -181,21 +181,7 @@ class NavGymEnv(gym.Env, EzPickle):
         self.steps_since_reset = 0
         self.prev_action = np.array([0., 0.])
         self.prev_obs = None
-        for _ in range(20):
-            if np.random.random() < self.indoor_ratio:
-                self.map_info = maps.create_indoor_map(self.env_param['corridor_width'],
-                                                       self.env_param['iterations'])
-            else:
-                self.map_info = maps.create_outdoor_map(self.env_param['obstacle_number'],
-                                                        self.env_param['obstacle_width'])
-            mp = MapPool([self.map_info], self.device)
-            pool = maps.spawn_pool(self.map_info, 64, min_goal_dist=self.min_goal_dist,
-                                   max_goal_dist=self.max_goal_dist)
-            pool = filter_spawn_pool(self.map_info, pool, self.device, map_pool=mp)
-            if len(pool):
-                break
-        else:
-            raise RuntimeError('[sample_start_goal_path] something is wrong...')
+        self.map_info, mp, pool = self._sample_world(MapPool, filter_spawn_pool)
         sx, sy, gx, gy, th = pool[np.random.randint(len(pool))]
         self.robot = KetiRobot(sx, sy, th, gx, gy, self.time_step)
         n_h = int(self.env_param['num_humans'])
@@ -220,6 +206,36 @@ class NavGymEnv(gym.Env, EzPickle):
         self.prev_obs = obs
         return obs
 
+    def _sample_world(self, MapPool, filter_spawn_pool):
+        """A map with its EDT on the device and a pool of valid (start, goal, heading) tuples
+        (env.py:294-383, 748-783).  The reference draws a fresh map every episode, and so does
+        this by default; NAVGYM_WORLD_CACHE=k keeps the last k worlds (map + EDT + spawn pool +
+        the pedestrians' planning fields) and re-draws episodes among them once k exist, which
+        takes the map generation, EDT build and BFS passes off all later resets."""
+        import os
+        keep = int(os.environ.get('NAVGYM_WORLD_CACHE', '0'))
+        worlds = self.__dict__.setdefault('_worlds', [])
+        if keep > 0 and len(worlds) >= keep:
+            return worlds[np.random.randint(len(worlds))]
+        for _ in range(20):
+            if np.random.random() < self.indoor_ratio:
+                map_info = maps.create_indoor_map(self.env_param['corridor_width'],
+                                                  self.env_param['iterations'])
+            else:
+                map_info = maps.create_outdoor_map(self.env_param['obstacle_number'],
+                                                   self.env_param['obstacle_width'])
+            mp = MapPool([map_info], self.device)
+            pool = maps.spawn_pool(map_info, 64, min_goal_dist=self.min_goal_dist,
+                                   max_goal_dist=self.max_goal_dist)
+            pool = filter_spawn_pool(map_info, pool, self.device, map_pool=mp)
+            if len(pool):
+                break
+        else:
+            raise RuntimeError('[sample_start_goal_path] something is wrong...')
+        if keep > 0:
+            worlds.append((map_info, mp, pool))
+        return map_info, mp, pool
+
     _policy_cache = None
 
     def _human_policy(self):
@@ -238,7 +254,8 @@ class NavGymEnv(gym.Env, EzPickle):
         return NavGymEnv._policy_cache
 
     def _obs(self):
-        view = self._sim.export_env(0)
+        """One packed device-to-host copy per step (BatchedNavGym.export_env)."""
+        view = self._view = self._sim.export_env(0)
         self.robot.px, self.robot.py, self.robot.theta = view.robot.px, view.robot.py, view.robot.theta
         self.humans = view.humans
         return view.prev_obs
@@ -256,14 +273,13 @@ class NavGymEnv(gym.Env, EzPickle):
             self._crowd.step(torch.from_numpy(action[None].astype(np.float32)))
         else:
             sim.step(torch.from_numpy(action[None].astype(np.float32)))
-        torch.cuda.synchronize(sim.device)
         obs = self._obs()
+        view = self._view
         self.robot.v, self.robot.r = float(action[0]), float(action[1])
-        reward = np.float64(sim.reward[0].item())
-        done = np.bool_(sim.done[0].item())
-        info = {'is_success': np.float32(sim.is_success[0].item()),
-                'is_crash': np.float32(sim.is_crash[0].item()),
-                'distance': np.float64(sim.distance[0].item())}
+        reward = np.float64(view.reward)
+        done = np.bool_(view.done)
+        info = {'is_success': np.float32(view.is_success), 'is_crash': np.float32(view.is_crash),
+                'distance': np.float64(view.distance)}
         self.prev_action = action
         self.prev_obs = obs
         return obs, reward, done, info

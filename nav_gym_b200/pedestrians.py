@@ -173,6 +173,8 @@ class PedestrianSim(object):
         assert precision in ('fp32', 'tf32x3', 'tf32', 'bf16')
         self.env, self.device = env, env.device
         self.B, self.P = env.B, int(max_ped)
+        if self.P > 127:  # navgym_agent_scan_batch, crowd mode: one thread per other agent
+            raise ValueError('at most 127 pedestrians per environment')
         self.dt = float(env.args.dt)
         self.precision = precision
         self.lib = _lib.load()
@@ -183,28 +185,39 @@ class PedestrianSim(object):
             policy = HumanPolicy()
         self.policy = policy.to(dev).eval()
         self.fold_frames = bool(fold_frames)
-        # ---- planning fields + free-cell pools per map
-        rng = np.random.RandomState(int(seed) + 77)
-        pm = (_lib.PlanMapT * len(env.pool.maps))()
-        fl, gl, xl = [], [], []
-        foff = goff = xoff = 0
-        for i, m in enumerate(env.pool.maps):
-            fields, goals, cm = M.goal_fields(m, num_goals, rng)
-            r, c = np.where(cm['data'] == 0)
-            xy = np.column_stack([(c + 0.5) * cm['resolution'] + cm['origin'][0],
-                                  (r + 0.5) * cm['resolution'] + cm['origin'][1]]).astype(np.float64)
-            pm[i] = _lib.PlanMapT(cm['width'], cm['height'], num_goals, 0, foff, goff, xoff, len(xy),
-                                  float(cm['origin'][0]), float(cm['origin'][1]), float(cm['resolution']))
-            fl.append(fields.reshape(-1))
-            gl.append(goals)
-            xl.append(xy)
-            foff += fields.size
-            goff += num_goals
-            xoff += len(xy)
-        self.plan_maps = torch.from_numpy(np.frombuffer(bytes(pm), dtype=np.uint8).copy()).to(dev)
-        self.fields = torch.from_numpy(np.concatenate(fl).view(np.int16)).to(dev)
-        self.goals = torch.from_numpy(np.concatenate(gl)).to(dev)
-        self.free_xy = torch.from_numpy(np.concatenate(xl)).to(dev)
+        # ---- planning fields + free-cell pools per map (kept on the MapPool: a pool that is
+        # reused for another episode / another sim does not rebuild them)
+        cache = getattr(env.pool, '_plan_cache', None)
+        if cache is None:
+            cache = env.pool._plan_cache = {}
+        if int(num_goals) not in cache:
+            rng = np.random.RandomState(int(seed) + 77)
+            pm = (_lib.PlanMapT * len(env.pool.maps))()
+            fl, gl, xl = [], [], []
+            foff = goff = xoff = 0
+            for i, m in enumerate(env.pool.maps):
+                fields, goals, cm = M.goal_fields(m, num_goals, rng)
+                # spawn cells (env.py:786-797): free cost-map cells connected to the goals'
+                # component, so that a spawned pedestrian always has a route (a
+                # pedestrian in a disconnected pocket walked at its goal through walls)
+                r, c = np.where((cm['data'] == 0) & (fields[0] != 65535))
+                xy = np.column_stack([(c + 0.5) * cm['resolution'] + cm['origin'][0],
+                                      (r + 0.5) * cm['resolution'] + cm['origin'][1]]).astype(np.float64)
+                pm[i] = _lib.PlanMapT(cm['width'], cm['height'], num_goals, 0, foff, goff, xoff, len(xy),
+                                      float(cm['origin'][0]), float(cm['origin'][1]), float(cm['resolution']))
+                fl.append(fields.reshape(-1))
+                gl.append(goals)
+                xl.append(xy.reshape(-1, 2))
+                foff += fields.size
+                goff += num_goals
+                xoff += len(xy)
+            xy_all = np.concatenate(xl) if sum(len(x) for x in xl) else np.zeros((1, 2))
+            cache[int(num_goals)] = (
+                torch.from_numpy(np.frombuffer(bytes(pm), dtype=np.uint8).copy()).to(dev),
+                torch.from_numpy(np.concatenate(fl).view(np.int16)).to(dev),
+                torch.from_numpy(np.concatenate(gl)).to(dev),
+                torch.from_numpy(xy_all).to(dev))
+        self.plan_maps, self.fields, self.goals, self.free_xy = cache[int(num_goals)]
         self.num_goals = int(num_goals)
         # ---- state
         self.pose = torch.zeros(B, P, 3, dtype=f64, device=dev)
