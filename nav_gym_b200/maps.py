@@ -15,6 +15,11 @@ import numpy as np
 from . import _lib
 
 
+# fixture-minting scripts (oracle/make_bench_world.py) route the BFS through the CPU checker so
+# that they run without the CUDA library; None = the library's navgym_grid_bfs
+_BFS_OVERRIDE = None
+
+
 def _map_info(occ, resolution=0.05):
     data = np.zeros(occ.shape, np.int8)
     data[occ.astype(bool)] = 100
@@ -51,27 +56,35 @@ def create_large_outdoor_map(rng=None, size=2000, obstacle_number=250):
 
 
 def create_indoor_map(corridor_width=3, iterations=100, rng=None, cells=100, scale=10):
-    """Random corridor tree on a cells x cells grid, every new node joined to its L1-nearest
-    tree node by an L-shaped corridor of half-width `corridor_width`, then upsampled by
-    `scale` (map_generator.py:97-123: 100 x 100 -> 1000 x 1000 at 0.05 m)."""
+    """Random corridor tree on a cells x cells grid (map_generator.py:97-123): every new node is
+    joined to its L1-nearest tree node (first of equals, :26-35) by an L-shaped corridor of
+    half-width `corridor_width` whose elbow is one of the two corners of the nodes' bounding
+    box that is not a node, chosen by a coin flip (:57-85); the grid is then upsampled by
+    `scale` (100 x 100 -> 1000 x 1000 at 0.05 m) and flipped.  Draws from `rng` in the
+    reference's order (x, y, coin per iteration), so `rng=None` under np.random.seed(s), or
+    RandomState(s), reproduces the reference's map for that seed bit for bit
+    (tests/golden/bench_world.npz, tests/test_host_helpers.py)."""
     rng = np.random if rng is None else rng
     r = int(corridor_width)
     occ = np.ones((cells, cells), np.uint8)
     nodes = [(cells // 2, cells // 2)]
     occ[nodes[0]] = 0
     for _ in range(int(iterations)):
-        p = (rng.randint(r + 2, cells - r - 1), rng.randint(r + 2, cells - r - 1))
+        p = (int(rng.randint(r + 2, cells - r - 1)), int(rng.randint(r + 2, cells - r - 1)))
         arr = np.asarray(nodes)
         q = nodes[int(np.argmin(np.abs(arr[:, 0] - p[0]) + np.abs(arr[:, 1] - p[1])))]
         nodes.append(p)
         occ[p] = 0
+        heads = rng.random_sample() >= 0.5
         x1, x2 = sorted((p[0], q[0]))
         y1, y2 = sorted((p[1], q[1]))
-        # corner of the L: one of the two axis-aligned elbows, by coin flip
-        if rng.random_sample() >= 0.5:
-            xc, yc = p[0], q[1]
+        # the nodes sit on the anti-diagonal of their bounding box (x1, y2) / (x2, y1) or on its
+        # diagonal; the elbow is a corner of the other diagonal
+        anti = (p[0] > q[0] and p[1] < q[1]) or (p[0] < q[0] and p[1] > q[1])
+        if anti:
+            xc, yc = (x1, y1) if heads else (x2, y2)
         else:
-            xc, yc = q[0], p[1]
+            xc, yc = (x1, y2) if heads else (x2, y1)
         occ[xc - r:xc + r + 1, y1 - r:y2 + r + 1] = 0
         occ[x1 - r:x2 + r + 1, yc - r:yc + r + 1] = 0
     occ = np.kron(occ, np.ones((scale, scale), np.uint8))
@@ -98,6 +111,8 @@ def cost_map(map_info, new_resolution=0.25, inflate=4):
 def grid_bfs(blocked, start_rc):
     """4-connected geodesic distance (cells) from start over free cells; -1 = unreachable.
     Stands in for pyastar2d.astar_path on the uniform-cost grid of env.py:343-354."""
+    if _BFS_OVERRIDE is not None:
+        return _BFS_OVERRIDE(blocked, start_rc)
     lib = _lib.load()
     b = np.ascontiguousarray(blocked, np.uint8)
     out = np.empty(b.shape, np.int32)

@@ -34,12 +34,18 @@ TRACES = [
     ('outdoor_n15_random', 16, 0.0, [15, 15], 'random', 150),
     # num_scan_stack = 3 (env.py:257-279): [pads | previous scans | current scan]
     ('indoor_n3_stack3', 17, 1.0, [3, 3], 'random', 150, 3),
+    # min_turning_radius = 0.5 (env.py:595-600 clamps |v| >= |w| r and edits `action`, :725):
+    # signed linear velocities reach both branches of the clamp
+    ('indoor_n2_turnradius', 18, 1.0, [2, 2], 'random_signed', 150, 1, 0.5),
+    ('outdoor_n6_turnradius_seek', 19, 0.0, [6, 6], 'seek', 400, 1, 0.5),
 ]
 
 
 def _action(mode, env, rng):
     if mode == 'random':
         a = rng.uniform([0.0, -0.64], [0.5, 0.64])
+    elif mode == 'random_signed':  # the reference does not clip actions (env.py:611-613)
+        a = rng.uniform([-0.25, -0.64], [0.5, 0.64])
     else:  # head for the goal, with a little dither
         r = env.robot
         bearing = np.arctan2(r.gy - r.py, r.gx - r.px)
@@ -66,7 +72,7 @@ def _pack(recs, key, width):
     return out, cnt
 
 
-def run_trace(name, seed, indoor_ratio, nh, mode, max_steps, stack=1):
+def run_trace(name, seed, indoor_ratio, nh, mode, max_steps, stack=1, min_turning_radius=0.0):
     np.random.seed(seed)
     import torch
     torch.manual_seed(seed)
@@ -74,7 +80,8 @@ def run_trace(name, seed, indoor_ratio, nh, mode, max_steps, stack=1):
     epr = dict(num_humans=(nh, 'int'), corridor_width=([3, 4], 'int'), iterations=([80, 150], 'int'),
                obstacle_number=([10, 10], 'int'), obstacle_width=([0.3, 1.0], 'float'),
                scan_noise_std=([0., 0.05], 'float'))
-    env = rh.make_env(indoor_ratio=indoor_ratio, env_param_range=epr, num_scan_stack=stack)
+    env = rh.make_env(indoor_ratio=indoor_ratio, env_param_range=epr, num_scan_stack=stack,
+                      min_turning_radius=min_turning_radius)
     NS = NB * stack
     rh.REC.clear()
     obs0 = env.reset()
@@ -86,7 +93,7 @@ def run_trace(name, seed, indoor_ratio, nh, mode, max_steps, stack=1):
         noise_std=np.float64(env.env_param['scan_noise_std']),
         start=np.array([env.robot.px, env.robot.py, env.robot.theta], np.float64),
         goal=np.array([env.robot.gx, env.robot.gy], np.float64),
-        num_scan_stack=np.int32(stack),
+        num_scan_stack=np.int32(stack), min_turning_radius=np.float64(min_turning_radius),
         obs0=obs0['observation'].astype(np.float64), hits0=first['hits'].astype(np.int16),
         cell0=first['ins'][0, :2].astype(np.int32),
         discs0=first['discs'], segs0=first['segs'],

@@ -560,6 +560,34 @@ void nvo_reset_obs_batch(const nvo_params_t *P, int B, const nvo_map_t *maps, co
     }
 }
 
+/* ------------------------------------------------ reset path: grid BFS ----------------
+ * 4-connected geodesic distance in cells over blocked[H][W] (non-zero = blocked), -1 where
+ * unreachable: the uniform-cost form of pyastar2d.astar_path on the 0.25 m cost map
+ * (env.py:343-354), used when minting spawn pools (oracle/make_bench_world.py). */
+void nvo_grid_bfs(const uint8_t *blocked, int H, int W, int sr, int sc, int32_t *dist)
+{
+    size_t n = (size_t)H * W;
+    for (size_t i = 0; i < n; i++) dist[i] = -1;
+    if (sr < 0 || sc < 0 || sr >= H || sc >= W || blocked[(size_t)sr * W + sc]) return;
+    int32_t *queue = (int32_t *)malloc(n * sizeof(int32_t));
+    size_t head = 0, tail = 0;
+    queue[tail++] = sr * W + sc;
+    dist[(size_t)sr * W + sc] = 0;
+    while (head < tail) {
+        int32_t cur = queue[head++];
+        int r = cur / W, c = cur % W;
+        const int nr[4] = {r + 1, r - 1, r, r}, nc[4] = {c, c, c + 1, c - 1};
+        for (int k = 0; k < 4; k++) {
+            if (nr[k] < 0 || nc[k] < 0 || nr[k] >= H || nc[k] >= W) continue;
+            size_t ni = (size_t)nr[k] * W + nc[k];
+            if (blocked[ni] || dist[ni] >= 0) continue;
+            dist[ni] = dist[cur] + 1;
+            queue[tail++] = (int32_t)ni;
+        }
+    }
+    free(queue);
+}
+
 void nvo_set_num_threads(int n)
 {
 #ifdef _OPENMP

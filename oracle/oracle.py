@@ -98,6 +98,14 @@ def edt_sq(occ):
     return out
 
 
+def grid_bfs(blocked, start_rc):
+    """4-connected BFS distance (cells) over a blocked[H, W] grid, -1 = unreachable."""
+    b = np.ascontiguousarray(blocked, np.uint8)
+    out = np.empty(b.shape, np.int32)
+    lib().nvo_grid_bfs(_p(b), b.shape[0], b.shape[1], int(start_rc[0]), int(start_rc[1]), _p(out))
+    return out
+
+
 def calc_range_many(dist, ins, max_range, t_stop=None, want_hits=False, want_steps=False):
     """range_libc PyRayMarching.calc_range_many restated; ranges in cells."""
     H, W = dist.shape

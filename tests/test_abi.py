@@ -74,3 +74,72 @@ def test_plain_c_client_links_and_runs(lib, tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
     assert 'abi ok' in out.stdout
+
+
+# ---- field-by-field layout: the ctypes mirrors in _lib.py against the header as gcc lays it out
+_MIRRORS = {
+    'navgym_map_t': 'MapT', 'navgym_step_args_t': 'StepArgs', 'navgym_her_args_t': 'HerArgs',
+    'navgym_peds_args_t': 'PedsArgs', 'navgym_scan_args_t': 'ScanArgs', 'navgym_plan_map_t': 'PlanMapT',
+    'navgym_plan_args_t': 'PlanArgs', 'navgym_move_args_t': 'MoveArgs', 'navgym_action_bank_t': 'ActionBank',
+}
+
+
+def _header_structs():
+    """{typedef name: [field names in declaration order]} parsed from the header's text."""
+    src = open(os.path.join(ROOT, 'include', 'navgym_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    out = {}
+    for body, name in re.findall(r'typedef\s+struct\s*\{(.*?)\}\s*(navgym_[a-z0-9_]+)\s*;', src, flags=re.S):
+        fields = []
+        for decl in body.split(';'):
+            decl = decl.strip()
+            if not decl:
+                continue
+            # "const float *thr, *dthr" / "double robot_fp[8], agent_fp[8]" / "int32_t W, H"
+            first, *rest = decl.split(',')
+            names = [first.split()[-1]] + [r.strip() for r in rest]
+            fields += [re.sub(r'\[.*?\]', '', n).replace('*', '').strip() for n in names]
+        out[name] = fields
+    return out
+
+
+def test_every_field_offset_matches_the_header(tmp_path):
+    """A C program built from the header prints offsetof / sizeof of EVERY field of every
+    argument struct; the ctypes mirrors must agree name by name, in order.  (Two swapped
+    same-size fields pass a sizeof check and corrupt silently.)"""
+    import shutil
+    import subprocess
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('no gcc')
+    structs = _header_structs()
+    assert set(_MIRRORS) <= set(structs), sorted(set(_MIRRORS) - set(structs))
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "navgym_b200.h"', 'int main(void) {']
+    for s, fields in structs.items():
+        if s not in _MIRRORS:
+            continue
+        for f in fields:
+            lines.append('  printf("%s %s %%zu %%zu\\n", offsetof(%s, %s), sizeof(((%s *)0)->%s));' % (s, f, s, f, s, f))
+        lines.append('  printf("%s . %%zu 0\\n", sizeof(%s));' % (s, s))
+    lines += ['  return 0;', '}']
+    src = tmp_path / 'offsets.c'
+    src.write_text('\n'.join(lines))
+    exe = str(tmp_path / 'offsets')
+    subprocess.check_call([gcc, '-std=c99', '-I', os.path.dirname(_lib.HDR), str(src), '-o', exe])
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    seen = {}
+    for ln in out.split('\n'):
+        if ln:
+            s, f, off, size = ln.split()
+            seen.setdefault(s, []).append((f, int(off), int(size)))
+    n_checked = 0
+    for s, mirror in _MIRRORS.items():
+        cls = getattr(_lib, mirror)
+        c_fields = [x for x in seen[s] if x[0] != '.']
+        assert [f for f, _, _ in c_fields] == [f for f, _ in cls._fields_], s
+        for f, off, size in c_fields:
+            d = getattr(cls, f)
+            assert (d.offset, d.size) == (off, size), (s, f, (d.offset, d.size), (off, size))
+            n_checked += 1
+        assert C.sizeof(cls) == [x for x in seen[s] if x[0] == '.'][0][1], s
+    assert n_checked > 150

@@ -132,3 +132,46 @@ def test_pose2d_and_astar_stand_ins():
     grid[:, 20] = np.inf
     assert natives.astar_path(grid, (2, 3), (28, 35)) is None
     assert natives.astar_path(grid, (10, 6), (2, 3)) is None            # start on a blocked cell
+
+
+def test_map_generator_reproduces_the_reference_bit_for_bit():
+    """nav_gym_b200.maps restates map_generator.py:97-143; with the same seed it must draw the
+    same map.  The known answers are SHA-256 digests of maps minted by the reference's own
+    generator in the build container (oracle/make_bench_world.py)."""
+    import hashlib
+    z = np.load(gu.GOLDEN + '/bench_world.npz')
+    for name, want in zip(z['known_names'], z['known_sha']):
+        kind, p0, p1, seed = str(name).split('_')
+        seed = int(seed[4:])
+        if kind == 'indoor':
+            m = maps.create_indoor_map(int(p0), int(p1), np.random.RandomState(seed))
+        else:
+            m = maps.create_outdoor_map(int(p0), float(p1), np.random.RandomState(seed))
+        assert m['data'].dtype == np.int8
+        assert hashlib.sha256(np.ascontiguousarray(m['data']).tobytes()).hexdigest() == str(want), name
+
+
+def test_bench_world_fixture_obeys_the_episode_law():
+    """tests/golden/bench_world.npz: the reference's create_indoor_map(3, 100) under seed 0 and a
+    65 536-tuple spawn pool -- starts and goals on free cost-map cells, 10 m < distance < 20 m
+    (env.py:379), first scan free of discomfort (env.py:779-783, checked with the oracle on a
+    sample)."""
+    from nav_gym_b200 import worlds
+    from oracle import oracle as orc
+    m, pool = worlds.load_bench_world()
+    ref = maps.create_indoor_map(3, 100, np.random.RandomState(0))
+    assert np.array_equal(m['data'], ref['data']) and m['resolution'] == 0.05 and m['width'] == 1000
+    assert pool.shape == (65536, 5)
+    d = np.hypot(pool[:, 2] - pool[:, 0], pool[:, 3] - pool[:, 1])
+    assert d.min() > 10.0 and d.max() < 20.0
+    assert pool[:, 4].min() >= 0 and pool[:, 4].max() < 2 * np.pi
+    cm = maps.cost_map(m)
+    for cols in ((0, 1), (2, 3)):
+        c = np.floor(pool[:, cols[0]] / 0.25).astype(int)
+        r = np.floor(pool[:, cols[1]] / 0.25).astype(int)
+        assert (cm['data'][r, c] == 0).all()
+    rows = pool[::512]
+    o = orc.OracleBatch([m], np.zeros(len(rows), np.int32), rows[:, 0:2], rows[:, 2:4], rows[:, 4],
+                        params=dict(t_stop=502.0))
+    obs = o.reset_obs(want_hits=False)
+    assert not (obs[:, :512] < o.dthr[None, :]).any()

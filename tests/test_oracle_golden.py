@@ -14,6 +14,7 @@ def make_oracle(G, **params):
     md, ms = gu.geom_dims(G)
     p = dict(cell_rule=1)  # the fixtures were minted under NumPy 2 (float32 cell division)
     p['num_scan_stack'] = int(G['num_scan_stack']) if 'num_scan_stack' in G else 1
+    p['min_turn_radius'] = float(G['min_turning_radius']) if 'min_turning_radius' in G else 0.0
     p.update(params)
     return OracleStepper([gu.map_info(G)], np.zeros(1, np.int32), G['start'][None, :2], G['goal'][None],
                          G['start'][2:3], params=p, max_disc=md, max_seg=ms)
