@@ -56,31 +56,14 @@ static int env_int(const char *name, int dflt)
     return s ? atoi(s) : dflt;
 }
 
-template <bool RESET, int WPE, int SLOTS>
-static void launch_one(const navgym_step_args_t &a, cudaStream_t st)
+// Launch shape of the fused kernel: one 64-thread CTA per environment of the launch.
+template <bool RESET>
+static cudaError_t launch_step(const navgym_step_args_t &a, cudaStream_t st)
 {
     const int count = a.env_count > 0 ? a.env_count : a.num_envs - a.env_begin;
-    step_kernel<RESET, WPE, SLOTS><<<count, WPE * 32, 0, st>>>(a);
-}
-
-template <bool RESET>
-static void launch_step(const navgym_step_args_t &a, cudaStream_t st)
-{
-    static const int wpe = env_int("NAVGYM_WPE", 2), slots = env_int("NAVGYM_SLOTS", 1);
-    switch (wpe * 10 + slots) {
-    case 11: launch_one<RESET, 1, 1>(a, st); break;
-    case 12: launch_one<RESET, 1, 2>(a, st); break;
-    case 14: launch_one<RESET, 1, 4>(a, st); break;
-    case 22: launch_one<RESET, 2, 2>(a, st); break;
-    case 24: launch_one<RESET, 2, 4>(a, st); break;
-    case 41: launch_one<RESET, 4, 1>(a, st); break;
-    case 44: launch_one<RESET, 4, 4>(a, st); break;
-    case 81: launch_one<RESET, 8, 1>(a, st); break;
-    case 82: launch_one<RESET, 8, 2>(a, st); break;
-    case 42: launch_one<RESET, 4, 2>(a, st); break;
-    default: launch_one<RESET, 2, 1>(a, st); break;
-    }
+    step_kernel<RESET><<<count, NAVGYM_CTA_THREADS, 0, st>>>(a);
     g_launches++;
+    return cudaSuccess;
 }
 
 #define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return (int)_e; } while (0)
@@ -115,8 +98,8 @@ int navgym_step_batch(const navgym_step_args_t *args, void *stream)
     if (args->num_envs <= 0) return 0;
     if (args->obs_stride < (args->num_scan_stack > 1 ? args->num_scan_stack : 1) * NB + NAVGYM_OBS_TAIL || args->env_begin < 0 || args->env_begin + args->env_count > args->num_envs)
         return (int)cudaErrorInvalidValue;
-    launch_step<false>(*args, (cudaStream_t)stream);
-    return (int)cudaGetLastError();
+    const cudaError_t err = launch_step<false>(*args, (cudaStream_t)stream);
+    return (int)(err ? err : cudaGetLastError());
 }
 
 #include "host_pipe.inl"
@@ -126,8 +109,8 @@ int navgym_reset_obs_batch(const navgym_step_args_t *args, void *stream)
     if (args->num_envs <= 0) return 0;
     if (args->obs_stride < (args->num_scan_stack > 1 ? args->num_scan_stack : 1) * NB + NAVGYM_OBS_TAIL)
         return (int)cudaErrorInvalidValue;
-    launch_step<true>(*args, (cudaStream_t)stream);
-    return (int)cudaGetLastError();
+    const cudaError_t err = launch_step<true>(*args, (cudaStream_t)stream);
+    return (int)(err ? err : cudaGetLastError());
 }
 
 int navgym_export_env_len(int num_scan_stack)

@@ -28,9 +28,15 @@ struct EnvSmem {
     float lx, ly, lt, res32, max_range, t_stop;
     int ci, cj, W, H;
     long long edt_off;
+#ifdef NAVGYM_PROFILE
+    int prof_iters_a[8], prof_rounds_b[8], prof_alive, prof_cyc_b[8], prof_walk[8];   // per warp: tail iterations / cooperative rounds
+#endif
 };
 
 enum { PASS_STEP = 0, PASS_RESCAN = 1, PASS_RESET = 2, PASS_END = 3 };
+#ifndef NAVGYM_HEAD_STEPS
+#define NAVGYM_HEAD_STEPS 4  // samples every beam marches in the lockstep head phase
+#endif
 
 // Angular window of beams that can see an obstacle spanning bearings [phi0, phi0 + width].
 // Beam k looks along lin[k] + theta with lin[k] = ANGLE_MIN + k * step (env.py:388-390).
@@ -93,125 +99,273 @@ __device__ __forceinline__ void pass_setup(EnvSmem &sm, const navgym_map_t &m, c
     sm.next_beam = next_beam;
 }
 
-// Tail phase with S survivors per lane in flight, dealt from a shared counter (sm.next_beam
-// starts at S * TPB): a slot whose beam ends takes the next undealt survivor.
-template <int S, int TPB>
-__device__ __forceinline__ void march_tail_slots(EnvSmem &sm, const float *__restrict__ dist, float x0, float y0,
-                                                 int W, int H, float t_stop, int n_alive, int tid)
+template <int WPE>
+__device__ __forceinline__ void cta_sync()
 {
-    const unsigned FULL = 0xffffffffu;
-    int kb[S];  // the slot's current beam, -1 = none left
-    float t[S], dx[S], dy[S];
-#pragma unroll
-    for (int s = 0; s < S; s++) {
-        const int i = s * TPB + tid;
-        kb[s] = i < n_alive ? (int)sm.alive[i] : -1;
-        const int kk = kb[s] >= 0 ? kb[s] : 0;
-        t[s] = __int_as_float(sm.scan[kk]);
-        const float2 dd = sm.dir[kk];
-        dx[s] = dd.x;
-        dy[s] = dd.y;
-    }
-    if (n_alive <= 0) return;
-    for (;;) {
-        float d[S];
-        int cx[S], cy[S];
-        bool inb[S];
-#pragma unroll
-        for (int s = 0; s < S; s++) {
-            cx[s] = __float2int_rz(__fmaf_rn(dx[s], t[s], x0));
-            cy[s] = __float2int_rz(__fmaf_rn(dy[s], t[s], y0));
-            inb[s] = ((unsigned)cx[s] < (unsigned)W) & ((unsigned)cy[s] < (unsigned)H);
-            const unsigned idx = (inb[s] & (kb[s] >= 0)) ? (unsigned)(cy[s] * W + cx[s]) : 0u;
-            d[s] = __ldg(dist + idx);
-        }
-#pragma unroll
-        for (int s = 0; s < S; s++) {
-            const bool hit = inb[s] & (d[s] <= 0.0f);
-            float tn = __fadd_rn(t[s], fmaxf(__fmul_rn(d[s], 0.999f), 1.0f));
-            const bool fin = !inb[s] | hit | !(tn < t_stop);
-            if (fin & (kb[s] >= 0)) {
-                // absolute hit cell, (y << 16 | x), or -1 for "no hit"
-                sm.scan[kb[s]] = hit ? (cy[s] << 16 | cx[s]) : -1;
-                const int i = atomicAdd(&sm.next_beam, 1);
-                kb[s] = -1;
-                if (i < n_alive) {
-                    const int k = sm.alive[i];
-                    kb[s] = k;
-                    tn = __int_as_float(sm.scan[k]);
-                    const float2 dd = sm.dir[k];
-                    dx[s] = dd.x;
-                    dy[s] = dd.y;
-                }
-            }
-            t[s] = tn;
-        }
-        bool live = false;
-#pragma unroll
-        for (int s = 0; s < S; s++) live |= kb[s] >= 0;
-        if (!__any_sync(FULL, live)) break;
-    }
+    if (WPE > 1) __syncthreads(); else __syncwarp();
+}
+template <int WPE>
+__device__ __forceinline__ int cta_or(int pred)
+{
+    return WPE > 1 ? __syncthreads_or(pred) : __any_sync(0xffffffffu, pred);
 }
 
-// One CTA = one environment, WPE warps (default 2).  Thread t owns beams t + 32 WPE i, i = 0 ..
+// Tail phase.  Two regimes:
+//  A  dealing: warp w owns list entries w, w + WPE, w + 2 WPE, ...; they are dealt to its lanes
+//     with ballot ranks (no atomics, no cross-warp traffic): a lane whose beam ends takes the
+//     warp's next undealt entry; one beam per lane, one EDT gather per lane and round trip.
+//  B  cooperative: once the warp's entries are all dealt and at most NAVGYM_COOP_ENTER beams are
+//     still marching, the idle lanes stop idling: the L live beams are regrouped onto G = 32 / L
+//     (power of two) lanes each, and lane j of a group fetches the cell the beam would sample
+//     at t + j -- a guess at where the march goes next (along a wall the step is max(0.999 d, 1)
+//     ~ 1..2 cells).  The group then WALKS the true march in registers: the next sample's cell
+//     is computed with the canonical arithmetic and looked up among the fetched cells (shuffles;
+//     an EDT value depends on the cell alone, so a match is exactly the value the march would
+//     load); the walk goes on until a sample's cell was not fetched, and the next fetch starts
+//     there.  Sample 0 of a fetch is the beam's own next sample, so every round trip advances
+//     the beam at least as far as regime A would -- and the dependent-gather chain of a scan's
+//     longest beams (max 226 samples on the bench world, one L2 round trip each) shrinks 3-5x
+//     (oracle/analysis/coop_march.py).  The sequence of t values and hit cells is bit-identical.
+#ifndef NAVGYM_COOP_ENTER
+#define NAVGYM_COOP_ENTER 1
+#endif
+template <int WPE>
+__device__ __forceinline__ void march_tail_dealt(EnvSmem &sm, const float *__restrict__ dist, float x0, float y0,
+                                                 int W, int H, float t_stop, int n_alive, int warp, int lane)
+{
+    const unsigned FULL = 0xffffffffu;
+    int next_j = 32;                       // warp-uniform: entries dealt so far
+    int idx = warp + WPE * lane;
+    int kb = idx < n_alive ? (int)sm.alive[idx] : -1;
+    float t = __int_as_float(sm.scan[kb >= 0 ? kb : 0]);
+    float2 dd = sm.dir[kb >= 0 ? kb : 0];
+    unsigned live = __ballot_sync(FULL, kb >= 0);
+    if (!live) return;
+    // ---- regime A
+    while (NAVGYM_COOP_ENTER == 0 || warp + WPE * next_j < n_alive || __popc(live) > NAVGYM_COOP_ENTER) {
+        const int cx = __float2int_rz(__fmaf_rn(dd.x, t, x0));
+        const int cy = __float2int_rz(__fmaf_rn(dd.y, t, y0));
+        const bool inb = ((unsigned)cx < (unsigned)W) & ((unsigned)cy < (unsigned)H);
+        const unsigned ci_ = (inb & (kb >= 0)) ? (unsigned)(cy * W + cx) : 0u;
+        const float d = __ldg(dist + ci_);
+        const bool hit = inb & (d <= 0.0f);
+        t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+        const bool fin = (kb >= 0) & (!inb | hit | !(t < t_stop));
+        const unsigned fm = __ballot_sync(FULL, fin);
+        if (fin) {
+            // absolute hit cell, (y << 16 | x), or -1 for "no hit"
+            sm.scan[kb] = hit ? (cy << 16 | cx) : -1;
+            idx = warp + WPE * (next_j + __popc(fm & ((1u << lane) - 1u)));
+            kb = -1;
+            if (idx < n_alive) {
+                kb = sm.alive[idx];
+                t = __int_as_float(sm.scan[kb]);
+                dd = sm.dir[kb];
+            }
+        }
+        next_j += __popc(fm);
+        live = __ballot_sync(FULL, kb >= 0);
+#ifdef NAVGYM_PROFILE
+        if (lane == 0) sm.prof_iters_a[warp]++;
+#endif
+        if (!live) return;
+    }
+    // ---- regime B: `live` marks the lanes that hold a marching beam (kb, t, dd)
+#ifdef NAVGYM_PROFILE
+    const long long prof_b0 = clock64();
+#endif
+    while (live) {
+        const int L = __popc(live);        // <= NAVGYM_COOP_ENTER <= 16
+        const int lg = L > 8 ? 1 : L > 4 ? 2 : L > 2 ? 3 : L > 1 ? 4 : 5;   // G = 32 / L, a power of two
+        const int G = 1 << lg;             // lanes per beam
+        const int g = lane >> lg, j = lane & (G - 1), base = lane & ~(G - 1);
+        const bool act = g < L;
+        const int owner = act ? (int)__fns(live, 0, g + 1) : 0;
+        const int bk = __shfl_sync(FULL, kb, owner);
+        float bt = __shfl_sync(FULL, t, owner);
+        const float bdx = __shfl_sync(FULL, dd.x, owner), bdy = __shfl_sync(FULL, dd.y, owner);
+        bool fin = !act;                   // group-uniform
+        int res = -1;
+        const int regroup_at = L > 1 ? (32 >> (lg + 1)) : 0;   // unfinished beams that fit twice the lanes
+        for (;;) {
+            // fetch: lane j guesses the sample at t + j (j = 0: the beam's own next sample)
+            const float tj = __fadd_rn(bt, (float)j);
+            const int fx = __float2int_rz(__fmaf_rn(bdx, tj, x0));
+            const int fy = __float2int_rz(__fmaf_rn(bdy, tj, y0));
+            const bool finb = ((unsigned)fx < (unsigned)W) & ((unsigned)fy < (unsigned)H);
+            const int fcell = finb ? (fy << 16 | fx) : -2;
+            const float fd = __ldg(dist + ((finb & !fin) ? (unsigned)(fy * W + fx) : 0u));
+            // walk the true march through the fetched cells
+            const float t0 = bt;
+            bool walking = !fin;
+#pragma unroll 1
+            for (int it = 0; it < G; it++) {
+                const int wx = __float2int_rz(__fmaf_rn(bdx, bt, x0));
+                const int wy = __float2int_rz(__fmaf_rn(bdy, bt, y0));
+                const bool winb = ((unsigned)wx < (unsigned)W) & ((unsigned)wy < (unsigned)H);
+                const int wcell = wy << 16 | wx;
+                // the guess nearest to t (one candidate finds all but ~2 % of what three would)
+                const int l0 = base + min(__float2int_rn(__fsub_rn(bt, t0)), G - 1);
+                const int c0 = __shfl_sync(FULL, fcell, l0);
+                const float d = __shfl_sync(FULL, fd, l0);
+                const float tn = __fadd_rn(bt, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
+                if (walking) {
+                    if (!winb) { fin = true; res = -1; walking = false; }
+                    else if (c0 != wcell) walking = false;      // not fetched: the next fetch starts here
+                    else if (d <= 0.0f) { fin = true; res = wcell; walking = false; }
+                    else {
+                        bt = tn;
+                        if (!(tn < t_stop)) { fin = true; res = -1; walking = false; }
+                    }
+                }
+#ifdef NAVGYM_PROFILE
+                if (lane == 0) sm.prof_walk[warp]++;
+#endif
+                if (!__any_sync(FULL, walking)) break;
+            }
+#ifdef NAVGYM_PROFILE
+            if (lane == 0) sm.prof_rounds_b[warp]++;
+#endif
+            const unsigned un = __ballot_sync(FULL, !fin & (j == 0));
+            if (__popc(un) <= regroup_at) break;
+        }
+        if (act & fin & (j == 0)) sm.scan[bk] = res;
+        // the group's first lane now holds the beam
+        kb = (act & !fin & (j == 0)) ? bk : -1;
+        t = bt;
+        dd = make_float2(bdx, bdy);
+        live = __ballot_sync(FULL, kb >= 0);
+    }
+#ifdef NAVGYM_PROFILE
+    if (lane == 0) sm.prof_cyc_b[warp] += (int)(clock64() - prof_b0);
+#endif
+}
+
+// One scan's occupancy-grid march (env.py:425-426) for the beams of head rounds [r_begin, r_end)
+// (round r = this thread's beams BEAM(4 r .. 4 r + 3)): beam directions, lockstep head phase,
+// survivor list, tail phase.  Leaves every beam's hit cell, (y << 16 | x) or -1, in sm.scan and
+// its direction in sm.dir; ends on a CTA barrier.  Scan set-up is read from sm (pass_setup).
+template <int WPE>
+__device__ __forceinline__ void march_scan(EnvSmem &sm, const navgym_step_args_t &a, const int r_begin, const int r_end,
+                                           const int tid)
+{
+    constexpr int BPL = NB / (32 * WPE);
+    constexpr int TPB = WPE * 32;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = tid & 31, warp = tid >> 5;
+#define BEAM(i) (tid + TPB * (i))
+    const int W = sm.W, H = sm.H, ci = sm.ci, cj = sm.cj;
+    const float x0 = (float)ci, y0 = (float)cj;
+    const float t_stop = sm.t_stop;
+    const float *dist = a.edt_pool + sm.edt_off;
+    asm volatile("" : "+l"(dist));  // keep base + offset folded into one register pair
+    // xy_to_cell clips ci against H and cj against W (the reference's quirk, env.py:1245-1248):
+    // on a non-square map the origin can still lie outside [0, W) x [0, H), where
+    // calc_range's first sample returns "no hit" for every beam
+    const bool o_in = ((unsigned)ci < (unsigned)W) & ((unsigned)cj < (unsigned)H);
+    const float d0 = o_in ? __ldg(dist + cj * W + ci) : 1.0f;
+    const float t1 = fmaxf(__fmul_rn(d0, 0.999f), 1.0f);  // == 0.0f + first step
+    const bool degenerate = !o_in | (d0 <= 0.0f) | !(t1 < t_stop);
+    constexpr int HB = BPL >= 4 ? 4 : BPL;   // beams in flight per thread in the head phase
+#pragma unroll 1
+    for (int r = r_begin; r < r_end; r++) {
+        float th_[HB], dxh[HB], dyh[HB];
+        // beam directions (env.py:388-390, 420-424)
+#pragma unroll
+        for (int j = 0; j < HB; j++) {
+            const int k = BEAM(r * HB + j);
+            const float h = (float)__dadd_rn(a.lin[k], (double)sm.lt);
+            double sd, cd;
+            dir_sincos((double)h, sd, cd);
+            dxh[j] = (float)cd;
+            dyh[j] = (float)sd;
+            sm.dir[k] = make_float2(dxh[j], dyh[j]);
+            th_[j] = t1;
+            if (degenerate) { sm.scan[k] = (o_in & (d0 <= 0.0f)) ? (cj << 16 | ci) : -1; th_[j] = -1.0f; }
+        }
+#pragma unroll 1
+        for (int st = 0; st < NAVGYM_HEAD_STEPS; st++) {
+            float dv[HB];
+            int cx[HB], cy[HB];
+            bool inb[HB];
+#pragma unroll
+            for (int j = 0; j < HB; j++) {
+                cx[j] = __float2int_rz(__fmaf_rn(dxh[j], th_[j], x0));
+                cy[j] = __float2int_rz(__fmaf_rn(dyh[j], th_[j], y0));
+                inb[j] = ((unsigned)cx[j] < (unsigned)W) & ((unsigned)cy[j] < (unsigned)H);
+                const unsigned idx = (inb[j] & (th_[j] >= 0.0f)) ? (unsigned)(cy[j] * W + cx[j]) : 0u;
+                dv[j] = __ldg(dist + idx);
+            }
+#pragma unroll
+            for (int j = 0; j < HB; j++) {
+                const bool alive = th_[j] >= 0.0f;
+                const bool hit = inb[j] & (dv[j] <= 0.0f);
+                const float tn = __fadd_rn(th_[j], fmaxf(__fmul_rn(dv[j], 0.999f), 1.0f));
+                const bool fin = !inb[j] | hit | !(tn < t_stop);
+                if (alive & fin) sm.scan[BEAM(r * HB + j)] = hit ? (cy[j] << 16 | cx[j]) : -1;
+                th_[j] = (alive & !fin) ? tn : -1.0f;
+            }
+        }
+        // survivors: park t in the scan slot and append the beam to the compact list
+#pragma unroll
+        for (int j = 0; j < HB; j++) {
+            const int k = BEAM(r * HB + j);
+            const bool alive = th_[j] >= 0.0f;
+            if (alive) sm.scan[k] = __float_as_int(th_[j]);
+            const unsigned mk = __ballot_sync(FULL, alive);
+            int base = 0;
+            if (lane == 0 && mk) base = atomicAdd(&sm.n_alive, __popc(mk));
+            base = __shfl_sync(FULL, base, 0);
+            if (alive) sm.alive[base + __popc(mk & ((1u << lane) - 1u))] = (short)k;
+        }
+    }
+    cta_sync<WPE>();  // any lane may be dealt any survivor
+    {
+        const int n_alive = sm.n_alive;
+#ifdef NAVGYM_PROFILE
+        if (tid == 0) sm.prof_alive += n_alive;
+#endif
+        march_tail_dealt<WPE>(sm, dist, x0, y0, W, H, t_stop, n_alive, warp, lane);
+    }
+    cta_sync<WPE>();
+#undef BEAM
+}
+
+// One CTA of WPE warps = one environment.  Thread t of the CTA owns beams t + 32 WPE i, i = 0 ..
 // 16 / WPE - 1: the lanes of a warp work on neighbouring beams, whose EDT gathers share sectors.
 // A scan marches in two phases (see the march section below): a lockstep head phase, four
 // samples per beam with four beams per thread in flight, then a tail phase in which the beams
-// still alive are dealt to lanes as lanes fall free (MARCH_SLOTS = 1: ballot-rank dealing, one
-// beam per lane at a time; > 1: several per lane from a shared counter).  The three scans a step
+// still alive are dealt to lanes as lanes fall free (ballot-rank dealing, one beam per lane at a
+// time; the last beam of a warp is marched by all its lanes together).  The three scans a step
 // may need (the step's scan, the crash re-scan env.py:718, the auto-reset first scan) run
 // through ONE copy of the scan code inside a CTA-uniform pass loop.
-#ifndef NAVGYM_HEAD_STEPS
-#define NAVGYM_HEAD_STEPS 4  // samples every beam marches in the lockstep head phase
-#endif
 #ifndef NAVGYM_RISK_MARGIN
 #define NAVGYM_RISK_MARGIN 0.25f  // [m] clearance under which the next step may end the episode
 #endif
-#ifndef NAVGYM_THREADS_PER_SM
-#define NAVGYM_THREADS_PER_SM 1024  // resident threads the register budget is tuned for
+#define NAVGYM_CTA_THREADS 64
+#ifndef NAVGYM_CTAS_PER_SM
+#define NAVGYM_CTAS_PER_SM 16  // resident CTAs the register budget is tuned for (64 registers)
 #endif
-template <bool IS_RESET_KERNEL, int WPE, int MARCH_SLOTS>
-__global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) step_kernel(const navgym_step_args_t a)
+template <bool IS_RESET_KERNEL, int WPE>
+__device__ __forceinline__ void step_body(const navgym_step_args_t &a, EnvSmem &sm, const int e, const int tid,
+                                          int *sched_cnt, int *sched_list)
 {
     constexpr int BPL = NB / (32 * WPE);  // beams per lane
-    constexpr int TPB = WPE * 32;
-    static_assert(BPL >= MARCH_SLOTS && BPL % MARCH_SLOTS == 0, "beams per lane vs slots");
-    __shared__ EnvSmem sm;
-    const int tid = threadIdx.x;
+    constexpr int TPB = WPE * 32;         // threads of the CTA
+    constexpr int MARCH_SLOTS = 1;
     const int lane = tid & 31, warp = tid >> 5;
     const int B = a.num_envs;
     const long long t_begin = clock64();
-    // Which environment this CTA steps.  With a schedule buffer, CTAs take environments in
-    // descending order of the cycles they cost in the previous step (they change slowly from
-    // step to step), so the longest ones start first and the launch does not end on a lone
-    // straggler; NAVGYM_SCHED_BUCKETS cost classes, bucket 0 = most expensive.
-    int e = a.env_begin + blockIdx.x;
-    int *sched_cnt = nullptr, *sched_list = nullptr;
-    if (!IS_RESET_KERNEL && a.sched) {
-        const int cur = a.sched_phase, nxt = (a.sched_phase + 1) % 3, clr = (a.sched_phase + 2) % 3;
-        int *cnt = a.sched;                                   // [3][NBK]
-        int *lst = a.sched + 3 * NAVGYM_SCHED_BUCKETS;        // [3][NBK][B]
-        const int c = cnt[cur * NAVGYM_SCHED_BUCKETS + (threadIdx.x & 31)];
-        int incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((threadIdx.x & 31) >= o) incl += v;
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, (int)blockIdx.x < incl);
-        const int b = m ? __ffs(m) - 1 : 31;
-        const int excl = __shfl_sync(0xffffffffu, incl - c, b);
-        e = lst[((size_t)cur * NAVGYM_SCHED_BUCKETS + b) * B + ((int)blockIdx.x - excl)];
-        sched_cnt = cnt + nxt * NAVGYM_SCHED_BUCKETS;
-        sched_list = lst + (size_t)nxt * NAVGYM_SCHED_BUCKETS * B;
-        if (blockIdx.x == 0 && threadIdx.x < NAVGYM_SCHED_BUCKETS) cnt[clr * NAVGYM_SCHED_BUCKETS + threadIdx.x] = 0;
-    }
     const unsigned FULL = 0xffffffffu;
     double *S = a.state;
 #define ST(f) S[(size_t)(f) * B + e]
 #define BEAM(i) (tid + TPB * (i))
 
     PROF_DECL
+#ifdef NAVGYM_PROFILE
+    if (tid < 8) { sm.prof_iters_a[tid] = 0; sm.prof_rounds_b[tid] = 0; sm.prof_cyc_b[tid] = 0; sm.prof_walk[tid] = 0; }
+    if (tid == 0) sm.prof_alive = 0;
+#endif
     // ---------------- prologue (warp 0): state (lane f holds row f), kinematics ----------
     // Every global load the prologue needs is issued up front (they only depend on e), the map
     // descriptor as soon as the map id is back, so one L2 round trip overlaps the next and the
@@ -300,11 +454,11 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
     float margin = CUDART_INF_F; // its smallest clearance over the crash thresholds [m]
     for (bool first = true;; first = false) {
         // ---- per-pass setup; the first pass was set up by the prologue
-        if (WPE > 1) __syncthreads(); else __syncwarp();
+        cta_sync<WPE>();
         if (!first) {
             t_pass = clock64();
             if (tid == 0) pass_setup(sm, a.maps[sm.map], a, TPB * MARCH_SLOTS);
-            if (WPE > 1) __syncthreads(); else __syncwarp();
+            cta_sync<WPE>();
         }
         margin = CUDART_INF_F;
         PROF_MARK(0);
@@ -323,115 +477,8 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
         // The loops only find each beam's hit cell (packed into sm.scan); ranges are computed
         // afterwards with all lanes active.
         {
-            const int W = sm.W, H = sm.H, ci = sm.ci, cj = sm.cj;
-            const float x0 = (float)ci, y0 = (float)cj;
-            const float t_stop = sm.t_stop;
-            const float *dist = a.edt_pool + sm.edt_off;
-            asm volatile("" : "+l"(dist));  // keep base + offset folded into one register pair
-            // xy_to_cell clips ci against H and cj against W (the reference's quirk, env.py:1245-1248):
-            // on a non-square map the origin can still lie outside [0, W) x [0, H), where
-            // calc_range's first sample returns "no hit" for every beam
-            const bool o_in = ((unsigned)ci < (unsigned)W) & ((unsigned)cj < (unsigned)H);
-            const float d0 = o_in ? __ldg(dist + cj * W + ci) : 1.0f;
-            const float t1 = fmaxf(__fmul_rn(d0, 0.999f), 1.0f);  // == 0.0f + first step
-            const bool degenerate = !o_in | (d0 <= 0.0f) | !(t1 < t_stop);
-            constexpr int HB = BPL >= 4 ? 4 : BPL;   // beams in flight per thread in the head phase
-#pragma unroll 1
-            for (int r = 0; r < BPL / HB; r++) {
-                float th_[HB], dxh[HB], dyh[HB];
-                // beam directions (env.py:388-390, 420-424)
-#pragma unroll
-                for (int j = 0; j < HB; j++) {
-                    const int k = BEAM(r * HB + j);
-                    const float h = (float)__dadd_rn(a.lin[k], (double)lt);
-                    double sd, cd;
-                    dir_sincos((double)h, sd, cd);
-                    dxh[j] = (float)cd;
-                    dyh[j] = (float)sd;
-                    sm.dir[k] = make_float2(dxh[j], dyh[j]);
-                    th_[j] = t1;
-                    if (degenerate) { sm.scan[k] = (o_in & (d0 <= 0.0f)) ? (cj << 16 | ci) : -1; th_[j] = -1.0f; }
-                }
-#pragma unroll 1
-                for (int st = 0; st < NAVGYM_HEAD_STEPS; st++) {
-                    float dv[HB];
-                    int cx[HB], cy[HB];
-                    bool inb[HB];
-#pragma unroll
-                    for (int j = 0; j < HB; j++) {
-                        cx[j] = __float2int_rz(__fmaf_rn(dxh[j], th_[j], x0));
-                        cy[j] = __float2int_rz(__fmaf_rn(dyh[j], th_[j], y0));
-                        inb[j] = ((unsigned)cx[j] < (unsigned)W) & ((unsigned)cy[j] < (unsigned)H);
-                        const unsigned idx = (inb[j] & (th_[j] >= 0.0f)) ? (unsigned)(cy[j] * W + cx[j]) : 0u;
-                        dv[j] = __ldg(dist + idx);
-                    }
-#pragma unroll
-                    for (int j = 0; j < HB; j++) {
-                        const bool alive = th_[j] >= 0.0f;
-                        const bool hit = inb[j] & (dv[j] <= 0.0f);
-                        const float tn = __fadd_rn(th_[j], fmaxf(__fmul_rn(dv[j], 0.999f), 1.0f));
-                        const bool fin = !inb[j] | hit | !(tn < t_stop);
-                        if (alive & fin) sm.scan[BEAM(r * HB + j)] = hit ? (cy[j] << 16 | cx[j]) : -1;
-                        th_[j] = (alive & !fin) ? tn : -1.0f;
-                    }
-                }
-                // survivors: park t in the scan slot and append the beam to the compact list
-#pragma unroll
-                for (int j = 0; j < HB; j++) {
-                    const int k = BEAM(r * HB + j);
-                    const bool alive = th_[j] >= 0.0f;
-                    if (alive) sm.scan[k] = __float_as_int(th_[j]);
-                    const unsigned mk = __ballot_sync(FULL, alive);
-                    int base = 0;
-                    if (lane == 0 && mk) base = atomicAdd(&sm.n_alive, __popc(mk));
-                    base = __shfl_sync(FULL, base, 0);
-                    if (alive) sm.alive[base + __popc(mk & ((1u << lane) - 1u))] = (short)k;
-                }
-            }
-            if (WPE > 1) __syncthreads(); else __syncwarp();  // any lane may be dealt any survivor
-            PROF_MARK(2);
-            {
-                const int n_alive = sm.n_alive;
-                if (MARCH_SLOTS == 1) {
-                    // Warp w owns list entries w, w + WPE, w + 2 WPE, ...; they are dealt to its
-                    // lanes with ballot ranks (no atomics, no cross-warp traffic): a lane whose
-                    // beam ends takes the warp's next undealt entry.
-                    int next_j = 32;                       // warp-uniform: entries dealt so far
-                    int idx = warp + WPE * lane;
-                    int kb = idx < n_alive ? (int)sm.alive[idx] : -1;
-                    float t = __int_as_float(sm.scan[kb >= 0 ? kb : 0]);
-                    float2 dd = sm.dir[kb >= 0 ? kb : 0];
-                    if (__any_sync(FULL, kb >= 0)) {
-                        for (;;) {
-                            const int cx = __float2int_rz(__fmaf_rn(dd.x, t, x0));
-                            const int cy = __float2int_rz(__fmaf_rn(dd.y, t, y0));
-                            const bool inb = ((unsigned)cx < (unsigned)W) & ((unsigned)cy < (unsigned)H);
-                            const unsigned ci_ = (inb & (kb >= 0)) ? (unsigned)(cy * W + cx) : 0u;
-                            const float d = __ldg(dist + ci_);
-                            const bool hit = inb & (d <= 0.0f);
-                            t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
-                            const bool fin = (kb >= 0) & (!inb | hit | !(t < t_stop));
-                            const unsigned fm = __ballot_sync(FULL, fin);
-                            if (fin) {
-                                // absolute hit cell, (y << 16 | x), or -1 for "no hit"
-                                sm.scan[kb] = hit ? (cy << 16 | cx) : -1;
-                                idx = warp + WPE * (next_j + __popc(fm & ((1u << lane) - 1u)));
-                                kb = -1;
-                                if (idx < n_alive) {
-                                    kb = sm.alive[idx];
-                                    t = __int_as_float(sm.scan[kb]);
-                                    dd = sm.dir[kb];
-                                }
-                            }
-                            next_j += __popc(fm);
-                            if (!__any_sync(FULL, kb >= 0)) break;
-                        }
-                    }
-                } else {
-                    march_tail_slots<MARCH_SLOTS, TPB>(sm, dist, x0, y0, W, H, t_stop, n_alive, tid);
-                }
-            }
-            if (WPE > 1) __syncthreads(); else __syncwarp();
+            march_scan<WPE>(sm, a, 0, BPL / 4, tid);
+            const int ci = sm.ci, cj = sm.cj;
             // ranges (env.py:426), all lanes active: sqrt(di^2 + dj^2) * resolution
             const bool rec = pass == (IS_RESET_KERNEL ? PASS_RESET : PASS_STEP) && a.hits;
             const float max_range = sm.max_range, res32 = sm.res32;
@@ -455,7 +502,7 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
         // ---- pedestrians: segments (env.py:430-431) and discs (env.py:432), min-merged.
         // One warp per obstacle, lanes across the beams of its angular window.
         if (ns + nd > 0) {
-            if (WPE > 1) __syncthreads(); else __syncwarp();
+            cta_sync<WPE>();
             // (the first scan after an auto-reset sees the next episode's pedestrians, if given)
             const bool nxt = !IS_RESET_KERNEL && pass == PASS_RESET && a.discs_reset != nullptr;
             const float *discs = (nxt ? a.discs_reset : a.discs) + (size_t)e * a.max_disc * 3;
@@ -494,7 +541,7 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
                     }
                 }
             }
-            if (WPE > 1) __syncthreads(); else __syncwarp();
+            cta_sync<WPE>();
         }
         PROF_MARK(4);
         // ---- clip + noise (env.py:435-440), thresholds, observation row
@@ -518,7 +565,7 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
                             (uint32_t)pass, (uint32_t)q, z);
                     *reinterpret_cast<float4 *>(zs + 4 * q) = make_float4(z[0], z[1], z[2], z[3]);
                 }
-                if (WPE > 1) __syncthreads(); else __syncwarp();
+                cta_sync<WPE>();
             }
 #pragma unroll 1
             for (int g = 0; g < BPL / G; g++) {
@@ -556,13 +603,8 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
         if (pass == PASS_STEP) {
             // ---- reward / done / info on this observation (env.py:464-589)
             int crash, discomf;
-            if (WPE > 1) {
-                crash = __syncthreads_or(c_any);
-                discomf = __syncthreads_or(d_any) && !crash;
-            } else {
-                crash = __any_sync(FULL, c_any);
-                discomf = __any_sync(FULL, d_any) && !crash;
-            }
+            crash = cta_or<WPE>(c_any);
+            discomf = cta_or<WPE>(d_any) && !crash;
             double mn = CUDART_INF;
             if (discomf) {
                 for (int i = 0; i < BPL; i++) {
@@ -575,7 +617,7 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
                 for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(FULL, mn, o));
                 if (WPE > 1) {
                     if (lane == 0) sm.red[warp] = mn;
-                    __syncthreads();
+                    cta_sync<WPE>();
                 }
             }
             if (warp == 0) {
@@ -637,7 +679,7 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
                     sm.next_pass = next;
                 }
             }
-            if (WPE > 1) __syncthreads(); else __syncwarp();
+            cta_sync<WPE>();
             pass = sm.next_pass;
             if (pass == PASS_RESET && a.discs_reset != nullptr) {
                 nd = min(a.ndisc_reset[e], a.max_disc);
@@ -664,7 +706,7 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
             risky |= gx * gx + gy * gy < (a.dist_thresh + NAVGYM_RISK_MARGIN) * (a.dist_thresh + NAVGYM_RISK_MARGIN);
             risky |= a.max_episode_steps > 0 && sm.steps + 1 >= a.max_episode_steps;
         }
-        risky = (WPE > 1 ? __syncthreads_or(risky) : __any_sync(FULL, risky)) && a.auto_reset;
+        risky = cta_or<WPE>(risky) && a.auto_reset;
         if (tid == 0) {
             const long long kc = ((clock64() - t_pass) << (risky ? 1 : 0)) >> 13;
             sched_b = NAVGYM_SCHED_BUCKETS - 1 - (int)(kc > NAVGYM_SCHED_BUCKETS - 1 ? NAVGYM_SCHED_BUCKETS - 1 : kc);
@@ -728,8 +770,50 @@ __global__ void __launch_bounds__(WPE * 32, NAVGYM_THREADS_PER_SM / (WPE * 32)) 
         a.tail64[(size_t)e * 7 + 1] = (double)t_end;
         a.tail64[(size_t)e * 7 + 2] = (double)smid;
         a.tail64[(size_t)e * 7 + 3] = (double)blockIdx.x;
+        a.tail64[(size_t)e * 7 + 4] = (double)sm.prof_alive + 4096.0 * (double)max(sm.prof_cyc_b[0], sm.prof_cyc_b[1]) + 4096.0 * 16777216.0 * (double)max(sm.prof_walk[0], sm.prof_walk[1]);
+        a.tail64[(size_t)e * 7 + 5] = (double)max(sm.prof_iters_a[0], sm.prof_iters_a[1]);
+        a.tail64[(size_t)e * 7 + 6] = (double)max(sm.prof_rounds_b[0], sm.prof_rounds_b[1]);
     }
 #endif
 #undef ST
 #undef BEAM
+}
+
+// Launch order.  With a schedule buffer, teams take environments in descending order of the
+// cycles they cost in the previous step (they change slowly from step to step): position p of
+// the order is the p-th entry of the concatenated cost-class lists, NAVGYM_SCHED_BUCKETS classes,
+// class 0 = most expensive (a warp-wide prefix scan over the class counts finds it).
+__device__ __forceinline__ int sched_lookup(const navgym_step_args_t &a, const int pos, int *&sched_cnt, int *&sched_list)
+{
+    const int B = a.num_envs, lane = threadIdx.x & 31;
+    const int cur = a.sched_phase, nxt = (a.sched_phase + 1) % 3, clr = (a.sched_phase + 2) % 3;
+    int *cnt = a.sched;                                   // [3][NBK]
+    int *lst = a.sched + 3 * NAVGYM_SCHED_BUCKETS;        // [3][NBK][B]
+    const int c = cnt[cur * NAVGYM_SCHED_BUCKETS + lane];
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, pos < incl);
+    const int b = m ? __ffs(m) - 1 : 31;
+    const int excl = __shfl_sync(0xffffffffu, incl - c, b);
+    sched_cnt = cnt + nxt * NAVGYM_SCHED_BUCKETS;
+    sched_list = lst + (size_t)nxt * NAVGYM_SCHED_BUCKETS * B;
+    if (blockIdx.x == 0 && threadIdx.x < NAVGYM_SCHED_BUCKETS) cnt[clr * NAVGYM_SCHED_BUCKETS + threadIdx.x] = 0;
+    return lst[((size_t)cur * NAVGYM_SCHED_BUCKETS + b) * B + (pos - excl)];
+}
+
+// One CTA (2 warps) = one environment; CTA b of the launch takes the b-th environment of the
+// launch order.
+template <bool IS_RESET_KERNEL>
+__global__ void __launch_bounds__(NAVGYM_CTA_THREADS, NAVGYM_CTAS_PER_SM) step_kernel(const navgym_step_args_t a)
+{
+    __shared__ EnvSmem sm;
+    constexpr int WPE = NAVGYM_CTA_THREADS / 32;
+    int e = a.env_begin + (int)blockIdx.x;
+    int *sched_cnt = nullptr, *sched_list = nullptr;
+    if (!IS_RESET_KERNEL && a.sched) e = sched_lookup(a, (int)blockIdx.x, sched_cnt, sched_list);
+    step_body<IS_RESET_KERNEL, WPE>(a, sm, e, (int)threadIdx.x, sched_cnt, sched_list);
 }

@@ -8,7 +8,7 @@ OUT = os.path.join(ROOT, 'tools', '_prof', 'libnavgym_b200_prof.so')
 if sys.argv[1] == 'build':
     from nav_gym_b200 import _lib
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    for tag, extra in (('', []),):
+    for tag, extra in (('', []), ('_nocoop', ['-DNAVGYM_COOP_ENTER=0']), ('_e1', ['-DNAVGYM_COOP_ENTER=1']), ('_e2', ['-DNAVGYM_COOP_ENTER=2'])):
         out = OUT.replace('.so', tag + '.so')
         r = subprocess.run(['nvcc'] + _lib.NVCC_FLAGS + ['-DNAVGYM_PROFILE', '-Xptxas', '-v'] + extra + ['-o', out, _lib.SRC], capture_output=True, text=True)
         lines = r.stderr.splitlines()
@@ -28,9 +28,9 @@ else:
     mp = MapPool([m], 'cuda:0', spawn_pools=[pool])
     env = BatchedNavGym(B, mp, seed=1, auto_reset=True)
     env.reset_from_spawn_pool(np.random.RandomState(1))
-    act = torch.rand(B, 2, device='cuda') * torch.tensor([0.5, 1.28], device='cuda') + torch.tensor([0, -0.64], device='cuda')
-    if npool: act = act[:1].expand(B, 2).contiguous() * 0
-    for _ in range(10): env.step(act)
+    bank = torch.rand(16, B, 2, device='cuda') * torch.tensor([0.5, 1.28], device='cuda') + torch.tensor([0, -0.64], device='cuda')
+    if npool: bank = bank * 0
+    for i in range(40): env.step(bank[i % 16])
     torch.cuda.synchronize()
     lib = _lib.load()
     buf = (C.c_ulonglong * 16)()
@@ -38,7 +38,7 @@ else:
     n = 20
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(n): env.step(act)
+    for i in range(n): env.step(bank[i % 16])
     e1.record(); torch.cuda.synchronize()
     lib.navgym_debug_read_prof(buf, 1)
     names = ['prologue(kinematics)', 'pass setup', 'beam dirs(sincos)', 'march', 'obstacles', 'clip+noise+obs', 'reward/branch', 'epilogue']
@@ -62,3 +62,17 @@ else:
     sm = tl[:, 2].astype(int)
     busy = np.array([en[sm == i].max() for i in np.unique(sm)])
     print('per-SM finish time us: min %.1f mean %.1f max %.1f' % (busy.min(), busy.mean(), busy.max()))
+    wk = np.floor(tl[:, 4] / (4096.0 * 16777216.0)); cb = np.floor((tl[:, 4] - wk * 4096.0 * 16777216.0) / 4096.0); tl[:, 4] = tl[:, 4] - wk * 4096.0 * 16777216.0 - cb * 4096.0
+    al, ia, rb = tl[:, 4], tl[:, 5], tl[:, 6]
+    print('regime B: cycles per CTA mean %.0f (max warp); rounds %.1f; walk iterations %.1f; cycles/round %.0f; walk its/round %.1f' % (cb.mean(), rb.mean(), wk.mean(), cb.sum() / max(rb.sum(), 1), wk.sum() / max(rb.sum(), 1)))
+    print('survivors per env: mean %.0f p99 %.0f max %.0f; regime A iterations (max over warps): mean %.1f p99 %.0f max %.0f; regime B rounds: mean %.1f p99 %.0f max %.0f' % (
+        al.mean(), np.percentile(al, 99), al.max(), ia.mean(), np.percentile(ia, 99), ia.max(), rb.mean(), np.percentile(rb, 99), rb.max()))
+    one = ~dn
+    print('corr(duration, survivors) %.3f  corr(duration, A iters) %.3f  corr(duration, A+B) %.3f' % (
+        np.corrcoef(dur[one], al[one])[0, 1], np.corrcoef(dur[one], ia[one])[0, 1], np.corrcoef(dur[one], (ia + rb)[one])[0, 1]))
+    for i in np.argsort(dur)[-8:]:
+        print('  slow env %5d: start %.1f dur %.1f us  survivors %d  A iters %d  B rounds %d  done %d' % (i, st[i], dur[i], al[i], ia[i], rb[i], dn[i]))
+    cyc = dur[one] * 1.965e3
+    print('one-scan envs: cycles per (A iter + B round): mean %.0f' % (cyc.sum() / max((ia + rb)[one].sum(), 1)))
+    if os.environ.get('NAVGYM_DUMP'):
+        np.save(os.environ['NAVGYM_DUMP'], np.column_stack([tl, dn.astype(np.float64), env.is_crash.cpu().numpy()]))
