@@ -56,12 +56,23 @@ static int env_int(const char *name, int dflt)
     return s ? atoi(s) : dflt;
 }
 
+static int coop_default_max()
+{
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return (int)(2.4 * sms * NAVGYM_CTAS_PER_SM);
+}
+
 // Launch shape of the fused kernel: one 64-thread CTA per environment of the launch.
 template <bool RESET>
 static cudaError_t launch_step(const navgym_step_args_t &a, cudaStream_t st)
 {
     const int count = a.env_count > 0 ? a.env_count : a.num_envs - a.env_begin;
-    step_kernel<RESET><<<count, NAVGYM_CTA_THREADS, 0, st>>>(a);
+    // tail regime B (see step_kernel) while the launch is at most ~2.4 waves of CTAs (measured
+    // crossover on B200: 5120 envs -2 %, 6144 envs +2 %); NAVGYM_COOP_MAX_ENVS overrides
+    static const int coop_max = env_int("NAVGYM_COOP_MAX_ENVS", coop_default_max());
+    if (count <= coop_max) step_kernel<RESET, true><<<count, NAVGYM_CTA_THREADS, 0, st>>>(a);
+    else step_kernel<RESET, false><<<count, NAVGYM_CTA_THREADS, 0, st>>>(a);
     g_launches++;
     return cudaSuccess;
 }

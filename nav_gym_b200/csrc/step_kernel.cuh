@@ -129,7 +129,10 @@ __device__ __forceinline__ int cta_or(int pred)
 #ifndef NAVGYM_COOP_ENTER
 #define NAVGYM_COOP_ENTER 1
 #endif
-template <int WPE>
+#ifndef NAVGYM_COOP_LOG2_WIDTH
+#define NAVGYM_COOP_LOG2_WIDTH 5   // at most 2^5 lanes fetch ahead for one beam
+#endif
+template <int WPE, bool COOP>
 __device__ __forceinline__ void march_tail_dealt(EnvSmem &sm, const float *__restrict__ dist, float x0, float y0,
                                                  int W, int H, float t_stop, int n_alive, int warp, int lane)
 {
@@ -142,7 +145,7 @@ __device__ __forceinline__ void march_tail_dealt(EnvSmem &sm, const float *__res
     unsigned live = __ballot_sync(FULL, kb >= 0);
     if (!live) return;
     // ---- regime A
-    while (NAVGYM_COOP_ENTER == 0 || warp + WPE * next_j < n_alive || __popc(live) > NAVGYM_COOP_ENTER) {
+    while (!COOP || NAVGYM_COOP_ENTER == 0 || warp + WPE * next_j < n_alive || __popc(live) > NAVGYM_COOP_ENTER) {
         const int cx = __float2int_rz(__fmaf_rn(dd.x, t, x0));
         const int cy = __float2int_rz(__fmaf_rn(dd.y, t, y0));
         const bool inb = ((unsigned)cx < (unsigned)W) & ((unsigned)cy < (unsigned)H);
@@ -176,7 +179,7 @@ __device__ __forceinline__ void march_tail_dealt(EnvSmem &sm, const float *__res
 #endif
     while (live) {
         const int L = __popc(live);        // <= NAVGYM_COOP_ENTER <= 16
-        const int lg = L > 8 ? 1 : L > 4 ? 2 : L > 2 ? 3 : L > 1 ? 4 : 5;   // G = 32 / L, a power of two
+        const int lg = min(L > 8 ? 1 : L > 4 ? 2 : L > 2 ? 3 : L > 1 ? 4 : 5, NAVGYM_COOP_LOG2_WIDTH);   // G = 32 / L, a power of two
         const int G = 1 << lg;             // lanes per beam
         const int g = lane >> lg, j = lane & (G - 1), base = lane & ~(G - 1);
         const bool act = g < L;
@@ -245,7 +248,7 @@ __device__ __forceinline__ void march_tail_dealt(EnvSmem &sm, const float *__res
 // (round r = this thread's beams BEAM(4 r .. 4 r + 3)): beam directions, lockstep head phase,
 // survivor list, tail phase.  Leaves every beam's hit cell, (y << 16 | x) or -1, in sm.scan and
 // its direction in sm.dir; ends on a CTA barrier.  Scan set-up is read from sm (pass_setup).
-template <int WPE>
+template <int WPE, bool COOP>
 __device__ __forceinline__ void march_scan(EnvSmem &sm, const navgym_step_args_t &a, const int r_begin, const int r_end,
                                            const int tid)
 {
@@ -325,7 +328,7 @@ __device__ __forceinline__ void march_scan(EnvSmem &sm, const navgym_step_args_t
 #ifdef NAVGYM_PROFILE
         if (tid == 0) sm.prof_alive += n_alive;
 #endif
-        march_tail_dealt<WPE>(sm, dist, x0, y0, W, H, t_stop, n_alive, warp, lane);
+        march_tail_dealt<WPE, COOP>(sm, dist, x0, y0, W, H, t_stop, n_alive, warp, lane);
     }
     cta_sync<WPE>();
 #undef BEAM
@@ -346,7 +349,7 @@ __device__ __forceinline__ void march_scan(EnvSmem &sm, const navgym_step_args_t
 #ifndef NAVGYM_CTAS_PER_SM
 #define NAVGYM_CTAS_PER_SM 16  // resident CTAs the register budget is tuned for (64 registers)
 #endif
-template <bool IS_RESET_KERNEL, int WPE>
+template <bool IS_RESET_KERNEL, int WPE, bool COOP>
 __device__ __forceinline__ void step_body(const navgym_step_args_t &a, EnvSmem &sm, const int e, const int tid,
                                           int *sched_cnt, int *sched_list)
 {
@@ -477,7 +480,7 @@ __device__ __forceinline__ void step_body(const navgym_step_args_t &a, EnvSmem &
         // The loops only find each beam's hit cell (packed into sm.scan); ranges are computed
         // afterwards with all lanes active.
         {
-            march_scan<WPE>(sm, a, 0, BPL / 4, tid);
+            march_scan<WPE, COOP>(sm, a, 0, BPL / 4, tid);
             const int ci = sm.ci, cj = sm.cj;
             // ranges (env.py:426), all lanes active: sqrt(di^2 + dj^2) * resolution
             const bool rec = pass == (IS_RESET_KERNEL ? PASS_RESET : PASS_STEP) && a.hits;
@@ -806,8 +809,10 @@ __device__ __forceinline__ int sched_lookup(const navgym_step_args_t &a, const i
 }
 
 // One CTA (2 warps) = one environment; CTA b of the launch takes the b-th environment of the
-// launch order.
-template <bool IS_RESET_KERNEL>
+// launch order.  COOP selects tail regime B (march_tail_dealt): it shortens the launch's slowest
+// environments at the price of ~4 % more gathers and instructions, which pays while a launch is
+// at most ~2 waves of CTAs (4096 envs: -16 %) and costs beyond (32768 envs: +7 %).
+template <bool IS_RESET_KERNEL, bool COOP>
 __global__ void __launch_bounds__(NAVGYM_CTA_THREADS, NAVGYM_CTAS_PER_SM) step_kernel(const navgym_step_args_t a)
 {
     __shared__ EnvSmem sm;
@@ -815,5 +820,5 @@ __global__ void __launch_bounds__(NAVGYM_CTA_THREADS, NAVGYM_CTAS_PER_SM) step_k
     int e = a.env_begin + (int)blockIdx.x;
     int *sched_cnt = nullptr, *sched_list = nullptr;
     if (!IS_RESET_KERNEL && a.sched) e = sched_lookup(a, (int)blockIdx.x, sched_cnt, sched_list);
-    step_body<IS_RESET_KERNEL, WPE>(a, sm, e, (int)threadIdx.x, sched_cnt, sched_list);
+    step_body<IS_RESET_KERNEL, WPE, COOP>(a, sm, e, (int)threadIdx.x, sched_cnt, sched_list);
 }
