@@ -412,6 +412,9 @@ void navgym_grid_bfs(const uint8_t *blocked, int H, int W, int sr, int sc, int32
 const char *navgym_error_string(int code);
 int navgym_device_count(void);
 int navgym_abi_version(void);
+/* 1: the march samples trunc(fmaf(dx, t, x0)) (canonical); 0: this build rounds dx * t and the
+ * sum separately (-DNAVGYM_MARCH_NO_FMA; range_libc's own rounding is unknown) */
+int navgym_march_is_fused(void);
 int navgym_sizeof_step_args(void);   /* layout check for FFI bindings */
 int navgym_sizeof_map(void);
 int navgym_sizeof_her_args(void);

@@ -36,6 +36,19 @@ def _nvcc():
     return None
 
 
+SO_NOFMA = os.path.join(_PKG, 'libnavgym_b200_nofma.so')  # -DNAVGYM_MARCH_NO_FMA build (tests)
+
+
+def build_variants(force=False):
+    """The alternative builds the parity tests exercise: the march with separately rounded
+    multiply and add (see csrc/device_helpers.cuh march_pos)."""
+    csrc = os.path.dirname(SRC)
+    newest = max([os.path.getmtime(HDR)] + [os.path.getmtime(os.path.join(csrc, f)) for f in os.listdir(csrc)])
+    if force or not os.path.exists(SO_NOFMA) or os.path.getmtime(SO_NOFMA) < newest:
+        subprocess.check_call([_nvcc()] + NVCC_FLAGS + ['-DNAVGYM_MARCH_NO_FMA', '-o', SO_NOFMA, SRC])
+    return SO_NOFMA
+
+
 def build(force=False, verbose=False):
     """Compile the CUDA library for sm_100a (cross-compiles without a GPU)."""
     if not force and os.path.exists(SO):
@@ -169,7 +182,7 @@ EXPORTS = [
     'navgym_peds_plan', 'navgym_sizeof_plan_args', 'navgym_sizeof_plan_map',
     'navgym_peds_move', 'navgym_sizeof_move_args', 'navgym_policy_features',
     'navgym_host_pipe_groups', 'navgym_host_pipe_group_bounds', 'navgym_host_rollout',
-    'navgym_policy_action_bank', 'navgym_export_env', 'navgym_export_env_len',
+    'navgym_policy_action_bank', 'navgym_export_env', 'navgym_export_env_len', 'navgym_march_is_fused',
 ]
 
 _lib = None

@@ -44,6 +44,21 @@ __device__ __forceinline__ void dir_sincos(double x, double &sn, double &cs)
     cs = ((n + 1) & 2) ? -b : b;
 }
 
+// Sample position of the march, x0 + dx * t (range_libc RayMarching::calc_range).  The real
+// range_libc is built -O3 -march=native -ffast-math, where the compiler is free to contract the
+// multiply-add; its source is absent ("parity unpinned"), so which form its binary uses is
+// unknown.  Canonical: fused (one rounding).  -DNAVGYM_MARCH_NO_FMA builds the separately
+// rounded form -- the oracle has the matching switch (-DNVO_MARCH_NO_FMA) and both pairs are
+// parity-tested, so the real package can be matched by flipping one flag.
+__device__ __forceinline__ float march_pos(float d, float t, float o)
+{
+#ifdef NAVGYM_MARCH_NO_FMA
+    return __fadd_rn(__fmul_rn(d, t), o);
+#else
+    return __fmaf_rn(d, t, o);
+#endif
+}
+
 // range_libc RayMarching::calc_range, canonical form (oracle/navgym_oracle.c nvo_calc_range).
 __device__ __forceinline__ float march(const float *__restrict__ dist, int W, int H, float x0,
                                        float y0, float dx, float dy, float max_range,
@@ -53,8 +68,8 @@ __device__ __forceinline__ float march(const float *__restrict__ dist, int W, in
     hx = HIT_NONE;
     hy = HIT_NONE;
     while (t < t_stop) {
-        int px = __float2int_rz(__fmaf_rn(dx, t, x0));
-        int py = __float2int_rz(__fmaf_rn(dy, t, y0));
+        int px = __float2int_rz(march_pos(dx, t, x0));
+        int py = __float2int_rz(march_pos(dy, t, y0));
         if ((unsigned)px >= (unsigned)W || (unsigned)py >= (unsigned)H) break;
         float d = __ldg(dist + (size_t)py * W + px);
         if (d <= 0.0f) {

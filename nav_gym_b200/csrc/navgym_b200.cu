@@ -91,6 +91,14 @@ int navgym_debug_read_prof(unsigned long long *out, int reset)
 #endif
 
 int navgym_abi_version(void) { return 1; }
+int navgym_march_is_fused(void)
+{
+#ifdef NAVGYM_MARCH_NO_FMA
+    return 0;
+#else
+    return 1;
+#endif
+}
 int navgym_sizeof_step_args(void) { return (int)sizeof(navgym_step_args_t); }
 int navgym_sizeof_map(void) { return (int)sizeof(navgym_map_t); }
 int navgym_sizeof_her_args(void) { return (int)sizeof(navgym_her_args_t); }

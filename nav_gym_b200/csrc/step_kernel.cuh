@@ -146,8 +146,8 @@ __device__ __forceinline__ void march_tail_dealt(EnvSmem &sm, const float *__res
     if (!live) return;
     // ---- regime A
     while (!COOP || NAVGYM_COOP_ENTER == 0 || warp + WPE * next_j < n_alive || __popc(live) > NAVGYM_COOP_ENTER) {
-        const int cx = __float2int_rz(__fmaf_rn(dd.x, t, x0));
-        const int cy = __float2int_rz(__fmaf_rn(dd.y, t, y0));
+        const int cx = __float2int_rz(march_pos(dd.x, t, x0));
+        const int cy = __float2int_rz(march_pos(dd.y, t, y0));
         const bool inb = ((unsigned)cx < (unsigned)W) & ((unsigned)cy < (unsigned)H);
         const unsigned ci_ = (inb & (kb >= 0)) ? (unsigned)(cy * W + cx) : 0u;
         const float d = __ldg(dist + ci_);
@@ -193,8 +193,8 @@ __device__ __forceinline__ void march_tail_dealt(EnvSmem &sm, const float *__res
         for (;;) {
             // fetch: lane j guesses the sample at t + j (j = 0: the beam's own next sample)
             const float tj = __fadd_rn(bt, (float)j);
-            const int fx = __float2int_rz(__fmaf_rn(bdx, tj, x0));
-            const int fy = __float2int_rz(__fmaf_rn(bdy, tj, y0));
+            const int fx = __float2int_rz(march_pos(bdx, tj, x0));
+            const int fy = __float2int_rz(march_pos(bdy, tj, y0));
             const bool finb = ((unsigned)fx < (unsigned)W) & ((unsigned)fy < (unsigned)H);
             const int fcell = finb ? (fy << 16 | fx) : -2;
             const float fd = __ldg(dist + ((finb & !fin) ? (unsigned)(fy * W + fx) : 0u));
@@ -203,8 +203,8 @@ __device__ __forceinline__ void march_tail_dealt(EnvSmem &sm, const float *__res
             bool walking = !fin;
 #pragma unroll 1
             for (int it = 0; it < G; it++) {
-                const int wx = __float2int_rz(__fmaf_rn(bdx, bt, x0));
-                const int wy = __float2int_rz(__fmaf_rn(bdy, bt, y0));
+                const int wx = __float2int_rz(march_pos(bdx, bt, x0));
+                const int wy = __float2int_rz(march_pos(bdy, bt, y0));
                 const bool winb = ((unsigned)wx < (unsigned)W) & ((unsigned)wy < (unsigned)H);
                 const int wcell = wy << 16 | wx;
                 // the guess nearest to t (one candidate finds all but ~2 % of what three would)
@@ -293,8 +293,8 @@ __device__ __forceinline__ void march_scan(EnvSmem &sm, const navgym_step_args_t
             bool inb[HB];
 #pragma unroll
             for (int j = 0; j < HB; j++) {
-                cx[j] = __float2int_rz(__fmaf_rn(dxh[j], th_[j], x0));
-                cy[j] = __float2int_rz(__fmaf_rn(dyh[j], th_[j], y0));
+                cx[j] = __float2int_rz(march_pos(dxh[j], th_[j], x0));
+                cy[j] = __float2int_rz(march_pos(dyh[j], th_[j], y0));
                 inb[j] = ((unsigned)cx[j] < (unsigned)W) & ((unsigned)cy[j] < (unsigned)H);
                 const unsigned idx = (inb[j] & (th_[j] >= 0.0f)) ? (unsigned)(cy[j] * W + cx[j]) : 0u;
                 dv[j] = __ldg(dist + idx);

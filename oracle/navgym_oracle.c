@@ -172,6 +172,22 @@ void nvo_sincos(double x, double *sn, double *cs)
  * (dx, dy) = float(nvo_sincos(h)); sample cell = trunc(fmaf(dx, t, x0)); occupied <=> d <= 0;
  * t += max(d * 0.999f, 1.0f); out of map or t >= t_stop -> max_range.
  * hit[0..1] receives (px - x0, py - y0) as integers, or (INT16_MIN, INT16_MIN). */
+/* x0 + dx * t: fused by default; -DNVO_MARCH_NO_FMA = separately rounded multiply and add (the
+ * real range_libc is built with -ffast-math, its source is absent: either may be what its
+ * binary does -- the CUDA library has the matching -DNAVGYM_MARCH_NO_FMA build). */
+#ifdef NVO_MARCH_NO_FMA
+#define NVO_MARCH_POS(d, t, o) ((d) * (t) + (o))
+#else
+#define NVO_MARCH_POS(d, t, o) fmaf((d), (t), (o))
+#endif
+int nvo_march_is_fused(void)
+{
+#ifdef NVO_MARCH_NO_FMA
+    return 0;
+#else
+    return 1;
+#endif
+}
 float nvo_calc_range(const float *dist, int W, int H, float x0, float y0, float heading,
                      float max_range, float t_stop, int32_t *hit, int32_t *nsteps)
 {
@@ -182,8 +198,8 @@ float nvo_calc_range(const float *dist, int W, int H, float x0, float y0, float 
     int32_t n = 0;
     if (hit) { hit[0] = INT16_MIN; hit[1] = INT16_MIN; }
     while (t < t_stop) {
-        int px = (int)fmaf(dx, t, x0);
-        int py = (int)fmaf(dy, t, y0);
+        int px = (int)NVO_MARCH_POS(dx, t, x0);
+        int py = (int)NVO_MARCH_POS(dy, t, y0);
         if (px < 0 || px >= W || py < 0 || py >= H)
             break;
         float d = dist[(size_t)py * W + px];

@@ -11,7 +11,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, '_build', 'libnavgym_oracle.so')
+# NAVGYM_ORACLE_VARIANT=_nofma selects the build whose march rounds x0 + dx * t in two steps
+_SO = os.path.join(_HERE, '_build', 'libnavgym_oracle%s.so' % os.environ.get('NAVGYM_ORACLE_VARIANT', ''))
 
 NB = 512
 OBS_DIM = NB + 7

@@ -247,3 +247,56 @@ def test_map_pool_auto_reset_with_pedestrians_is_deterministic():
         assert int(env.steps.max()) <= 25
     for a, b in zip(*runs):
         assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+def test_no_fma_build_matches_no_fma_oracle():
+    """The -DNAVGYM_MARCH_NO_FMA library (x0 + dx * t rounded in two steps) against the oracle
+    built the same way: the pair the real range_libc would be matched with if its binary does
+    not contract the multiply-add.  Runs in a subprocess (one process loads one library)."""
+    import os
+    import subprocess
+    import sys
+    from nav_gym_b200 import _lib
+    if not os.path.exists(_lib.SO_NOFMA):
+        pytest.skip('libnavgym_b200_nofma.so not built (python -c "import __graft_entry__ as g; g.build()")')
+    code = r'''
+import numpy as np, sys, os
+sys.path.insert(0, os.path.join(os.getcwd(), 'tests'))
+import synth, cuda_util
+from oracle import oracle as orc
+from nav_gym_b200 import _lib, natives
+assert _lib.load().navgym_march_is_fused() == 0 and orc.lib().nvo_march_is_fused() == 0
+rng = np.random.RandomState(2)
+maps = [synth.indoor_map(rng), synth.outdoor_map(rng)]
+for m in maps:
+    occ = np.ascontiguousarray(np.asarray(m['data']) >= 0.1)
+    dist = orc.edt(occ)
+    H, W = occ.shape
+    n = 400000
+    ins = np.column_stack([rng.randint(0, W, n), rng.randint(0, H, n), rng.uniform(-7, 7, n)]).astype(np.float32)
+    rm = natives.PyRayMarching(natives.PyOMap(occ), W * H)
+    got, hits = rm.calc_range_many_with_hits(ins)
+    want, wh = orc.calc_range_many(dist, ins, float(W * H), want_hits=True)
+    assert np.array_equal(got, want) and np.array_equal(hits, wh.astype(np.int16))
+B = 512
+map_id = rng.randint(0, 2, B).astype(np.int32)
+edts = [orc.edt(np.asarray(m['data']) >= 0.1) for m in maps]
+start = np.zeros((B, 2))
+for i, m in enumerate(maps):
+    sel = np.where(map_id == i)[0]
+    start[sel] = synth.free_poses(rng, m, len(sel), 14, edts[i])
+goal = start + rng.uniform(-3, 3, (B, 2)); theta = rng.uniform(0, 2 * np.pi, B)
+o = orc.OracleBatch(maps, map_id, start, goal, theta, params=dict(t_stop=502.0))
+c = cuda_util.CudaStepper(maps, map_id, start, goal, theta, early_stop=True)
+o.reset_obs(); c.reset_obs()
+for t in range(10):
+    act = rng.uniform([-0.1, -0.7], [0.55, 0.7], (B, 2)).astype(np.float32)
+    o.step(act); c.step(act)
+    assert np.array_equal(c.hits, o.hits) and np.array_equal(c.obs[:, :512], o.obs[:, :512]), t
+    assert np.array_equal(c.done, o.done)
+print('no-fma pair ok')
+'''
+    env = dict(os.environ, NAVGYM_LIB=_lib.SO_NOFMA, NAVGYM_ORACLE_VARIANT='_nofma')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-c', code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'no-fma pair ok' in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])

@@ -66,3 +66,78 @@ def test_kinematics_known_answers():
     ok = o.is_crash == 0   # crashed envs are rolled back (env.py:707-723)
     assert ok.sum() > n // 2
     assert np.allclose(o.state[:3].T[ok], K['kin_out'][ok], rtol=0, atol=1e-12)
+
+
+def test_third_edt_witness_scipy():
+    """The oracle's Felzenszwalb-Huttenlocher EDT against scipy.ndimage.distance_transform_edt
+    (an independent implementation): exact squared distances equal on reference-style maps."""
+    from scipy import ndimage
+    from nav_gym_b200 import maps
+    rng = np.random.RandomState(5)
+    for m in (maps.create_indoor_map(3, 60, rng, cells=60, scale=5), maps.create_outdoor_map(10, 0.7, rng, size=300),
+              gu.map_info(gu.load(gu.trace_names()[0]))):
+        occ = np.asarray(m['data']) >= 0.1
+        d2 = orc.edt_sq(occ)
+        want = ndimage.distance_transform_edt(~occ) ** 2
+        assert np.array_equal(d2, np.rint(want).astype(np.int64))
+        assert np.array_equal(orc.edt(occ), np.sqrt(np.rint(want)).astype(np.float32))
+
+
+def test_axis_and_heading_convention_on_an_asymmetric_map():
+    """What the code of the reference fixes about the native boundary (not its absent sources):
+    map_info['data'] is [row = y][col = x] (map_generator.py:113-122; env.py:221,356 index
+    data.T as [i = x, j = y]); the ray origin is (i, j) = (x cell, y cell) and beam k looks along
+    lin[k] + theta in the world frame, counter-clockwise, beam 0 backwards and beam 256 forwards
+    (env.py:386-390, 419-424; ros_env.py publishes the scan as a LaserScan from angle_min = -pi).
+    One wall 3 m ahead on +x, another 5 m to the left on +y, nothing behind / to the right."""
+    H, W = 400, 600
+    data = np.zeros((H, W), np.int8)
+    x0, y0 = 10.0, 8.0
+    data[:, int((x0 + 3.0) / 0.05):int((x0 + 3.0) / 0.05) + 4] = 100          # wall at x = 13 m (columns)
+    data[int((y0 + 5.0) / 0.05):int((y0 + 5.0) / 0.05) + 4, :] = 100          # wall at y = 13 m (rows)
+    m = dict(data=data, origin=(0, 0), resolution=0.05, width=W, height=H)
+    for theta, fwd, left in ((0.0, 3.0, 5.0), (np.pi / 2, 5.0, None)):
+        o = orc.OracleBatch([m], np.zeros(1, np.int32), np.array([[x0, y0]]), np.array([[x0 + 1, y0]]),
+                            np.array([theta]))
+        scan = o.reset_obs()[0, :512]
+        assert abs(scan[256] - fwd) < 0.06, (theta, scan[256])                # beam 256: straight ahead
+        if left is not None:
+            assert abs(scan[384] - left) < 0.06, scan[384]                    # beam 384: +90 deg = left
+            assert scan[128] == 25.0 and scan[0] == 25.0                      # right / behind: open
+        else:
+            assert abs(scan[128] - 3.0) < 0.06                                # facing +y, the +x wall is on the right
+            assert scan[384] == 25.0
+    # a pedestrian box on the left shows up around beam 384, not 128 (render_contours_in_lidar)
+    o = orc.OracleBatch([m], np.zeros(1, np.int32), np.array([[x0, y0]]), np.array([[x0 + 1, y0]]),
+                        np.array([0.0]), max_seg=4)
+    box = np.array([[[x0 - 0.2, y0 + 2.0, x0 + 0.2, y0 + 2.0], [x0 + 0.2, y0 + 2.0, x0 + 0.2, y0 + 2.4],
+                     [x0 + 0.2, y0 + 2.4, x0 - 0.2, y0 + 2.4], [x0 - 0.2, y0 + 2.4, x0 - 0.2, y0 + 2.0]]], np.float32)
+    scan = o.reset_obs(segs=box, nseg=np.array([4], np.int32))[0, :512]
+    assert abs(scan[384] - 2.0) < 1e-3 and scan[128] == 25.0
+
+
+def test_march_rounding_switch():
+    """The oracle builds in two forms, x0 + dx * t fused (canonical) or separately rounded
+    (-DNVO_MARCH_NO_FMA): the forms agree on almost every ray and are distinguishable, so that
+    the real range_libc's choice can be matched by flipping the flag (the CUDA library has the
+    same switch; tests/test_gpu_parity.py runs both pairs)."""
+    import ctypes as C
+    import os
+    orc.build()
+    alt = C.CDLL(os.path.join(os.path.dirname(orc.__file__), '_build', 'libnavgym_oracle_nofma.so'))
+    assert orc.lib().nvo_march_is_fused() == 1 and alt.nvo_march_is_fused() == 0
+    G = gu.load(gu.trace_names()[0])
+    dist = orc.edt(np.asarray(G['map_data']) >= 0.1)
+    H, W = dist.shape
+    rng = np.random.RandomState(0)
+    ys, xs = np.where(dist > 4)
+    pick = rng.randint(len(xs), size=3000000)
+    ins = np.column_stack([xs[pick], ys[pick], rng.uniform(-np.pi, np.pi, len(pick))]).astype(np.float32)
+    a = orc.calc_range_many(dist, ins, float(W * H))
+    b = np.empty(len(ins), np.float32)
+    alt.nvo_calc_range_many(dist.ctypes.data_as(C.c_void_p), W, H, ins.ctypes.data_as(C.c_void_p),
+                            b.ctypes.data_as(C.c_void_p), len(ins), C.c_float(W * H), C.c_float(W * H), None, None)
+    diff = a != b
+    # (the two roundings differ in 16 % of the sample positions but pick another CELL only ~1e-5 of
+    # the time, and a ray's range changes more rarely still)
+    assert 0 < diff.sum() and diff.mean() < 1e-3, diff.sum()
