@@ -15,6 +15,7 @@
 #ifndef NAVGYM_B200_H
 #define NAVGYM_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -367,6 +368,44 @@ int navgym_sizeof_plan_map(void);
  * b2 [32]: float32 device pointers in torch's layout. */
 int navgym_policy_features(const float *scan, int n, const float *w1, const float *b1,
                            const float *w2, const float *b2, float *features, void *stream);
+
+/* ---- the whole pedestrian policy, natively: HumanPolicy's deterministic action mean
+ * (human_policy.py:38-55, the only output env.py:649-656 uses) for n pedestrians,
+ *   mean = (sigmoid(actor1(a)), tanh(actor2(a))),  a = relu(act_fc2([relu(act_fc1(feat)), goal, speed])),
+ *   feat = the convolutional front end of navgym_policy_features on the pedestrian's newest scan
+ *          (env.py:647 feeds it to all three input frames; the fold is done here from the
+ *          reference-shaped act_fea_cv1 weight).
+ * Three launches, no library GEMM: the front end (features leave as two f16 halves), act_fc1 on
+ * the tcgen05 tensor cores with TMA-fed operands and TMEM accumulators in the "f16x3" scheme
+ * (hi/lo f16 splits of both operands, three MMAs per K step: float32-grade results), act_fc2 and
+ * the heads on the CUDA cores.  Parameters are float32 device pointers in torch's state_dict
+ * layout; they are copied / pre-split into the caller's workspace by navgym_policy_create, so
+ * changing the weights means creating a new policy.  workspace: device memory, 1024-byte
+ * aligned, navgym_policy_workspace_bytes(max_n) bytes (the feature halves dominate: 16 KB per
+ * pedestrian), owned by the caller and kept alive for the policy's lifetime. */
+typedef struct {
+    int32_t max_n, _pad;
+    const float *cv1_w, *cv1_b;   /* act_fea_cv1: [32][3][5], [32] */
+    const float *cv2_w, *cv2_b;   /* act_fea_cv2: [32][32][3], [32] */
+    const float *fc1_w, *fc1_b;   /* act_fc1: [256][4096], [256] */
+    const float *fc2_w, *fc2_b;   /* act_fc2: [128][260], [128] */
+    const float *a1_w, *a1_b;     /* actor1: [128], [1] */
+    const float *a2_w, *a2_b;     /* actor2: [128], [1] */
+    void *workspace;
+    uint64_t workspace_bytes;
+} navgym_policy_params_t;
+typedef struct navgym_policy navgym_policy_t;
+size_t navgym_policy_workspace_bytes(int max_n);
+int navgym_sizeof_policy_params(void);
+navgym_policy_t *navgym_policy_create(const navgym_policy_params_t *params, void *stream); /* NULL on failure */
+void navgym_policy_destroy(navgym_policy_t *policy);
+/* scan f32 [n][512] metres (clipped to [0, 6] and centred inside, env.py:627-629), goal f32
+ * [n][2] (env.py:641-645), speed f32 [n][2] (the previous clipped mean) -> mean f32 [n][2]. */
+int navgym_policy_mean(navgym_policy_t *policy, const float *scan, const float *goal,
+                       const float *speed, int n, float *mean, void *stream);
+/* byte offsets inside the workspace of {features hi, features lo, act_fc1 output, scales, total}
+ * (tests compare the intermediate results against a float32 reference) */
+void navgym_policy_workspace_layout(int max_n, uint64_t *out5);
 
 /* ---- inner native boundary: range_libc --------------------------------------------- */
 /* PyOMap(bool[H,W]) + PyRayMarching(omap, max_range) (env.py:337-340): exact Euclidean

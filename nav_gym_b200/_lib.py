@@ -169,6 +169,13 @@ class PedsArgs(C.Structure):
                 ('peds', _P), ('nped', _P), ('discs', _P), ('ndisc', _P), ('segs', _P), ('nseg', _P)]
 
 
+class PolicyParams(C.Structure):
+    _fields_ = [('max_n', C.c_int32), ('_pad', C.c_int32),
+                ('cv1_w', _P), ('cv1_b', _P), ('cv2_w', _P), ('cv2_b', _P), ('fc1_w', _P), ('fc1_b', _P),
+                ('fc2_w', _P), ('fc2_b', _P), ('a1_w', _P), ('a1_b', _P), ('a2_w', _P), ('a2_b', _P),
+                ('workspace', _P), ('workspace_bytes', C.c_uint64)]
+
+
 EXPORTS = [
     'navgym_step_batch', 'navgym_reset_obs_batch', 'navgym_host_pipe_create', 'navgym_host_pipe_destroy',
     'navgym_step_batch_host', 'navgym_step_batch_host_submit', 'navgym_step_batch_host_wait', 'navgym_edt_build', 'navgym_calc_range_many',
@@ -183,6 +190,8 @@ EXPORTS = [
     'navgym_peds_move', 'navgym_sizeof_move_args', 'navgym_policy_features',
     'navgym_host_pipe_groups', 'navgym_host_pipe_group_bounds', 'navgym_host_rollout',
     'navgym_policy_action_bank', 'navgym_export_env', 'navgym_export_env_len', 'navgym_march_is_fused',
+    'navgym_policy_workspace_bytes', 'navgym_sizeof_policy_params', 'navgym_policy_create',
+    'navgym_policy_destroy', 'navgym_policy_mean', 'navgym_policy_workspace_layout',
 ]
 
 _lib = None
@@ -240,13 +249,23 @@ def load():
     lib.navgym_peds_plan.argtypes = [C.POINTER(PlanArgs), _P]
     lib.navgym_peds_move.argtypes = [C.POINTER(MoveArgs), _P]
     lib.navgym_policy_features.argtypes = [_P, C.c_int, _P, _P, _P, _P, _P, _P]
+    lib.navgym_policy_workspace_bytes.restype = C.c_size_t
+    lib.navgym_policy_workspace_bytes.argtypes = [C.c_int]
+    lib.navgym_policy_create.restype = _P
+    lib.navgym_policy_create.argtypes = [C.POINTER(PolicyParams), _P]
+    lib.navgym_policy_destroy.restype = None
+    lib.navgym_policy_destroy.argtypes = [_P]
+    lib.navgym_policy_mean.argtypes = [_P, _P, _P, _P, C.c_int, _P, _P]
+    lib.navgym_policy_workspace_layout.restype = None
+    lib.navgym_policy_workspace_layout.argtypes = [C.c_int, C.POINTER(C.c_uint64)]
     if (lib.navgym_sizeof_step_args() != C.sizeof(StepArgs) or lib.navgym_sizeof_map() != C.sizeof(MapT)
             or lib.navgym_sizeof_her_args() != C.sizeof(HerArgs)
             or lib.navgym_sizeof_peds_args() != C.sizeof(PedsArgs)
             or lib.navgym_sizeof_scan_args() != C.sizeof(ScanArgs)
             or lib.navgym_sizeof_plan_args() != C.sizeof(PlanArgs)
             or lib.navgym_sizeof_plan_map() != C.sizeof(PlanMapT)
-            or lib.navgym_sizeof_move_args() != C.sizeof(MoveArgs)):
+            or lib.navgym_sizeof_move_args() != C.sizeof(MoveArgs)
+            or lib.navgym_sizeof_policy_params() != C.sizeof(PolicyParams)):
         raise RuntimeError('libnavgym_b200.so ABI mismatch with nav_gym_b200/_lib.py (rebuild)')
     _lib = lib
     return lib

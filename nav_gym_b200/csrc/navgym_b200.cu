@@ -26,6 +26,7 @@
 //   host_pipe.inl           host-buffer entry points (chunked / asynchronous, CUDA-graph replay)
 // and this file holds the C ABI (include/navgym_b200.h) around them.
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <math_constants.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -46,6 +47,7 @@ static unsigned long long g_launches = 0;
 #include "her_kernel.cuh"
 #include "pedestrian_kernels.cuh"
 #include "native_kernels.cuh"
+#include "policy_gemm.cuh"
 
 // ------------------------------------------------------------------ C ABI
 // Launch shape of the fused kernel: warps per environment (WPE) and march slots per lane.
@@ -158,7 +160,7 @@ int navgym_compute_rewards(const navgym_her_args_t *args, void *stream)
 int navgym_peds_advance(const navgym_peds_args_t *args, void *stream)
 {
     if (args->num_envs <= 0) return 0;
-    peds_advance_kernel<<<(args->num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*args);
+    peds_advance_kernel<<<(args->num_envs + 3) / 4, 128, 0, (cudaStream_t)stream>>>(*args);  // a warp per environment
     g_launches++;
     return (int)cudaGetLastError();
 }
@@ -177,9 +179,81 @@ int navgym_policy_features(const float *scan, int n, const float *w1, const floa
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = n < 4 * sms ? n : 4 * sms;  // 4 CTAs of 48 KB shared memory per SM
-    policy_features_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(scan, n, w1, b1, w2, b2, features);
+    policy_features_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(scan, n, w1, b1, w2, b2, features, nullptr, nullptr, nullptr);
     g_launches++;
     return (int)cudaGetLastError();
+}
+
+// ---- the pedestrian policy as one native pipeline (include/navgym_b200.h, navgym_policy_*)
+size_t navgym_policy_workspace_bytes(int max_n) { return policy_ws_layout(max_n).total; }
+int navgym_sizeof_policy_params(void) { return (int)sizeof(navgym_policy_params_t); }
+
+navgym_policy_t *navgym_policy_create(const navgym_policy_params_t *p, void *stream)
+{
+    if (!p || p->max_n <= 0 || !p->workspace || !p->cv1_w || !p->cv1_b || !p->cv2_w || !p->cv2_b || !p->fc1_w ||
+        !p->fc1_b || !p->fc2_w || !p->fc2_b || !p->a1_w || !p->a1_b || !p->a2_w || !p->a2_b)
+        return nullptr;
+    const policy_ws_t L = policy_ws_layout(p->max_n);
+    if (p->workspace_bytes < L.total || ((uintptr_t)p->workspace & 1023)) return nullptr;
+    navgym_policy_t *pol = new navgym_policy_t();
+    pol->max_n = p->max_n;
+    pol->ws = (uint8_t *)p->workspace;
+    pol->L = L;
+    pol->sms = 148;
+    cudaGetDevice(&pol->device);
+    cudaDeviceGetAttribute(&pol->sms, cudaDevAttrMultiProcessorCount, pol->device);
+    const uint64_t np = ((uint64_t)p->max_n + 127) / 128 * 128;
+    cudaStream_t st = (cudaStream_t)stream;
+    bool ok = cudaMemsetAsync(pol->ws + L.fh, 0, (size_t)np * 4096 * 2, st) == cudaSuccess &&
+              cudaMemsetAsync(pol->ws + L.fl, 0, (size_t)np * 4096 * 2, st) == cudaSuccess;
+    ok = ok && policy_make_map(&pol->tm_fh, pol->ws + L.fh, np, pg::BM) == 0 &&
+         policy_make_map(&pol->tm_fl, pol->ws + L.fl, np, pg::BM) == 0 &&
+         policy_make_map(&pol->tm_wh, pol->ws + L.wh, 256, pg::BN) == 0 &&
+         policy_make_map(&pol->tm_wl, pol->ws + L.wl, 256, pg::BN) == 0;
+    ok = ok && cudaFuncSetAttribute(fc1_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pg::SMEM_BYTES) == cudaSuccess &&
+         cudaFuncSetAttribute(fc2_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (PF2_IN * 128 + 64 * PF2_ROW) * (int)sizeof(float)) == cudaSuccess;
+    if (ok) {
+        policy_prepare_kernel<<<1, 1024, 0, st>>>(*p, pol->ws, L);
+        g_launches++;
+        ok = cudaGetLastError() == cudaSuccess;
+    }
+    if (!ok) { delete pol; return nullptr; }
+    return pol;
+}
+
+void navgym_policy_destroy(navgym_policy_t *pol) { delete pol; }
+
+int navgym_policy_mean(navgym_policy_t *pol, const float *scan, const float *goal, const float *speed, int n,
+                       float *mean, void *stream)
+{
+    if (!pol) return (int)cudaErrorInvalidValue;
+    if (n <= 0) return 0;
+    if (n > pol->max_n || !scan || !goal || !speed || !mean) return (int)cudaErrorInvalidValue;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t *ws = pol->ws;
+    const policy_ws_t &L = pol->L;
+    const float *scales = (const float *)(ws + L.scales);
+    const int grid1 = n < 4 * pol->sms ? n : 4 * pol->sms;
+    policy_features_kernel<true><<<grid1, 128, 0, st>>>(scan, n, (const float *)(ws + L.w1f), (const float *)(ws + L.b1),
+                                                        (const float *)(ws + L.w2), (const float *)(ws + L.b2), nullptr,
+                                                        (__half *)(ws + L.fh), (__half *)(ws + L.fl), scales);
+    const int tiles = (n + pg::BM - 1) / pg::BM;
+    fc1_umma_kernel<<<tiles < pol->sms ? tiles : pol->sms, pg::THREADS, pg::SMEM_BYTES, st>>>(
+        pol->tm_fh, pol->tm_fl, pol->tm_wh, pol->tm_wl, (const float *)(ws + L.fc1_b), scales, (float *)(ws + L.h), n, tiles);
+    const int tiles2 = (n + 63) / 64;
+    fc2_heads_kernel<<<tiles2 < pol->sms ? tiles2 : pol->sms, 256, (PF2_IN * 128 + 64 * PF2_ROW) * sizeof(float), st>>>(
+        (const float *)(ws + L.h), goal, speed, n, (const float *)(ws + L.w2t), (const float *)(ws + L.fc2_b),
+        (const float *)(ws + L.heads), mean);
+    g_launches += 3;
+    return (int)cudaGetLastError();
+}
+
+/* test hook: byte offsets of the intermediate buffers inside the workspace */
+void navgym_policy_workspace_layout(int max_n, uint64_t *out /* [5]: fh, fl, h, scales, total */)
+{
+    const policy_ws_t L = policy_ws_layout(max_n);
+    out[0] = L.fh; out[1] = L.fl; out[2] = L.h; out[3] = L.scales; out[4] = L.total;
 }
 
 int navgym_peds_move(const navgym_move_args_t *args, void *stream)

@@ -320,10 +320,14 @@ __global__ void peds_move_kernel(const navgym_move_args_t a)
 // three loads and the warp's 24 weights as six broadcast LDS.128 -- 9 shared-memory loads per
 // 96 FMA, where one position per thread needed 25.
 #define PF_H1 264  // row pitch of h1 (32-byte multiple): [0] = left pad, [1 + q] = conv1 output q (q < 255), [256] = right pad
+// SPLIT: the features leave as two f16 arrays, hi = half(s f), lo = half(s f - hi), the operand
+// format of fc1_umma_kernel (policy_gemm.cuh); s = scales[0], a power of two.
+template <bool SPLIT>
 __global__ void __launch_bounds__(128) policy_features_kernel(const float *__restrict__ scan, int n,
                                                               const float *__restrict__ w1, const float *__restrict__ b1,
                                                               const float *__restrict__ w2, const float *__restrict__ b2,
-                                                              float *__restrict__ out)
+                                                              float *__restrict__ out, __half *__restrict__ out_hi,
+                                                              __half *__restrict__ out_lo, const float *__restrict__ scales)
 {
     __shared__ __align__(16) float w2s[32 * 3 * 32];  // [ci][tap][co]
     __shared__ __align__(16) float h1[32 * PF_H1];
@@ -382,11 +386,28 @@ __global__ void __launch_bounds__(128) policy_features_kernel(const float *__res
                     for (int j = 0; j < 4; j++) acc[c][j] = fmaf(in[2 * j + k], wv[c], acc[c][j]);
             }
         }
-        float *o = out + (size_t)ped * 4096 + p0;
+        if (SPLIT) {
+            const float sc = scales[0];
+            const size_t o = (size_t)ped * 4096 + p0;
 #pragma unroll
-        for (int c = 0; c < 8; c++)
-            *reinterpret_cast<float4 *>(o + (wco + c) * 128) =
-                make_float4(fmaxf(acc[c][0], 0.0f), fmaxf(acc[c][1], 0.0f), fmaxf(acc[c][2], 0.0f), fmaxf(acc[c][3], 0.0f));
+            for (int c = 0; c < 8; c++) {
+                __half hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float v = fmaxf(acc[c][j], 0.0f) * sc;
+                    hi[j] = __float2half_rn(v);
+                    lo[j] = __float2half_rn(v - __half2float(hi[j]));
+                }
+                *reinterpret_cast<uint2 *>(out_hi + o + (wco + c) * 128) = *reinterpret_cast<const uint2 *>(hi);
+                *reinterpret_cast<uint2 *>(out_lo + o + (wco + c) * 128) = *reinterpret_cast<const uint2 *>(lo);
+            }
+        } else {
+            float *o = out + (size_t)ped * 4096 + p0;
+#pragma unroll
+            for (int c = 0; c < 8; c++)
+                *reinterpret_cast<float4 *>(o + (wco + c) * 128) =
+                    make_float4(fmaxf(acc[c][0], 0.0f), fmaxf(acc[c][1], 0.0f), fmaxf(acc[c][2], 0.0f), fmaxf(acc[c][3], 0.0f));
+        }
     }
 }
 
@@ -398,22 +419,27 @@ __global__ void __launch_bounds__(128) policy_features_kernel(const float *__res
 // advances as in _update_dist_travelled (env.py:237-255).  Emits what the robot's lidar sees:
 // two leg discs (pymap2d CSimAgent "legs") for legged pedestrians, the 0.44 x 0.38 m box
 // footprint (human.py:5-10) as four segments otherwise (env.py:398-414), or one trunk disc
-// per pedestrian in trunk mode.  One thread per environment.
-__global__ void peds_advance_kernel(const navgym_peds_args_t a)
+// per pedestrian in trunk mode.  One warp per environment, one lane per pedestrian (the
+// trigonometry of all pedestrians of an environment runs side by side; a thread per environment
+// walked them one after the other); the slots of the disc / segment lists are handed out in
+// pedestrian order by a warp prefix sum, so the lists are those of the sequential loop.
+__global__ void __launch_bounds__(128) peds_advance_kernel(const navgym_peds_args_t a)
 {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (e >= a.num_envs) return;
     const int P = a.nped ? min(a.nped[e], a.max_ped) : a.max_ped;
     float *pp = a.peds + (size_t)e * a.max_ped * NAVGYM_PED_F;
     float *discs = a.discs + (size_t)e * a.max_disc * 3;
     float *segs = a.segs ? a.segs + (size_t)e * a.max_seg * 4 : nullptr;
-    int nd = 0, ns = 0;
-    for (int p = 0; p < P; p++) {
-        float *q = pp + p * NAVGYM_PED_F;
+    int nd = 0, ns = 0;   // warp-uniform running totals
+    for (int p0 = 0; p0 < P; p0 += 32) {
+        const int p = p0 + lane;
+        const bool live = p < P;
+        float *q = pp + (live ? p : 0) * NAVGYM_PED_F;
         float x = q[0], y = q[1], th = q[2];
-        const float v = q[3];
-        float tgt = q[8];
-        if (a.advance) {
+        if (live && a.advance) {
+            const float v = q[3];
+            float tgt = q[8];
             float gx = tgt > 0.5f ? q[6] : q[4], gy = tgt > 0.5f ? q[7] : q[5];
             if ((gx - x) * (gx - x) + (gy - y) * (gy - y) < 0.25f) {  // reached: turn back
                 tgt = 1.0f - tgt;
@@ -435,31 +461,45 @@ __global__ void peds_advance_kernel(const navgym_peds_args_t a)
             th = thn - 6.2831853f * floorf(thn * 0.15915494f);
             q[0] = x; q[1] = y; q[2] = th; q[8] = tgt;
         }
+        // what this pedestrian contributes: 1 trunk disc | 2 leg discs | 4 box segments
+        const bool legs = q[12] > 0.5f;
+        const int want_d = !live ? 0 : (a.trunk_mode ? 1 : (legs ? 2 : 0));
+        const int want_s = (!live || a.trunk_mode || legs || !segs) ? 0 : 4;
+        int pre_d = want_d, pre_s = want_s;   // inclusive warp prefix sums
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int ud = __shfl_up_sync(0xffffffffu, pre_d, o), us = __shfl_up_sync(0xffffffffu, pre_s, o);
+            if (lane >= o) { pre_d += ud; pre_s += us; }
+        }
+        const int at_d = nd + pre_d - want_d, at_s = ns + pre_s - want_s;
+        // items of one kind have one size, so "fits after everything before it" is the
+        // sequential loop's "fits at the running count"
+        const bool put_d = want_d && at_d + want_d <= a.max_disc, put_s = want_s && at_s + want_s <= a.max_seg;
         const float c = cosf(th), s_ = sinf(th);
-        if (a.trunk_mode) {
-            if (nd < a.max_disc) { discs[3 * nd] = x; discs[3 * nd + 1] = y; discs[3 * nd + 2] = q[13]; nd++; }
-        } else if (q[12] > 0.5f) {  // legs
+        if (put_d && a.trunk_mode) {
+            discs[3 * at_d] = x; discs[3 * at_d + 1] = y; discs[3 * at_d + 2] = q[13];
+        } else if (put_d) {  // legs
             const float front = 0.3f * cosf(q[9] * (2.0f / 0.3f) + q[11]);
             const float side = 0.1f * cosf(q[10] * (2.0f / 0.1f) + q[11]) + 0.1f;
-            if (nd + 1 < a.max_disc) {
-                discs[3 * nd] = x + c * front - s_ * side; discs[3 * nd + 1] = y + s_ * front + c * side;
-                discs[3 * nd + 2] = 0.03f; nd++;
-                discs[3 * nd] = x - c * front + s_ * side; discs[3 * nd + 1] = y - s_ * front - c * side;
-                discs[3 * nd + 2] = 0.03f; nd++;
-            }
-        } else if (segs && ns + 3 < a.max_seg) {  // box footprint, closed
+            discs[3 * at_d] = x + c * front - s_ * side; discs[3 * at_d + 1] = y + s_ * front + c * side;
+            discs[3 * at_d + 2] = 0.03f;
+            discs[3 * at_d + 3] = x - c * front + s_ * side; discs[3 * at_d + 4] = y - s_ * front - c * side;
+            discs[3 * at_d + 5] = 0.03f;
+        }
+        if (put_s) {  // box footprint, closed
             const float fx[4] = {0.22f, -0.22f, -0.22f, 0.22f}, fy[4] = {0.19f, 0.19f, -0.19f, -0.19f};
             float wx[4], wy[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) { wx[i] = c * fx[i] - s_ * fy[i] + x; wy[i] = s_ * fx[i] + c * fy[i] + y; }
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                float *sg = segs + 4 * (ns + i);
-                sg[0] = wx[i]; sg[1] = wy[i]; sg[2] = wx[(i + 1) & 3]; sg[3] = wy[(i + 1) & 3];
-            }
-            ns += 4;
+            for (int i = 0; i < 4; i++)
+                *reinterpret_cast<float4 *>(segs + 4 * (at_s + i)) = make_float4(wx[i], wy[i], wx[(i + 1) & 3], wy[(i + 1) & 3]);
         }
+        nd += __popc(__ballot_sync(0xffffffffu, put_d)) * (a.trunk_mode ? 1 : 2);
+        ns += __popc(__ballot_sync(0xffffffffu, put_s)) * 4;
     }
-    a.ndisc[e] = nd;
-    if (a.nseg) a.nseg[e] = ns;
+    if (lane == 0) {
+        a.ndisc[e] = nd;
+        if (a.nseg) a.nseg[e] = ns;
+    }
 }

@@ -11,8 +11,10 @@ over [num_envs, max_ped] on the GPU:
                            them with load_state_dict when available, else random-init)
   PedestrianSim            device state + the per-step sequence of env.py:617-693
 
-PyTorch carries the dense policy forward and the elementwise bookkeeping; raycasts are the
-library's CUDA kernels.  Nothing here touches the CPU oracle.
+Everything on the per-step path is a kernel of the library, the policy forward included
+(NativePolicy: tcgen05 tensor cores for the one dense layer that matters); torch owns the device
+memory and, in the comparison modes only, runs the dense layers.  Nothing here touches the CPU
+oracle.
 """
 import ctypes as C
 
@@ -101,6 +103,69 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
+class NativePolicy(object):
+    """HumanPolicy.mean (human_policy.py:38-55) through the library's own kernels
+    (navgym_policy_create / navgym_policy_mean): convolutional front end -> act_fc1 on the
+    tcgen05 tensor cores (f16x3 operand split, float32-grade) -> act_fc2 + heads.  No torch op
+    and no library GEMM runs in `mean`; torch only owns the workspace memory.  The weights are
+    copied (pre-split) at construction: build a new NativePolicy after changing them."""
+
+    def __init__(self, policy, max_n, device):
+        self.lib = _lib.load()
+        self.device, self.max_n = torch.device(device), int(max_n)
+        nbytes = int(self.lib.navgym_policy_workspace_bytes(self.max_n))
+        self.workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
+        off = (-self.workspace.data_ptr()) % 1024
+        self._ws = self.workspace[off:off + nbytes]
+        f = lambda t: t.detach().to(self.device, torch.float32).contiguous()
+        self._w = [f(t) for t in (policy.act_fea_cv1.weight, policy.act_fea_cv1.bias, policy.act_fea_cv2.weight,
+                                  policy.act_fea_cv2.bias, policy.act_fc1.weight, policy.act_fc1.bias,
+                                  policy.act_fc2.weight, policy.act_fc2.bias, policy.actor1.weight, policy.actor1.bias,
+                                  policy.actor2.weight, policy.actor2.bias)]
+        assert tuple(self._w[0].shape) == (32, 3, 5) and tuple(self._w[4].shape) == (256, 4096)
+        p = _lib.PolicyParams()
+        p.max_n = self.max_n
+        for name, t in zip(('cv1_w', 'cv1_b', 'cv2_w', 'cv2_b', 'fc1_w', 'fc1_b', 'fc2_w', 'fc2_b',
+                            'a1_w', 'a1_b', 'a2_w', 'a2_b'), self._w):
+            setattr(p, name, _ptr(t))
+        p.workspace, p.workspace_bytes = _ptr(self._ws), nbytes
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            self.handle = self.lib.navgym_policy_create(C.byref(p), C.c_void_p(stream))
+        if not self.handle:
+            raise RuntimeError('navgym_policy_create failed (needs an sm_100a device and a driver with TMA support)')
+
+    def mean(self, scan, goal, speed, out=None):
+        """scan f32 [n, 512] raw metres, goal / speed f32 [n, 2] -> mean f32 [n, 2] (into `out`)."""
+        n = int(scan.shape[0])
+        for t in (scan, goal, speed):
+            assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda
+        if out is None:
+            out = torch.empty(n, 2, dtype=torch.float32, device=self.device)
+        assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == 2 * n
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(self.lib.navgym_policy_mean(self.handle, _ptr(scan), _ptr(goal), _ptr(speed), n, _ptr(out),
+                                                   C.c_void_p(stream)), 'policy_mean')
+        return out
+
+    def intermediates(self, n):
+        """(features hi, features lo) f16 [n, 4096], act_fc1 output f32 [n, 256], scales f32 [2]:
+        views of the workspace (tests)."""
+        L = (C.c_uint64 * 5)()
+        self.lib.navgym_policy_workspace_layout(self.max_n, L)
+        w = self._ws
+        fh = w[L[0]:L[0] + n * 8192].view(torch.float16).reshape(n, 4096)
+        fl = w[L[1]:L[1] + n * 8192].view(torch.float16).reshape(n, 4096)
+        h = w[L[2]:L[2] + n * 1024].view(torch.float32).reshape(n, 256)
+        return fh, fl, h, w[L[3]:L[3] + 8].view(torch.float32)
+
+    def __del__(self):
+        h, self.handle = getattr(self, 'handle', None), None
+        if h:
+            self.lib.navgym_policy_destroy(h)
+
+
 class AgentScanner(object):
     """navgym_agent_scan_batch bound to one MapPool: scans of [num_envs, agents_per_env] agents
     with the pedestrian lidar (human.py:11-16) against the map and the other agents' closed
@@ -154,10 +219,12 @@ class PedestrianSim(object):
     (the clipped policy mean, the policy's `speed` input), scan f32 [.., 512], goal_id i32,
     waypoint f64, goal_local f32.
 
-    precision of the dense layers: 'fp32' (default; the policy mean matches the reference's CPU
-    forward to ~1e-5), 'tf32x3' (the 4096 x 256 layer as three TF32 tensor-core products of the
-    operands' high and low halves: float32-grade results, same tolerance), 'tf32' or 'bf16'
-    (means move by ~1e-3, the pedestrians' paths are not comparable step by step any more).
+    precision: 'f16x3' (default) runs the whole policy through the library's own kernels
+    (NativePolicy: act_fc1 on the tcgen05 tensor cores with hi/lo f16 operand splits, float32-grade:
+    the mean matches the reference's CPU forward to ~1e-5).  The other modes keep the dense layers
+    in torch / cuBLAS for comparison: 'fp32', 'tf32x3' (three TF32 products of the operands' high
+    and low halves, same tolerance), 'tf32' or 'bf16' (means move by ~1e-3, the pedestrians' paths
+    are not comparable step by step any more).
 
     Auto-reset: every act() also draws the pedestrians of each environment's NEXT episode (at
     least 4 m from where the robot's auto-reset will put it -- the same Philox draw the step
@@ -168,9 +235,9 @@ class PedestrianSim(object):
 
     def __init__(self, env, max_ped, nped=None, policy=None, v_pref_range=(0.0, 0.6), has_legs_ratio=0.5,
                  num_goals=32, min_goal_dist=10.0, min_robot_dist=4.0, seed=0, fold_frames=True,
-                 precision='fp32'):
+                 precision='f16x3'):
         from . import maps as M
-        assert precision in ('fp32', 'tf32x3', 'tf32', 'bf16')
+        assert precision in ('f16x3', 'fp32', 'tf32x3', 'tf32', 'bf16')
         self.env, self.device = env, env.device
         self.B, self.P = env.B, int(max_ped)
         if self.P > 127:  # navgym_agent_scan_batch, crowd mode: one thread per other agent
@@ -185,6 +252,7 @@ class PedestrianSim(object):
             policy = HumanPolicy()
         self.policy = policy.to(dev).eval()
         self.fold_frames = bool(fold_frames)
+        self.native = NativePolicy(self.policy, self.B * self.P, dev) if precision == 'f16x3' else None
         # ---- planning fields + free-cell pools per map (kept on the MapPool: a pool that is
         # reused for another episode / another sim does not rebuild them)
         cache = getattr(env.pool, '_plan_cache', None)
@@ -328,12 +396,17 @@ class PedestrianSim(object):
         if respawn is not None:
             self._scan(respawn)  # first scans of the respawned pedestrians (env.py:808-815)
         goal, speed = self.goal_local.reshape(-1, 2), self.prev_action.reshape(-1, 2)
-        self._mean.copy_(self._policy_mean(self.scan.reshape(self.B * self.P, -1), goal, speed).reshape(self.B, self.P, 2))
+        if self.native is not None:   # three launches of the library, straight into the move kernel's input
+            self.native.mean(self.scan.reshape(self.B * self.P, -1), goal, speed, out=self._mean)
+        else:
+            self._mean.copy_(self._policy_mean(self.scan.reshape(self.B * self.P, -1), goal, speed).reshape(self.B, self.P, 2))
         self._call(self.lib.navgym_peds_move, self.move_args, 'peds_move')
         env._peds_emit(advance=False)
 
     def _policy_mean(self, x, goal, speed):
         """x: the raw scans [N, 512] in metres."""
+        if self.native is not None:
+            return self.native.mean(x.contiguous(), goal.contiguous(), speed.contiguous())
         if self.precision == 'bf16':
             with torch.autocast('cuda', dtype=torch.bfloat16):
                 return self._mean_fp(x, goal, speed).float()

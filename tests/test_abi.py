@@ -81,6 +81,7 @@ _MIRRORS = {
     'navgym_map_t': 'MapT', 'navgym_step_args_t': 'StepArgs', 'navgym_her_args_t': 'HerArgs',
     'navgym_peds_args_t': 'PedsArgs', 'navgym_scan_args_t': 'ScanArgs', 'navgym_plan_map_t': 'PlanMapT',
     'navgym_plan_args_t': 'PlanArgs', 'navgym_move_args_t': 'MoveArgs', 'navgym_action_bank_t': 'ActionBank',
+    'navgym_policy_params_t': 'PolicyParams',
 }
 
 

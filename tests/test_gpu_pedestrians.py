@@ -112,6 +112,77 @@ def test_policy_features_kernel_and_folded_forward(name):
     assert np.allclose(m.cpu().numpy().reshape(T, P, 2), G['mean'], rtol=0, atol=2e-5)
 
 
+def _f32_reference(fn):
+    """Run fn with TF32 off everywhere (cuDNN / cuBLAS would round operands to TF32)."""
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            return fn()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.mark.parametrize('n', [1, 77, 128, 300, 1029])
+def test_native_policy_stage_by_stage(n):
+    """navgym_policy_mean (front end -> tcgen05 act_fc1 in the f16x3 scheme -> act_fc2 + heads)
+    against torch float32 / float64 on random scans, one stage at a time: the feature halves
+    re-assemble the float32 features, the tensor-core layer equals a float64 product of those
+    very features to float32 rounding, the means equal torch's float32 forward.  n covers a
+    single row, partial 128-row tiles and several tiles per CTA."""
+    import torch.nn.functional as F
+    from nav_gym_b200.pedestrians import HumanPolicy, NativePolicy, preprocess_scan
+    torch.manual_seed(7)
+    pol = HumanPolicy().cuda()
+    with torch.no_grad():   # default-init biases are small; make every term count
+        pol.act_fc1.bias.uniform_(-0.3, 0.3)
+        pol.act_fea_cv2.bias.uniform_(-0.2, 0.2)
+    g = torch.Generator(device='cuda').manual_seed(n)
+    scan = (8.0 * torch.rand(n, 512, device='cuda', generator=g) - 1.0).contiguous()   # beyond [0, 6] on both sides
+    goal = 4.0 * torch.rand(n, 2, device='cuda', generator=g) - 2.0
+    speed = torch.rand(n, 2, device='cuda', generator=g)
+    nat = NativePolicy(pol, max(n, 5), 'cuda:0')
+    got = nat.mean(scan, goal, speed)
+    torch.cuda.synchronize()
+    fh, fl, h, scales = nat.intermediates(n)
+    x3 = preprocess_scan(scan)[:, None, :].expand(-1, 3, -1).contiguous()
+    feat = _f32_reference(lambda: F.relu(pol.act_fea_cv2(F.relu(pol.act_fea_cv1(x3)))).reshape(n, -1))
+    s_f = float(scales[0])
+    assert s_f > 0 and np.log2(s_f) == int(np.log2(s_f)) and float(fh.float().abs().max()) < 32768.0
+    mine = (fh.double() + fl.double()) / s_f
+    assert float((mine - feat.double()).abs().max()) < 2e-6
+    assert float(((fh.double() + fl.double()) / s_f - mine).abs().max()) == 0.0
+    # the tensor-core layer on the features the kernel itself produced
+    # (12 288 products per output accumulate in the tensor core's float32 adder: a few 1e-6, the
+    # size of a float32 GEMM's own rounding -- torch's SGEMM is checked against the same bar)
+    with torch.no_grad():
+        want_h = torch.relu(mine @ pol.act_fc1.weight.double().t() + pol.act_fc1.bias.double())
+        err = float((h.double() - want_h).abs().max())
+        sgemm = _f32_reference(lambda: torch.relu(mine.float() @ pol.act_fc1.weight.t() + pol.act_fc1.bias))
+        err_sgemm = float((sgemm.double() - want_h).abs().max())
+    bar = 1e-5 * max(1.0, float(want_h.abs().max()))
+    assert err < bar and err_sgemm < bar, (err, err_sgemm)
+    want = _f32_reference(lambda: pol.mean(x3, goal, speed))
+    assert float((got - want).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize('name', gu.human_trace_names())
+def test_native_policy_reproduces_the_reference_means(name):
+    """The reference's recorded policy outputs (humans_*.npz `mean`, minted by running its own
+    human_policy.py on the CPU) from its recorded raw scans, through the native pipeline."""
+    from nav_gym_b200.pedestrians import HumanPolicy, NativePolicy
+    G = gu.load(name)
+    torch.manual_seed(1234)
+    pol = HumanPolicy().cuda()
+    T, P = G['mean'].shape[:2]
+    raw = np.concatenate([G['scan0'][None], G['scan_out'][:-1]]).reshape(T * P, 512)
+    nat = NativePolicy(pol, T * P, 'cuda:0')
+    m = nat.mean(torch.from_numpy(raw).cuda().contiguous(), torch.from_numpy(G['goal_local']).cuda().reshape(-1, 2).contiguous(),
+                 torch.from_numpy(G['speed']).cuda().reshape(-1, 2).contiguous())
+    torch.cuda.synchronize()
+    assert np.allclose(m.cpu().numpy().reshape(T, P, 2), G['mean'], rtol=0, atol=2e-5)
+
+
 def _crowd(B=64, P=6, seed=0, **kw):
     from nav_gym_b200 import maps
     from nav_gym_b200.batched_env import BatchedNavGym, MapPool, filter_spawn_pool
@@ -125,7 +196,7 @@ def _crowd(B=64, P=6, seed=0, **kw):
     return m, env, PedestrianSim(env, P, seed=seed, **kw)
 
 
-@pytest.mark.parametrize('precision,tol', [('fp32', 1e-5), ('tf32x3', 1e-5), ('tf32', 5e-3), ('bf16', 2e-2)])
+@pytest.mark.parametrize('precision,tol', [('f16x3', 1e-5), ('fp32', 1e-5), ('tf32x3', 1e-5), ('tf32', 5e-3), ('bf16', 2e-2)])
 def test_policy_precisions(precision, tol):
     """PedestrianSim's policy forward in each precision mode against torch's float32 forward."""
     m, env, sim = _crowd(B=32, P=8, seed=3, precision=precision)

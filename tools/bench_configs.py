@@ -28,7 +28,7 @@ def crowd(dev, steps, warmup, B=4096, P=10):
     mp = MapPool([m], dev, spawn_pools=[pool])
     env = BatchedNavGym(B, mp, device=dev, seed=8, auto_reset=True)
     env.reset_from_spawn_pool(np.random.RandomState(4))
-    precision = os.environ.get('NAVGYM_CROWD_PRECISION', 'tf32')
+    precision = os.environ.get('NAVGYM_CROWD_PRECISION', 'f16x3')
     sim = PedestrianSim(env, P, seed=8, precision=precision)
     pol = random_policy(B, dev)
 
