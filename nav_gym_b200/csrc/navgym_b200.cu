@@ -179,7 +179,7 @@ int navgym_policy_features(const float *scan, int n, const float *w1, const floa
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = n < 4 * sms ? n : 4 * sms;  // 4 CTAs of 48 KB shared memory per SM
-    policy_features_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(scan, n, w1, b1, w2, b2, features, nullptr, nullptr, nullptr);
+    policy_features_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(scan, n, w1, b1, w2, b2, features);
     g_launches++;
     return (int)cudaGetLastError();
 }
@@ -211,6 +211,7 @@ navgym_policy_t *navgym_policy_create(const navgym_policy_params_t *p, void *str
          policy_make_map(&pol->tm_wh, pol->ws + L.wh, 256, pg::BN) == 0 &&
          policy_make_map(&pol->tm_wl, pol->ws + L.wl, 256, pg::BN) == 0;
     ok = ok && cudaFuncSetAttribute(fc1_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pg::SMEM_BYTES) == cudaSuccess &&
+         cudaFuncSetAttribute(policy_features_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pc::SMEM_BYTES) == cudaSuccess &&
          cudaFuncSetAttribute(fc2_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (PF2_IN * 128 + 64 * PF2_ROW) * (int)sizeof(float)) == cudaSuccess;
     if (ok) {
@@ -234,10 +235,9 @@ int navgym_policy_mean(navgym_policy_t *pol, const float *scan, const float *goa
     uint8_t *ws = pol->ws;
     const policy_ws_t &L = pol->L;
     const float *scales = (const float *)(ws + L.scales);
-    const int grid1 = n < 4 * pol->sms ? n : 4 * pol->sms;
-    policy_features_kernel<true><<<grid1, 128, 0, st>>>(scan, n, (const float *)(ws + L.w1f), (const float *)(ws + L.b1),
-                                                        (const float *)(ws + L.w2), (const float *)(ws + L.b2), nullptr,
-                                                        (__half *)(ws + L.fh), (__half *)(ws + L.fl), scales);
+    policy_features_umma_kernel<<<n < pol->sms ? n : pol->sms, pc::THREADS, pc::SMEM_BYTES, st>>>(
+        scan, n, (const uint4 *)(ws + L.conv_img), (const float *)(ws + L.w1s), (const float *)(ws + L.b2), scales,
+        (__half *)(ws + L.fh), (__half *)(ws + L.fl));
     const int tiles = (n + pg::BM - 1) / pg::BM;
     fc1_umma_kernel<<<tiles < pol->sms ? tiles : pol->sms, pg::THREADS, pg::SMEM_BYTES, st>>>(
         pol->tm_fh, pol->tm_fl, pol->tm_wh, pol->tm_wl, (const float *)(ws + L.fc1_b), scales, (float *)(ws + L.h), n, tiles);

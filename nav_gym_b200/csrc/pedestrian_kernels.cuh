@@ -320,14 +320,10 @@ __global__ void peds_move_kernel(const navgym_move_args_t a)
 // three loads and the warp's 24 weights as six broadcast LDS.128 -- 9 shared-memory loads per
 // 96 FMA, where one position per thread needed 25.
 #define PF_H1 264  // row pitch of h1 (32-byte multiple): [0] = left pad, [1 + q] = conv1 output q (q < 255), [256] = right pad
-// SPLIT: the features leave as two f16 arrays, hi = half(s f), lo = half(s f - hi), the operand
-// format of fc1_umma_kernel (policy_gemm.cuh); s = scales[0], a power of two.
-template <bool SPLIT>
 __global__ void __launch_bounds__(128) policy_features_kernel(const float *__restrict__ scan, int n,
                                                               const float *__restrict__ w1, const float *__restrict__ b1,
                                                               const float *__restrict__ w2, const float *__restrict__ b2,
-                                                              float *__restrict__ out, __half *__restrict__ out_hi,
-                                                              __half *__restrict__ out_lo, const float *__restrict__ scales)
+                                                              float *__restrict__ out)
 {
     __shared__ __align__(16) float w2s[32 * 3 * 32];  // [ci][tap][co]
     __shared__ __align__(16) float h1[32 * PF_H1];
@@ -386,28 +382,11 @@ __global__ void __launch_bounds__(128) policy_features_kernel(const float *__res
                     for (int j = 0; j < 4; j++) acc[c][j] = fmaf(in[2 * j + k], wv[c], acc[c][j]);
             }
         }
-        if (SPLIT) {
-            const float sc = scales[0];
-            const size_t o = (size_t)ped * 4096 + p0;
+        float *o = out + (size_t)ped * 4096 + p0;
 #pragma unroll
-            for (int c = 0; c < 8; c++) {
-                __half hi[4], lo[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const float v = fmaxf(acc[c][j], 0.0f) * sc;
-                    hi[j] = __float2half_rn(v);
-                    lo[j] = __float2half_rn(v - __half2float(hi[j]));
-                }
-                *reinterpret_cast<uint2 *>(out_hi + o + (wco + c) * 128) = *reinterpret_cast<const uint2 *>(hi);
-                *reinterpret_cast<uint2 *>(out_lo + o + (wco + c) * 128) = *reinterpret_cast<const uint2 *>(lo);
-            }
-        } else {
-            float *o = out + (size_t)ped * 4096 + p0;
-#pragma unroll
-            for (int c = 0; c < 8; c++)
-                *reinterpret_cast<float4 *>(o + (wco + c) * 128) =
-                    make_float4(fmaxf(acc[c][0], 0.0f), fmaxf(acc[c][1], 0.0f), fmaxf(acc[c][2], 0.0f), fmaxf(acc[c][3], 0.0f));
-        }
+        for (int c = 0; c < 8; c++)
+            *reinterpret_cast<float4 *>(o + (wco + c) * 128) =
+                make_float4(fmaxf(acc[c][0], 0.0f), fmaxf(acc[c][1], 0.0f), fmaxf(acc[c][2], 0.0f), fmaxf(acc[c][3], 0.0f));
     }
 }
 

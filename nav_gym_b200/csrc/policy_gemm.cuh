@@ -29,10 +29,18 @@
 #include <cuda_fp16.h>
 
 namespace pg {
-constexpr int BM = 128, BN = 256, BK = 64, UK = 16, KDIM = 4096, STAGES = 2;
-constexpr uint32_t A_BYTES = BM * BK * 2;                      // 16 KB: 128 rows x 128 B
-constexpr uint32_t B_BYTES = BN * BK * 2;                      // 32 KB
+#ifndef NAVGYM_FC1_BK
+#define NAVGYM_FC1_BK 32
+#endif
+// K block of a pipeline stage: 64 f16 = 128-byte rows (128-byte swizzle, 2 stages of 96 KB) or
+// 32 f16 = 64-byte rows (64-byte swizzle, 4 stages of 48 KB: the same bytes per MMA cycle, but
+// three stages in flight instead of one while a stage is being multiplied)
+constexpr int BM = 128, BN = 256, BK = NAVGYM_FC1_BK, UK = 16, KDIM = 4096;
+static_assert(BK == 64 || BK == 32, "K block = one swizzle row");
+constexpr uint32_t A_BYTES = BM * BK * 2;                      // 128 rows x (128 | 64) B
+constexpr uint32_t B_BYTES = BN * BK * 2;
 constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;    // Fh, Fl, Wh, Wl
+constexpr int STAGES = (192 * 1024) / STAGE_BYTES;
 constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 128 /* barriers */;
 constexpr int THREADS = 192;                                   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 constexpr uint32_t TMEM_COLS = 512;
@@ -86,6 +94,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr)
 {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// The same for 64-byte rows with the 64-byte swizzle: 8-row groups 512 B apart, layout type 4.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr)
+{
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+}
+__device__ __forceinline__ uint64_t umma_desc_fc1(uint32_t smem_addr)
+{
+    return BK == 64 ? umma_desc_sw128(smem_addr) : umma_desc_sw64(smem_addr);
 }
 // Instruction descriptor, kind::f16: D float32 (bits 4-5 = 1), A and B f16 (0), both K-major,
 // N >> 3 at bit 17, M >> 4 at bit 24.
@@ -166,8 +184,8 @@ fc1_umma_kernel(const __grid_constant__ CUtensorMap tm_fh, const __grid_constant
                     mbar_wait(full0 + 8 * s, ph);
                     tc_fence_after();
                     const uint32_t st = base + s * STAGE_BYTES;
-                    const uint64_t fh = umma_desc_sw128(st), fl = umma_desc_sw128(st + A_BYTES);
-                    const uint64_t wh = umma_desc_sw128(st + 2 * A_BYTES), wl = umma_desc_sw128(st + 2 * A_BYTES + B_BYTES);
+                    const uint64_t fh = umma_desc_fc1(st), fl = umma_desc_fc1(st + A_BYTES);
+                    const uint64_t wh = umma_desc_fc1(st + 2 * A_BYTES), wl = umma_desc_fc1(st + 2 * A_BYTES + B_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / UK; k++) {
                         const uint64_t adv = (uint64_t)((k * UK * 2) >> 4);   // 32 bytes along K inside the swizzle atom
@@ -216,13 +234,14 @@ fc1_umma_kernel(const __grid_constant__ CUtensorMap tm_fh, const __grid_constant
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
+        __syncwarp();
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
 // ------------------------------------------------------------------ fc2 + actor heads
-// 256 threads = 16 pedestrian groups (4 pedestrians each) x 16 output groups (8 of the 128 fc2
+// 256 threads = 16 pedestrian groups (4 pedestrians each) x 16 output groups (2 x 4 of the 128 fc2
 // outputs each): a 64-pedestrian tile per pass, the transposed fc2 weight (260 x 128) resident in
 // shared memory for the CTA's lifetime; the two heads are 16-lane shuffle reductions.
 #define PF2_IN 260
@@ -239,7 +258,10 @@ fc2_heads_kernel(const float *__restrict__ H, const float *__restrict__ goal, co
     for (int i = t; i < PF2_IN * 128 / 4; i += 256) reinterpret_cast<float4 *>(ws)[i] = reinterpret_cast<const float4 *>(w2t)[i];
     float bo[8], h1w[8], h2w[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) { bo[j] = b2[og * 8 + j]; h1w[j] = heads[og * 8 + j]; h2w[j] = heads[128 + og * 8 + j]; }
+    for (int j = 0; j < 8; j++) {   // this thread's outputs: 4 og .. 4 og + 3 and 64 + 4 og .. (conflict-free LDS.128)
+        const int o = (j >> 2) * 64 + og * 4 + (j & 3);
+        bo[j] = b2[o]; h1w[j] = heads[o]; h2w[j] = heads[128 + o];
+    }
     const float hb1 = heads[256], hb2 = heads[257];
     const int tiles = (n + 63) / 64;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -267,8 +289,8 @@ fc2_heads_kernel(const float *__restrict__ H, const float *__restrict__ goal, co
         const float *xr = xs + (pg_ * 4) * PF2_ROW;
 #pragma unroll 4
         for (int k = 0; k < PF2_IN; k++) {
-            const float4 wa = *reinterpret_cast<const float4 *>(ws + k * 128 + og * 8);
-            const float4 wb = *reinterpret_cast<const float4 *>(ws + k * 128 + og * 8 + 4);
+            const float4 wa = *reinterpret_cast<const float4 *>(ws + k * 128 + og * 4);
+            const float4 wb = *reinterpret_cast<const float4 *>(ws + k * 128 + 64 + og * 4);
             const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
             for (int p = 0; p < 4; p++) {
@@ -305,7 +327,7 @@ fc2_heads_kernel(const float *__restrict__ H, const float *__restrict__ goal, co
 // frames (env.py:647), transposes conv2 / fc2 for the kernels' access order, and chooses the two
 // power-of-two scales of the f16x3 scheme from bounds on the features and the fc1 weights.
 struct policy_ws_t {   // device workspace layout (byte offsets from the workspace base)
-    size_t fh, fl, wh, wl, h, w1f, b1, w2, b2, fc1_b, w2t, fc2_b, heads, scales, total;
+    size_t fh, fl, wh, wl, h, w1f, b1, w2, b2, fc1_b, w2t, fc2_b, heads, scales, conv_img, w1s, total;
 };
 static policy_ws_t policy_ws_layout(int max_n)
 {
@@ -318,7 +340,8 @@ static policy_ws_t policy_ws_layout(int max_n)
     L.h = take(np * 256 * 4);
     L.w1f = take(160 * 4); L.b1 = take(32 * 4); L.w2 = take(3072 * 4); L.b2 = take(32 * 4);
     L.fc1_b = take(256 * 4); L.w2t = take((size_t)PF2_IN * 128 * 4); L.fc2_b = take(128 * 4);
-    L.heads = take(258 * 4); L.scales = take(16);
+    L.heads = take(258 * 4); L.scales = take(32);
+    L.conv_img = take(16384); L.w1s = take(256 * 4);
     L.total = o;
     return L;
 }
@@ -326,7 +349,7 @@ static policy_ws_t policy_ws_layout(int max_n)
 __global__ void __launch_bounds__(1024) policy_prepare_kernel(const navgym_policy_params_t p, uint8_t *ws, const policy_ws_t L)
 {
     __shared__ float red[1024];
-    __shared__ float s_bound_h1, s_feat_scale, s_w_scale;
+    __shared__ float s_bound_h1, s_feat_scale, s_w_scale, s_h_scale, s_w2_scale;
     const int t = threadIdx.x;
     float *w1f = (float *)(ws + L.w1f), *b1 = (float *)(ws + L.b1), *w2 = (float *)(ws + L.w2), *b2 = (float *)(ws + L.b2);
     if (t < 160) {   // act_fea_cv1.weight [32][3][5] summed over the 3 frames
@@ -370,6 +393,12 @@ __global__ void __launch_bounds__(1024) policy_prepare_kernel(const navgym_polic
         int e;
         frexpf(m, &e);                          // m < 2^e
         s_feat_scale = ldexpf(1.0f, min(max(15 - e, -100), 100));   // features * scale < 2^15
+        frexpf(fmaxf(s_bound_h1, 1e-30f), &e);
+        s_h_scale = ldexpf(1.0f, min(max(15 - e, -100), 100));      // conv1 outputs * scale < 2^15
+        float w2m = 1e-30f;
+        for (int i = 0; i < 3072; i++) w2m = fmaxf(w2m, fabsf(w2[i]));
+        frexpf(w2m, &e);
+        s_w2_scale = ldexpf(1.0f, min(max(14 - e, -100), 100));
     }
     __syncthreads();
     float wm = 0.f;
@@ -384,15 +413,38 @@ __global__ void __launch_bounds__(1024) policy_prepare_kernel(const navgym_polic
         float *sc = (float *)(ws + L.scales);
         sc[0] = s_feat_scale;
         sc[1] = 1.0f / (s_feat_scale * s_w_scale);                  // powers of two: exact
+        sc[2] = s_h_scale;
+        sc[3] = 1.0f / (s_h_scale * s_w2_scale);
     }
     __syncthreads();
+    // act_fc1's weight, columns permuted from torch's channel-major feature order (c * 128 + pos)
+    // to the position-major order the front end writes (pos * 32 + c), scaled and split
     const float sw = s_w_scale;
     __half *wh = (__half *)(ws + L.wh), *wl = (__half *)(ws + L.wl);
     for (int i = t; i < 256 * 4096; i += 1024) {
-        const float x = p.fc1_w[i] * sw;
+        const int o = i >> 12, f = i & 4095, pos = f >> 5, c = f & 31;
+        const float x = p.fc1_w[o * 4096 + c * 128 + pos] * sw;
         const __half hi = __float2half_rn(x);
         wh[i] = hi;
         wl[i] = __float2half_rn(x - __half2float(hi));
+    }
+    // conv1 taps + bias, scaled: [32][8] = w0..w3 | w4, bias, 0, 0
+    if (t < 256) {
+        const int c = t >> 3, k = t & 7;
+        ((float *)(ws + L.w1s))[t] = k < 5 ? w1f[c * 5 + k] * s_h_scale : (k == 5 ? b1[c] * s_h_scale : 0.0f);
+    }
+    // conv2's weight as the B operand of policy_features_umma_kernel, byte for byte as it sits in
+    // shared memory: hi | lo, each two K blocks of [32 co][64] f16, K index = 4 ci + tap (tap 3 =
+    // 0), K-major rows of 128 bytes in 8-row groups with the 128-byte swizzle
+    __half *img = (__half *)(ws + L.conv_img);
+    for (int i = t; i < 32 * 32 * 4; i += 1024) {
+        const int co = i >> 7, ci = (i >> 2) & 31, tap = i & 3;
+        const float x = tap < 3 ? w2[(co * 32 + ci) * 3 + tap] * s_w2_scale : 0.0f;
+        const __half hi = __float2half_rn(x);
+        const uint32_t off = (uint32_t)(ci >> 4) * 4096u + (uint32_t)(co >> 3) * 1024u + (uint32_t)(co & 7) * 128u +
+                             ((((uint32_t)(ci & 15) >> 1) ^ (uint32_t)(co & 7)) << 4) + (uint32_t)(ci & 1) * 8u + (uint32_t)tap * 2u;
+        img[off >> 1] = hi;
+        img[(8192u + off) >> 1] = __float2half_rn(x - __half2float(hi));
     }
 }
 
@@ -408,7 +460,7 @@ typedef CUresult (*navgym_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, c
                                            const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                            CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// [rows][4096] f16, row-major: boxes of 64 columns (128 bytes, the swizzle span) x box_rows rows
+// [rows][4096] f16, row-major: boxes of BK columns (one swizzle span) x box_rows rows
 static int policy_make_map(CUtensorMap *m, void *base, uint64_t rows, uint32_t box_rows)
 {
     static navgym_encode_tiled_fn encode = nullptr;
@@ -423,6 +475,231 @@ static int policy_make_map(CUtensorMap *m, void *base, uint64_t rows, uint32_t b
     const cuuint32_t box[2] = {(cuuint32_t)pg::BK, box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                              pg::BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : -1;
+}
+
+// ------------------------------------------------------------------ convolutional front end on the tensor cores
+// conv1 (1 -> 32 channels, k 5, stride 2) stays on the CUDA cores -- 41 k FMA per pedestrian --
+// and writes its ReLU output straight into the A operand of conv2 seen as a GEMM per pedestrian:
+//   D[pos][co] = sum_{ci, tap} h1[ci][2 pos - 1 + tap] w2[co][ci][tap],   M 128 x N 32 x K 128,
+// K index = 4 ci + tap with a zero fourth tap, so that a row of A is, per input channel, four
+// consecutive conv1 outputs: thread `pos` computes the three it needs itself (each conv1 output is
+// evaluated by the two positions that read it: 2 x 41 k FMA is cheaper than exchanging them) and
+// stores them, hi/lo-split, as 16-byte pieces of the 128-byte-swizzled K-major tile a TMA load
+// would have produced.  conv2 then is 24 tcgen05.mma per pedestrian (8 K steps x the three
+// f16x3 products) instead of 393 k FMA; 128 epilogue threads read the accumulator row of their
+// position from TMEM, add the bias, ReLU, scale, split and store 2 x 64 contiguous bytes: the
+// features leave position-major ([pos][channel]; act_fc1's weight columns are permuted to match).
+// 21 warps: 2 producer groups of 8 (a pedestrian each, A operand in 3 rotating stages; within a
+// group warps 0-3 build K block 0 = input channels 0-15, warps 4-7 K block 1), 1 MMA issuer,
+// 4 epilogue warps (accumulators double-buffered in TMEM: 2 x 6 x 32 columns).  The producers are the
+// critical resource (~1400 instructions per position and pedestrian): 16 warps of them keep the
+// four schedulers issuing (8 warps: 0.73 ms for 40 960 pedestrians; the SIMT kernel: 0.97 ms).
+namespace pc {
+constexpr int THREADS = 21 * 32, MMA_WARP = 16;
+constexpr uint32_t A_HALF = 2 * 16384;             // hi (or lo) part of one A stage: 2 K blocks of [128][64] f16
+constexpr uint32_t A_STAGE = 2 * A_HALF;           // 64 KB
+constexpr uint32_t B_BYTES = 16384;                // hi + lo, 2 K blocks of [32][64] f16 each
+constexpr uint32_t XS_FLOATS = 520;
+constexpr int A_STAGES = 3;                        // a producer group never waits for the MMAs of its previous pedestrian
+constexpr uint32_t OFF_B = A_STAGES * A_STAGE, OFF_W1 = OFF_B + B_BYTES, OFF_XS = OFF_W1 + 32 * 8 * 4;
+constexpr uint32_t OFF_BAR = OFF_XS + 2 * XS_FLOATS * 4;
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 128 + 1024;
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}  // namespace pc
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b)
+{
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+// (hi, lo) f16 pairs of two floats: hi = half(x), lo = half(x - hi)
+__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo)
+{
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 back = __half22float2(h);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = pack_half2(a - back.x, b - back.y);
+}
+
+// conv_img: the B operand exactly as it sits in shared memory (policy_prepare_kernel), w1s
+// [32][8] = 5 conv1 taps and the bias, all times s_h, 2 pad; scales: see policy_prepare_kernel
+__global__ void __launch_bounds__(pc::THREADS, 1)
+policy_features_umma_kernel(const float *__restrict__ scan, int n, const uint4 *__restrict__ conv_img,
+                            const float *__restrict__ w1s, const float *__restrict__ b2, const float *__restrict__ scales,
+                            __half *__restrict__ out_hi, __half *__restrict__ out_lo)
+{
+    using namespace pg;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t base = smem_u32(sm);
+    const uint32_t bars = base + pc::OFF_BAR;
+    const uint32_t afull0 = bars, aempty0 = bars + 24, tfull0 = bars + 48, tempty0 = bars + 64, tmem_slot = bars + 80;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int i = threadIdx.x; i < (int)(pc::B_BYTES / 16); i += pc::THREADS) reinterpret_cast<uint4 *>(sm + pc::OFF_B)[i] = conv_img[i];
+    for (int i = threadIdx.x; i < 256; i += pc::THREADS) reinterpret_cast<float *>(sm + pc::OFF_W1)[i] = w1s[i];
+    if (threadIdx.x < 6) {   // the left padding of both scan buffers: x[-3 .. -1] = 0
+        reinterpret_cast<float *>(sm + pc::OFF_XS)[(threadIdx.x / 3) * pc::XS_FLOATS + threadIdx.x % 3] = 0.0f;
+    }
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < pc::A_STAGES; st++) { mbar_init(afull0 + 8 * st, 256); mbar_init(aempty0 + 8 * st, 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == pc::MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the B operand was written with ordinary stores
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+    const int my_count = blockIdx.x < n ? (n - 1 - blockIdx.x) / gridDim.x + 1 : 0;   // pedestrians of this CTA
+
+    if (warp < pc::MMA_WARP) {
+        // ---- producers: group g fills A stage g for this CTA's pedestrians j = g, g + 2, ...
+        const int g = warp >> 3, tg = threadIdx.x & 255, pos = tg & 127, half = tg >> 7;
+        float *xs = reinterpret_cast<float *>(sm + pc::OFF_XS) + g * pc::XS_FLOATS;   // xs[3 + i] = input i
+        const float *wt = reinterpret_cast<const float *>(sm + pc::OFF_W1) + half * 16 * 8;
+        // this thread's row of K block `half`; a 16-byte piece `chunk` of it sits at chunk ^ (row % 8)
+        uint8_t *row0 = sm + half * 16384 + (pos >> 3) * 1024 + (pos & 7) * 128;
+        const uint32_t rx = pos & 7;
+        float pre[2] = {0.0f, 0.0f};   // the next pedestrian's scan, loaded one pedestrian ahead
+        if (g < my_count) {
+#pragma unroll
+            for (int i = 0; i < 2; i++) pre[i] = scan[(size_t)(blockIdx.x + g * gridDim.x) * 512 + tg + 256 * i];
+        }
+        for (int j = g; j < my_count; j += 2) {
+            const uint32_t st = (uint32_t)j % pc::A_STAGES, use = (uint32_t)j / pc::A_STAGES;   // pedestrian j -> A stage j % 3
+            uint8_t *rowp = row0 + st * pc::A_STAGE;
+            asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");   // everyone is done with the previous scan
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const double r = fmin(fmax((double)pre[i], 0.0), 6.0);
+                xs[3 + tg + 256 * i] = (float)(r / 6.0 - 0.5);  // env.py:627-629, 648
+            }
+            if (j + 2 < my_count) {
+#pragma unroll
+                for (int i = 0; i < 2; i++) pre[i] = scan[(size_t)(blockIdx.x + (j + 2) * gridDim.x) * 512 + tg + 256 * i];
+            }
+            asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
+            mbar_wait(aempty0 + 8 * st, (use & 1) ^ 1);                  // the MMAs have read this stage
+            // conv1 outputs q = 2 pos - 1 + tap need inputs 2 q - 1 + k = 4 pos - 3 + 2 tap + k
+            const float4 xa = *reinterpret_cast<const float4 *>(xs + 4 * pos), xb = *reinterpret_cast<const float4 *>(xs + 4 * pos + 4);
+            const float x[9] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w, xs[4 * pos + 8]};
+            const bool pad0 = pos == 0, pad2 = pos == 127;   // conv2's own zero padding: q = -1 and q = 255
+#pragma unroll 2
+            for (int cp = 0; cp < 8; cp++) {   // two input channels = one 16-byte piece
+                float v[2][3];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const float4 wa = *reinterpret_cast<const float4 *>(wt + (2 * cp + h) * 8);
+                    const float2 wb = *reinterpret_cast<const float2 *>(wt + (2 * cp + h) * 8 + 4);
+#pragma unroll
+                    for (int tap = 0; tap < 3; tap++) {
+                        float a = wb.y;
+                        a = fmaf(wa.x, x[2 * tap], a); a = fmaf(wa.y, x[2 * tap + 1], a); a = fmaf(wa.z, x[2 * tap + 2], a);
+                        a = fmaf(wa.w, x[2 * tap + 3], a); a = fmaf(wb.x, x[2 * tap + 4], a);
+                        v[h][tap] = fmaxf(a, 0.0f);
+                    }
+                    if (pad0) v[h][0] = 0.0f;
+                    if (pad2) v[h][2] = 0.0f;
+                }
+                // three packed conversions (F2FP on the ALU pipe; a lone cvt.f16.f32 would go to
+                // the quarter-rate XU pipe): taps (0, 1) of either channel, and both third taps
+                uint32_t h01a, l01a, h01b, l01b, h2, l2;
+                split2(v[0][0], v[0][1], h01a, l01a);
+                split2(v[1][0], v[1][1], h01b, l01b);
+                split2(v[0][2], v[1][2], h2, l2);
+                const uint32_t hi[4] = {h01a, h2 & 0xffffu, h01b, h2 >> 16};   // the fourth tap is a zero
+                const uint32_t lo[4] = {l01a, l2 & 0xffffu, l01b, l2 >> 16};
+                const uint32_t off = ((uint32_t)cp ^ rx) << 4;
+                *reinterpret_cast<uint4 *>(rowp + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4 *>(rowp + pc::A_HALF + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // visible to the tensor core's reads
+            mbar_arrive(afull0 + 8 * st);
+        }
+    } else if (warp == pc::MMA_WARP) {
+        // ---- MMA issuer
+        if (lane == 0) {
+            const uint32_t bh = base + pc::OFF_B, bl = bh + 8192;
+            for (int j = 0; j < my_count; j++) {
+                const uint32_t g = j & 1, par = (j >> 1) & 1, st = (uint32_t)j % pc::A_STAGES, use = (uint32_t)j / pc::A_STAGES;
+                mbar_wait(tempty0 + 8 * g, par ^ 1);
+                mbar_wait(afull0 + 8 * st, use & 1);
+                tc_fence_after();
+                // Six accumulators of 32 columns (3 products x 2 K blocks), four chained MMAs each:
+                // an N = 32 MMA is ~30 cycles of tensor-pipe work but its result is only available
+                // to the next accumulating MMA ~170 cycles later, so 24 MMAs chained on one
+                // accumulator cost 4 000 cycles per pedestrian (measured: the whole kernel ran at
+                // that pace); six independent chains overlap.  The epilogue adds them up.
+                const uint32_t d = tmem_base + g * 256, ah = base + st * pc::A_STAGE, al = ah + pc::A_HALF;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+#pragma unroll
+                    for (int kb = 0; kb < 2; kb++) {
+                        const uint64_t fh = umma_desc_sw128(ah + kb * 16384 + k * 32), fl = umma_desc_sw128(al + kb * 16384 + k * 32);
+                        const uint64_t wh = umma_desc_sw128(bh + kb * 4096 + k * 32), wl = umma_desc_sw128(bl + kb * 4096 + k * 32);
+                        umma_f16(d + (0 + kb) * 32, fl, wh, pc::IDESC, k != 0);
+                        umma_f16(d + (2 + kb) * 32, fh, wl, pc::IDESC, k != 0);
+                        umma_f16(d + (4 + kb) * 32, fh, wh, pc::IDESC, k != 0);
+                    }
+                }
+                umma_commit(aempty0 + 8 * st);
+                umma_commit(tfull0 + 8 * g);
+            }
+        }
+    } else {
+        // ---- epilogue: warp w owns TMEM lanes 32 (w % 4) ... = positions
+        const int q = warp & 3, pos = q * 32 + lane;
+        const float descale = scales[3], fscale = scales[0];
+        for (int j = 0; j < my_count; j++) {
+            const uint32_t g = j & 1, par = (j >> 1) & 1;
+            const int ped = blockIdx.x + j * gridDim.x;
+            mbar_wait(tfull0 + 8 * g, par);
+            tc_fence_after();
+            float acc[32];
+            {
+                uint32_t v[32];
+                const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + g * 256;
+                tmem_ld32(t0, v);
+#pragma unroll
+                for (int c = 0; c < 32; c++) acc[c] = __uint_as_float(v[c]);
+#pragma unroll
+                for (int a = 1; a < 6; a++) {   // the two small products first, hi x hi last
+                    tmem_ld32(t0 + a * 32, v);
+#pragma unroll
+                    for (int c = 0; c < 32; c++) acc[c] += __uint_as_float(v[c]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty0 + 8 * g);   // the accumulators are in registers: the next MMAs may overwrite them
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+                const float a = fmaxf(fmaf(acc[c], descale, b2[c]), 0.0f) * fscale;
+                const float b = fmaxf(fmaf(acc[c + 1], descale, b2[c + 1]), 0.0f) * fscale;
+                split2(a, b, hi[c >> 1], lo[c >> 1]);
+            }
+            uint4 *oh = reinterpret_cast<uint4 *>(out_hi + (size_t)ped * 4096 + pos * 32);
+            uint4 *ol = reinterpret_cast<uint4 *>(out_lo + (size_t)ped * 4096 + pos * 32);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                oh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+                ol[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == pc::MMA_WARP) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
 }

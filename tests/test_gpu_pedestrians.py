@@ -150,7 +150,7 @@ def test_native_policy_stage_by_stage(n):
     s_f = float(scales[0])
     assert s_f > 0 and np.log2(s_f) == int(np.log2(s_f)) and float(fh.float().abs().max()) < 32768.0
     mine = (fh.double() + fl.double()) / s_f
-    assert float((mine - feat.double()).abs().max()) < 2e-6
+    assert float((mine - feat.double()).abs().max()) < 4e-6   # conv2 runs in the f16x3 scheme too
     assert float(((fh.double() + fl.double()) / s_f - mine).abs().max()) == 0.0
     # the tensor-core layer on the features the kernel itself produced
     # (12 288 products per output accumulate in the tensor core's float32 adder: a few 1e-6, the
