@@ -284,6 +284,54 @@ def config_c5(torch, dev, steps, warmup, world_mp):
             "roofline_gather": gather_block(B, ms_env, GATHERS_PER_ENV_STEP, "as C2 (same world)")}
 
 
+def config_crowd(torch, dev, steps, warmup, world_mp):
+    """the C2 world with the reference's policy-driven pedestrians on the device
+    (PedestrianSim: 10 per environment, each with its own 512-beam scan and a CNN policy forward
+    per step through the library's tcgen05 kernels; random-init weights, human_policy.pth is not
+    distributed).  One step = pedestrians act -> robots step -> pedestrians observe."""
+    from nav_gym_b200.batched_env import BatchedNavGym
+    from nav_gym_b200.pedestrians import PedestrianSim
+    B, P = 4096, 10
+    env = BatchedNavGym(B, world_mp, device=dev, seed=8, auto_reset=True)
+    env.reset_from_spawn_pool(np.random.RandomState(4))
+    sim = PedestrianSim(env, P, seed=8)
+    bank = _bank(torch, dev, 32, B, 66)
+
+    def timed(fn, n):
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n
+    for i in range(warmup):
+        sim.step(bank[i % 32])
+    ms = timed(lambda i: sim.step(bank[i % 32]), steps)
+    n = B * P
+    scan, goal, speed = sim.scan.reshape(n, -1), sim.goal_local.reshape(n, 2), sim.prev_action.reshape(n, 2)
+    ms_policy = timed(lambda i: sim.native.mean(scan, goal, speed, out=sim._mean), 20)
+    flop = 2.0 * n * 3 * (4096 * 256 + 128 * 32 * 128)   # f16x3: three MMAs per product; conv2 K padded to 128
+    tf = flop / (ms_policy * 1e-3) / 1e12
+    peak_tf = None
+    try:
+        peak_tf = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))).get('bf16_tflops'))
+    except Exception:
+        pass
+    out = {"envs": B, "pedestrians_per_env": P, "policy": "HumanPolicy (human_policy.py:19-71), random-init, precision f16x3 (float32-grade)",
+           "steps": steps, "warmup": warmup, "ms_per_step": ms, "env_steps_per_s": B / ms * 1e3,
+           "pedestrian_steps_per_s": n / ms * 1e3, "pedestrian_rays_per_s": n * NB / ms * 1e3,
+           "ms_policy_forward": ms_policy,
+           "ms_parts": {"act": timed(lambda i: sim.act(), 20), "robot_step": timed(lambda i: env.step(bank[i % 32]), 20),
+                        "observe": timed(lambda i: sim.observe(), 20)},
+           "roofline_policy": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s",
+                               "frac": (tf / peak_tf) if peak_tf else None,
+                               "note": "tensor-core flop of the 3 kernels' MMAs (act_fc1 + conv2, three f16 products each) over the "
+                                       "whole policy forward, conv1 / act_fc2 / heads on CUDA cores included in the time"}}
+    return out
+
+
 # ------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -430,6 +478,7 @@ def main():
         if world == 1:
             cfg['c3'] = config_c3(torch, dev, ks, kw)
             cfg['c5'] = config_c5(torch, dev, ks, kw, mp)
+            cfg['crowd'] = config_crowd(torch, dev, ks, kw, mp)
 
     t = torch.tensor([total_ms] + (e2e or [0.0, 0.0, 0.0]) + [c4_ms], dtype=torch.float64, device=dev)
     if world > 1:

@@ -31,7 +31,29 @@ struct EnvSmem {
 #ifdef NAVGYM_PROFILE
     int prof_iters_a[8], prof_rounds_b[8], prof_alive, prof_cyc_b[8], prof_walk[8];   // per warp: tail iterations / cooperative rounds
 #endif
+#ifdef NAVGYM_SMEM_WINDOW
+    // A/B build (profiles/r2_smem_window_ab.txt): the (2R)^2 EDT cells around the origin cell staged
+    // in shared memory; samples inside the window read it instead of L2
+    float win[4 * NAVGYM_SMEM_WINDOW * NAVGYM_SMEM_WINDOW];
+    int wx0, wy0;
+#endif
 };
+
+// EDT value of an in-map cell: from the staged window when it covers the cell (A/B build),
+// else through the read-only L1/L2 path.
+__device__ __forceinline__ float edt_at(const EnvSmem &sm, const float *__restrict__ dist, int cx, int cy, int W, bool valid)
+{
+#ifdef NAVGYM_SMEM_WINDOW
+    const unsigned ux = (unsigned)(cx - sm.wx0), uy = (unsigned)(cy - sm.wy0);
+    const bool inw = valid & (ux < 2u * NAVGYM_SMEM_WINDOW) & (uy < 2u * NAVGYM_SMEM_WINDOW);
+    float d = 0.0f;
+    if (inw) d = sm.win[uy * (2 * NAVGYM_SMEM_WINDOW) + ux];
+    else d = __ldg(dist + (valid ? (unsigned)(cy * W + cx) : 0u));
+    return d;
+#else
+    return __ldg(dist + (valid ? (unsigned)(cy * W + cx) : 0u));
+#endif
+}
 
 enum { PASS_STEP = 0, PASS_RESCAN = 1, PASS_RESET = 2, PASS_END = 3 };
 #ifndef NAVGYM_HEAD_STEPS
@@ -149,8 +171,7 @@ __device__ __forceinline__ void march_tail_dealt(EnvSmem &sm, const float *__res
         const int cx = __float2int_rz(march_pos(dd.x, t, x0));
         const int cy = __float2int_rz(march_pos(dd.y, t, y0));
         const bool inb = ((unsigned)cx < (unsigned)W) & ((unsigned)cy < (unsigned)H);
-        const unsigned ci_ = (inb & (kb >= 0)) ? (unsigned)(cy * W + cx) : 0u;
-        const float d = __ldg(dist + ci_);
+        const float d = edt_at(sm, dist, cx, cy, W, inb & (kb >= 0));
         const bool hit = inb & (d <= 0.0f);
         t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
         const bool fin = (kb >= 0) & (!inb | hit | !(t < t_stop));
@@ -197,7 +218,7 @@ __device__ __forceinline__ void march_tail_dealt(EnvSmem &sm, const float *__res
             const int fy = __float2int_rz(march_pos(bdy, tj, y0));
             const bool finb = ((unsigned)fx < (unsigned)W) & ((unsigned)fy < (unsigned)H);
             const int fcell = finb ? (fy << 16 | fx) : -2;
-            const float fd = __ldg(dist + ((finb & !fin) ? (unsigned)(fy * W + fx) : 0u));
+            const float fd = edt_at(sm, dist, fx, fy, W, finb & !fin);
             // walk the true march through the fetched cells
             const float t0 = bt;
             bool walking = !fin;
@@ -270,6 +291,21 @@ __device__ __forceinline__ void march_scan(EnvSmem &sm, const navgym_step_args_t
     const float t1 = fmaxf(__fmul_rn(d0, 0.999f), 1.0f);  // == 0.0f + first step
     const bool degenerate = !o_in | (d0 <= 0.0f) | !(t1 < t_stop);
     constexpr int HB = BPL >= 4 ? 4 : BPL;   // beams in flight per thread in the head phase
+#ifdef NAVGYM_SMEM_WINDOW
+    {   // stage the window: rows of 2R cells, coalesced; cells outside the map are never read
+        constexpr int R2 = 2 * NAVGYM_SMEM_WINDOW;
+        const int wx0 = ci - NAVGYM_SMEM_WINDOW, wy0 = cj - NAVGYM_SMEM_WINDOW;
+        if (tid == 0) { sm.wx0 = wx0; sm.wy0 = wy0; }
+        if (!degenerate) {
+            for (int i = tid; i < R2 * R2; i += TPB) {
+                const int x = wx0 + (i % R2), y = wy0 + (i / R2);
+                const bool ok = ((unsigned)x < (unsigned)W) & ((unsigned)y < (unsigned)H);
+                sm.win[i] = ok ? __ldg(dist + (unsigned)(y * W + x)) : 0.0f;
+            }
+        }
+        cta_sync<WPE>();
+    }
+#endif
 #pragma unroll 1
     for (int r = r_begin; r < r_end; r++) {
         float th_[HB], dxh[HB], dyh[HB];
@@ -296,8 +332,7 @@ __device__ __forceinline__ void march_scan(EnvSmem &sm, const navgym_step_args_t
                 cx[j] = __float2int_rz(march_pos(dxh[j], th_[j], x0));
                 cy[j] = __float2int_rz(march_pos(dyh[j], th_[j], y0));
                 inb[j] = ((unsigned)cx[j] < (unsigned)W) & ((unsigned)cy[j] < (unsigned)H);
-                const unsigned idx = (inb[j] & (th_[j] >= 0.0f)) ? (unsigned)(cy[j] * W + cx[j]) : 0u;
-                dv[j] = __ldg(dist + idx);
+                dv[j] = edt_at(sm, dist, cx[j], cy[j], W, inb[j] & (th_[j] >= 0.0f));
             }
 #pragma unroll
             for (int j = 0; j < HB; j++) {
