@@ -550,11 +550,17 @@ __device__ __forceinline__ void step_body(const navgym_step_args_t &a, EnvSmem &
                 if (o < ns) {
                     const float4 sg = *reinterpret_cast<const float4 *>(segs + 4 * o);
                     const float ax = sg.x, ay = sg.y, bx = sg.z, by = sg.w;
+                    float da2 = (ax - lx) * (ax - lx) + (ay - ly) * (ay - ly);
+                    float db2 = (bx - lx) * (bx - lx) + (by - ly) * (by - ly);
+                    // out of sight: every point of the segment is farther than range_max (its
+                    // nearer end minus its length still is), so any hit would be clipped to
+                    // range_max two phases on -- the same value as no hit (env.py:435)
+                    const float len2 = (bx - ax) * (bx - ax) + (by - ay) * (by - ay);
+                    const float reach = a.range_max * 1.001f + sqrtf(len2) + 0.01f;
+                    if (fminf(da2, db2) > reach * reach) continue;
                     float pa = atan2f(ay - ly, ax - lx), pb = atan2f(by - ly, bx - lx);
                     float dl = pb - pa;
                     dl -= 6.2831853f * rintf(dl * 0.15915494f);
-                    float da2 = (ax - lx) * (ax - lx) + (ay - ly) * (ay - ly);
-                    float db2 = (bx - lx) * (bx - lx) + (by - ly) * (by - ly);
                     if (fabsf(dl) > 3.0f || da2 < 1e-6f || db2 < 1e-6f) { k0 = 0; cnt = NB; }
                     else beam_window(dl >= 0 ? pa : pb, fabsf(dl), lt, k0, cnt);
                     for (int i = lane; i < cnt; i += 32) {
@@ -567,6 +573,7 @@ __device__ __forceinline__ void step_body(const navgym_step_args_t &a, EnvSmem &
                     const float X = discs[3 * q], Y = discs[3 * q + 1], Rd = discs[3 * q + 2];
                     const float cx = X - lx, cy = Y - ly;
                     const float dc = sqrtf(cx * cx + cy * cy);
+                    if (dc > a.range_max * 1.001f + fabsf(Rd) + 0.01f) continue;   // out of sight (see the segments)
                     if (dc <= Rd * 1.05f + 1e-3f) { k0 = 0; cnt = NB; }
                     else {
                         const float half = asinf(fminf(Rd / dc, 1.0f)) * 1.01f + 1e-4f;

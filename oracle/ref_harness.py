@@ -39,6 +39,14 @@ class Recorder(object):
     def __init__(self):
         self.scans = []   # finalized scan records
         self.cur = {}
+        # optional transcript of every call that crosses the native boundary, in order, with the
+        # arguments as the reference passed them and the result the stand-in produced
+        # (oracle/make_golden_native_calls.py); None = off
+        self.calls = None
+
+    def log(self, **rec):
+        if self.calls is not None:
+            self.calls.append(rec)
 
     def finalize(self, ranges_after, discs):
         rec = self.cur
@@ -68,12 +76,14 @@ class PyRayMarching(object):
     def __init__(self, omap, max_range):
         self.max_range = float(max_range)
         self.dist = orc.edt(omap.arr)
+        REC.log(fn='PyRayMarching', occ=omap.arr.copy(), max_range=float(max_range))
 
     def calc_range_many(self, ins, outs):
         assert ins.dtype == np.float32 and outs.dtype == np.float32
         assert ins.flags.c_contiguous and outs.flags.c_contiguous
         r, hits = orc.calc_range_many(self.dist, ins, self.max_range, want_hits=True)
         outs[:] = r
+        REC.log(fn='calc_range_many', ins=ins.copy(), outs=outs.copy())
         REC.cur['ins'] = ins.copy()
         REC.cur['hits'] = hits
         REC.cur['range_cells'] = r.copy()
@@ -87,7 +97,11 @@ def flatten_contours(contours):
 def render_contours_in_lidar(ranges, angles, flat_contours, lidar_xy):
     assert ranges.dtype == np.float32
     dirs = _libm_dirs(angles)
+    before = ranges.copy()
     orc.render_contours(ranges, dirs, flat_contours, np.asarray(lidar_xy, np.float32))
+    REC.log(fn='render_contours_in_lidar', ranges_in=before, angles=np.asarray(angles).copy(),
+            flat=np.asarray(flat_contours, np.float32).copy(), lidar_xy=np.asarray(lidar_xy, np.float64).copy(),
+            ranges_out=ranges.copy())
     REC.cur['segs'] = orc.contours_to_segments(flat_contours)
 
 
@@ -122,10 +136,16 @@ class CMap2D(object):
     def render_agents_in_lidar(self, ranges, angles, agents, lidar_xy):
         assert ranges.dtype == np.float32
         discs = np.zeros((0, 3), np.float32)
+        before = ranges.copy()
         if len(agents):
             discs = np.concatenate([orc.legs_to_discs(a.pose_2d_in_map_frame, a.state)
                                     for a in agents]).astype(np.float32)
             orc.render_discs(ranges, _libm_dirs(angles), discs, np.asarray(lidar_xy, np.float32))
+        REC.log(fn='render_agents_in_lidar', ranges_in=before, angles=np.asarray(angles).copy(),
+                poses=np.array([a.pose_2d_in_map_frame for a in agents], np.float32).reshape(-1, 3),
+                states=np.array([a.state for a in agents], np.float32).reshape(-1, 3),
+                vels=np.array([np.ravel(a.vel_in_map_frame) for a in agents], np.float32).reshape(len(agents), 2 if not len(agents) else -1),
+                lidar_xy=np.asarray(lidar_xy, np.float64).copy(), ranges_out=ranges.copy())
         REC.finalize(ranges, discs)
 
 

@@ -300,3 +300,42 @@ print('no-fma pair ok')
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, '-c', code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and 'no-fma pair ok' in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
+def test_level1_native_call_transcript():
+    """INTEGRATION.md level 1, end to end on the device: every call the unmodified reference
+    env.py made across its native boundary during one episode (tests/golden/native_calls.npz,
+    minted by oracle/make_golden_native_calls.py -- PyOMap / PyRayMarching construction, then per
+    _compute_scan of the robot and of every pedestrian: calc_range_many, render_contours_in_lidar,
+    CMap2D.render_agents_in_lidar with CSimAgent legs) is replayed, in order and with the
+    reference's own arguments, through nav_gym_b200.natives; every result equals the transcript
+    bit for bit.  (The transcript's results come from the oracle-backed stand-ins: the native
+    semantics themselves stay "parity unpinned".)"""
+    from nav_gym_b200 import natives
+    G = gu.load('native_calls')
+    names = [str(x) for x in G['kind_names']]
+    rm, n = None, {k: 0 for k in names}
+    for i, kind in enumerate(G['kind']):
+        fn = names[int(kind)]
+        g = lambda k: G['c%d_%s' % (i, k)]
+        if fn == 'PyRayMarching':
+            H, W = [int(v) for v in g('occ_shape')]
+            occ = np.ascontiguousarray(np.unpackbits(g('occ_bits'))[:H * W].reshape(H, W).astype(np.bool_))
+            rm = natives.PyRayMarching(natives.PyOMap(occ), float(g('max_range')))   # env.py:337-340
+        elif fn == 'calc_range_many':
+            ins = np.ascontiguousarray(g('ins'))
+            outs = np.zeros(len(ins), np.float32)
+            rm.calc_range_many(ins, outs)                                            # env.py:425
+            assert np.array_equal(outs, g('outs')), 'call %d calc_range_many' % i
+        elif fn == 'render_contours_in_lidar':
+            r = g('ranges_in').copy()
+            natives.render_contours_in_lidar(r, g('angles'), g('flat'), g('lidar_xy'))   # env.py:430-431
+            assert np.array_equal(r, g('ranges_out')), 'call %d render_contours_in_lidar' % i
+        else:
+            r = g('ranges_in').copy()
+            agents = [natives.CSimAgent(p, s_, v) for p, s_, v in zip(g('poses'), g('states'), g('vels'))]
+            cm = natives.CMap2D()
+            cm.render_agents_in_lidar(r, g('angles'), agents, g('lidar_xy'))         # env.py:432
+            assert np.array_equal(r, g('ranges_out')), 'call %d render_agents_in_lidar' % i
+        n[fn] += 1
+    assert n['PyRayMarching'] == 1 and min(n.values()) >= 1 and sum(n.values()) == len(G['kind']) > 60

@@ -141,3 +141,35 @@ def test_march_rounding_switch():
     # (the two roundings differ in 16 % of the sample positions but pick another CELL only ~1e-5 of
     # the time, and a ray's range changes more rarely still)
     assert 0 < diff.sum() and diff.mean() < 1e-3, diff.sum()
+
+
+def test_native_call_transcript_fixture_replays_through_the_oracle():
+    """tests/golden/native_calls.npz (the reference's own native-call sequence, minted by
+    oracle/make_golden_native_calls.py) is self-consistent: the oracle's restatements reproduce
+    every recorded result from the recorded arguments.  The GPU test replays the same transcript
+    through the product's level-1 binding."""
+    G = gu.load('native_calls')
+    names = [str(x) for x in G['kind_names']]
+    dist, max_range, seen = None, None, set()
+    for i, kind in enumerate(G['kind']):
+        fn = names[int(kind)]
+        g = lambda k: G['c%d_%s' % (i, k)]
+        seen.add(fn)
+        if fn == 'PyRayMarching':
+            H, W = [int(v) for v in g('occ_shape')]
+            dist = orc.edt(np.unpackbits(g('occ_bits'))[:H * W].reshape(H, W).astype(np.bool_))
+            max_range = float(g('max_range'))
+        elif fn == 'calc_range_many':
+            want, _ = orc.calc_range_many(dist, np.ascontiguousarray(g('ins')), max_range, want_hits=True)
+            assert np.array_equal(want, g('outs'))
+        else:
+            r = g('ranges_in').copy()
+            head = np.asarray(g('angles')).astype(np.float32)
+            _, dirs = orc.beam_dirs(np.float32(0), lin=head.astype(np.float64))
+            if fn == 'render_contours_in_lidar':
+                orc.render_contours(r, dirs, g('flat'), np.asarray(g('lidar_xy'), np.float32))
+            elif len(g('poses')):
+                discs = np.concatenate([orc.legs_to_discs(p, s_) for p, s_ in zip(g('poses'), g('states'))]).astype(np.float32)
+                orc.render_discs(r, dirs, discs, np.asarray(g('lidar_xy'), np.float32))
+            assert np.array_equal(r, g('ranges_out'))
+    assert seen == set(names)
