@@ -443,12 +443,33 @@ def main():
         barrier()
         e2e_sync_ms = (time.perf_counter() - t_s) * 1e3
 
-        n_groups = int(os.environ.get('NAVGYM_HOST_GROUPS', '4'))
+        # Group count: more groups hide more of the kernel behind the copies, but every group adds
+        # submissions and smaller DMA chunks; which wins depends on how many GPUs share the host's
+        # PCIe / memory system (8 GPUs: the copies are the bottleneck, fewer groups win).  The
+        # candidates are timed on a short rollout (max over ranks, so every rank picks the same),
+        # then the timed run uses the winner.  NAVGYM_HOST_GROUPS pins it.
         cur = torch.empty(B, 2, dtype=torch.float32).pin_memory()
-        bounds = env.host_groups(n_groups, cur, obs_h, rew_h, done_h)
         ab = _lib.ActionBank(C.c_void_p(act_h.data_ptr()), n_bank, B)
         policy = C.cast(lib.navgym_policy_action_bank, _lib.POLICY_FN)
-        env.rollout_host(min(60, max(W, 8)), policy, ab)
+        pinned = os.environ.get('NAVGYM_HOST_GROUPS')
+        cands = [int(pinned)] if pinned else [4, 2, 1]
+        trial = {}
+        for ng in cands:
+            bounds = env.host_groups(ng, cur, obs_h, rew_h, done_h)
+            env.rollout_host(min(60, max(W, 8)), policy, ab)
+            if len(cands) > 1:
+                barrier()
+                t_s = time.perf_counter()
+                env.rollout_host(200, policy, ab)
+                barrier()
+                tt = torch.tensor([time.perf_counter() - t_s], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                trial[ng] = float(tt)
+        n_groups = min(trial, key=trial.get) if trial else cands[0]
+        if n_groups != cands[-1]:
+            bounds = env.host_groups(n_groups, cur, obs_h, rew_h, done_h)
+            env.rollout_host(min(60, max(W, 8)), policy, ab)
         barrier()
         l0 = lib.navgym_launch_count()
         t_s = time.perf_counter()
@@ -456,13 +477,14 @@ def main():
         barrier()
         e2e_ms = (time.perf_counter() - t_s) * 1e3
         e2e_launches = int(lib.navgym_launch_count() - l0)
+        copy_bounds = [(B * g // 4, B * (g + 1) // 4) for g in range(4)]   # the copy-only leg keeps 4 chunks
 
-        streams = [torch.cuda.Stream(device=dev) for _ in bounds]
+        streams = [torch.cuda.Stream(device=dev) for _ in copy_bounds]
         torch.cuda.synchronize(dev)
         barrier()  # all ranks copy at the same time, as in the e2e legs
         t_s = time.perf_counter()
         for i in range(Ke):
-            for s_, (b0, b1) in zip(streams, bounds):
+            for s_, (b0, b1) in zip(streams, copy_bounds):
                 with torch.cuda.stream(s_):
                     obs_h[b0:b1].copy_(env.obs[b0:b1], non_blocking=True)
         torch.cuda.synchronize(dev)
@@ -534,6 +556,8 @@ def main():
             "api": ("BatchedNavGym.rollout_host (C ABI navgym_host_rollout): pinned host actions in, pinned "
                     "host obs/reward/done out, %d env groups rotated in C; a group's next actions are "
                     "written by the policy callback only after its previous results landed") % n_groups,
+            "groups": n_groups,
+            "groups_trial_env_steps_per_s": {str(k): world * B * 200 / v for k, v in trial.items()},
             "sync_value": world * B * Ke / (e2e_sync_ms * 1e-3),
             "copy_only_value": world * B * Ke / (copy_only_ms * 1e-3),
             "frac_of_copy_only": copy_only_ms / e2e_ms,
