@@ -160,8 +160,8 @@ def cpu_baseline_block(sample_steps=60):
                       "(oracle/navgym_oracle.c) with OpenMP over %d threads; noise pre-drawn; the "
                       "reference itself is one env per Python process with pip natives absent on "
                       "this box (its own Python loop, timed in the build container: "
-                      "tools/ref_python_baseline.py, BASELINE.md section 5: 474 env-steps/s with 1 "
-                      "pedestrian, 101 with 5-15, one core)" % (r['B'], sample_steps, r['cores'])}
+                      "tools/ref_python_baseline.py, BASELINE.md section 5: 372 env-steps/s with 1 "
+                      "pedestrian, 58 with 5-15, one core)" % (r['B'], sample_steps, r['cores'])}
 
 
 # ------------------------------------------------------------------------------ GPU legs
