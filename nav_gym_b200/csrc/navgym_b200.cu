@@ -287,9 +287,13 @@ int navgym_agent_scan_batch(const navgym_scan_args_t *args, void *stream)
 {
     if (args->num_envs <= 0 || args->agents_per_env <= 0) return 0;
     if (args->num_beams <= 0 || !args->pose || !args->lin || !args->ranges) return (int)cudaErrorInvalidValue;
-    // crowd mode: one thread per other agent builds its footprint into a fixed shared-memory list
-    if (!args->segs && args->robot_state && args->agents_per_env > NAVGYM_SCAN_AGENTS) return (int)cudaErrorInvalidValue;
-    agent_scan_kernel<<<args->num_envs * args->agents_per_env, 128, 0, (cudaStream_t)stream>>>(*args);
+    // crowd mode: one thread per other agent stages its footprint in a fixed shared-memory list
+    const bool crowd = !args->segs && args->robot_state;
+    if (crowd && args->agents_per_env > NAVGYM_SCAN_AGENTS) return (int)cudaErrorInvalidValue;
+    if (crowd || !args->segs || args->max_seg <= NAVGYM_SCAN_SEGS)
+        agent_scan_kernel<<<args->num_envs * args->agents_per_env, 128, 0, (cudaStream_t)stream>>>(*args);
+    else   // longer segment lists: every segment against every beam, straight from global memory
+        agent_scan_generic_kernel<<<args->num_envs * args->agents_per_env, 128, 0, (cudaStream_t)stream>>>(*args);
     g_launches++;
     return (int)cudaGetLastError();
 }

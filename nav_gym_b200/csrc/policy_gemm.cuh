@@ -327,7 +327,7 @@ fc2_heads_kernel(const float *__restrict__ H, const float *__restrict__ goal, co
 // frames (env.py:647), transposes conv2 / fc2 for the kernels' access order, and chooses the two
 // power-of-two scales of the f16x3 scheme from bounds on the features and the fc1 weights.
 struct policy_ws_t {   // device workspace layout (byte offsets from the workspace base)
-    size_t fh, fl, wh, wl, h, w1f, b1, w2, b2, fc1_b, w2t, fc2_b, heads, scales, conv_img, w1s, total;
+    size_t fh, fl, wh, wl, h, w1f, b1, w2, b2, fc1_b, w2t, fc2_b, heads, scales, conv_img, w1s, conv1_img, total;
 };
 static policy_ws_t policy_ws_layout(int max_n)
 {
@@ -340,8 +340,8 @@ static policy_ws_t policy_ws_layout(int max_n)
     L.h = take(np * 256 * 4);
     L.w1f = take(160 * 4); L.b1 = take(32 * 4); L.w2 = take(3072 * 4); L.b2 = take(32 * 4);
     L.fc1_b = take(256 * 4); L.w2t = take((size_t)PF2_IN * 128 * 4); L.fc2_b = take(128 * 4);
-    L.heads = take(258 * 4); L.scales = take(32);
-    L.conv_img = take(16384); L.w1s = take(256 * 4);
+    L.heads = take(258 * 4); L.scales = take(64);
+    L.conv_img = take(16384); L.w1s = take(256 * 4); L.conv1_img = take(6144);
     L.total = o;
     return L;
 }
@@ -432,6 +432,34 @@ __global__ void __launch_bounds__(1024) policy_prepare_kernel(const navgym_polic
     if (t < 256) {
         const int c = t >> 3, k = t & 7;
         ((float *)(ws + L.w1s))[t] = k < 5 ? w1f[c * 5 + k] * s_h_scale : (k == 5 ? b1[c] * s_h_scale : 0.0f);
+    }
+    // conv1 as a GEMM for policy_features_umma2_kernel: B1[n = 32 tap + c][k] = w1f[c][k - 2 tap] for
+    // 0 <= k - 2 tap <= 4, the bias at k = 9 (the A operand holds a constant there), else 0, times
+    // s_w1; K-major WITHOUT swizzle: 8-row x 16-byte core matrices, the two K cores of a row group
+    // 128 B apart (leading byte offset), row groups 256 B apart (stride byte offset); hi | lo
+    {
+        __shared__ float s_w1_scale;
+        if (t == 0) {
+            float m = 1e-30f;
+            for (int i = 0; i < 160; i++) m = fmaxf(m, fabsf(w1f[i]));
+            for (int c = 0; c < 32; c++) m = fmaxf(m, fabsf(b1[c]));
+            int e;
+            frexpf(m, &e);
+            s_w1_scale = ldexpf(1.0f, min(max(14 - e, -100), 100));
+            float *sc = (float *)(ws + L.scales);
+            sc[4] = 2048.0f;                                        // s_x: the scan inputs lie in [-0.5, 0.5]
+            sc[5] = s_h_scale / (2048.0f * s_w1_scale);             // conv1 accumulator -> A operand of conv2
+        }
+        __syncthreads();
+        __half *img1 = (__half *)(ws + L.conv1_img);
+        for (int i = t; i < 96 * 16; i += 1024) {
+            const int n = i >> 4, k = i & 15, tap = n >> 5, c = n & 31, kk = k - 2 * tap;
+            const float x = (kk >= 0 && kk <= 4) ? w1f[c * 5 + kk] * s_w1_scale : (k == 9 ? b1[c] * s_w1_scale : 0.0f);
+            const __half hi = __float2half_rn(x);
+            const uint32_t off = (uint32_t)(n >> 3) * 256u + (uint32_t)(k >> 3) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 7) * 2u;
+            img1[off >> 1] = hi;
+            img1[(3072u + off) >> 1] = __float2half_rn(x - __half2float(hi));
+        }
     }
     // conv2's weight as the B operand of policy_features_umma_kernel, byte for byte as it sits in
     // shared memory: hi | lo, each two K blocks of [32 co][64] f16, K index = 4 ci + tap (tap 3 =
