@@ -212,6 +212,7 @@ navgym_policy_t *navgym_policy_create(const navgym_policy_params_t *p, void *str
          policy_make_map(&pol->tm_wl, pol->ws + L.wl, 256, pg::BN) == 0;
     ok = ok && cudaFuncSetAttribute(fc1_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pg::SMEM_BYTES) == cudaSuccess &&
          cudaFuncSetAttribute(policy_features_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pc::SMEM_BYTES) == cudaSuccess &&
+         cudaFuncSetAttribute(policy_features_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pf::SMEM_BYTES) == cudaSuccess &&
          cudaFuncSetAttribute(fc2_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (PF2_IN * 128 + 64 * PF2_ROW) * (int)sizeof(float)) == cudaSuccess;
     if (ok) {
@@ -235,9 +236,16 @@ int navgym_policy_mean(navgym_policy_t *pol, const float *scan, const float *goa
     uint8_t *ws = pol->ws;
     const policy_ws_t &L = pol->L;
     const float *scales = (const float *)(ws + L.scales);
-    policy_features_umma_kernel<<<n < pol->sms ? n : pol->sms, pc::THREADS, pc::SMEM_BYTES, st>>>(
-        scan, n, (const uint4 *)(ws + L.conv_img), (const float *)(ws + L.w1s), (const float *)(ws + L.b2), scales,
-        (__half *)(ws + L.fh), (__half *)(ws + L.fl));
+    // front end: both convolutions on the tensor cores (2, default) or conv1 on the CUDA cores (1)
+    static const int front = env_int("NAVGYM_POLICY_FRONT", 2);
+    if (front == 2)
+        policy_features_umma2_kernel<<<n < pol->sms ? n : pol->sms, pf::THREADS, pf::SMEM_BYTES, st>>>(
+            scan, n, (const uint4 *)(ws + L.conv1_img), (const uint4 *)(ws + L.conv2_img), (const float *)(ws + L.b2), scales,
+            (__half *)(ws + L.fh), (__half *)(ws + L.fl));
+    else
+        policy_features_umma_kernel<<<n < pol->sms ? n : pol->sms, pc::THREADS, pc::SMEM_BYTES, st>>>(
+            scan, n, (const uint4 *)(ws + L.conv_img), (const float *)(ws + L.w1s), (const float *)(ws + L.b2), scales,
+            (__half *)(ws + L.fh), (__half *)(ws + L.fl));
     const int tiles = (n + pg::BM - 1) / pg::BM;
     fc1_umma_kernel<<<tiles < pol->sms ? tiles : pol->sms, pg::THREADS, pg::SMEM_BYTES, st>>>(
         pol->tm_fh, pol->tm_fl, pol->tm_wh, pol->tm_wl, (const float *)(ws + L.fc1_b), scales, (float *)(ws + L.h), n, tiles);

@@ -327,7 +327,7 @@ fc2_heads_kernel(const float *__restrict__ H, const float *__restrict__ goal, co
 // frames (env.py:647), transposes conv2 / fc2 for the kernels' access order, and chooses the two
 // power-of-two scales of the f16x3 scheme from bounds on the features and the fc1 weights.
 struct policy_ws_t {   // device workspace layout (byte offsets from the workspace base)
-    size_t fh, fl, wh, wl, h, w1f, b1, w2, b2, fc1_b, w2t, fc2_b, heads, scales, conv_img, w1s, conv1_img, total;
+    size_t fh, fl, wh, wl, h, w1f, b1, w2, b2, fc1_b, w2t, fc2_b, heads, scales, conv_img, w1s, conv1_img, conv2_img, total;
 };
 static policy_ws_t policy_ws_layout(int max_n)
 {
@@ -341,7 +341,7 @@ static policy_ws_t policy_ws_layout(int max_n)
     L.w1f = take(160 * 4); L.b1 = take(32 * 4); L.w2 = take(3072 * 4); L.b2 = take(32 * 4);
     L.fc1_b = take(256 * 4); L.w2t = take((size_t)PF2_IN * 128 * 4); L.fc2_b = take(128 * 4);
     L.heads = take(258 * 4); L.scales = take(64);
-    L.conv_img = take(16384); L.w1s = take(256 * 4); L.conv1_img = take(6144);
+    L.conv_img = take(16384); L.w1s = take(256 * 4); L.conv1_img = take(6144); L.conv2_img = take(12288);
     L.total = o;
     return L;
 }
@@ -433,32 +433,40 @@ __global__ void __launch_bounds__(1024) policy_prepare_kernel(const navgym_polic
         const int c = t >> 3, k = t & 7;
         ((float *)(ws + L.w1s))[t] = k < 5 ? w1f[c * 5 + k] * s_h_scale : (k == 5 ? b1[c] * s_h_scale : 0.0f);
     }
-    // conv1 as a GEMM for policy_features_umma2_kernel: B1[n = 32 tap + c][k] = w1f[c][k - 2 tap] for
-    // 0 <= k - 2 tap <= 4, the bias at k = 9 (the A operand holds a constant there), else 0, times
-    // s_w1; K-major WITHOUT swizzle: 8-row x 16-byte core matrices, the two K cores of a row group
-    // 128 B apart (leading byte offset), row groups 256 B apart (stride byte offset); hi | lo
+    // Operand images of policy_features_umma2_kernel, byte for byte as they sit in shared memory.
+    // conv1 as a GEMM per pedestrian, D1[pos][n = 3 c + tap] = conv1 output 2 pos - 1 + tap of channel c:
+    // the A operand row holds the 9 inputs 4 pos - 3 .. 4 pos + 5 (times 2048) at k = 0 .. 8, the constant
+    // 2048 at k = 9, and 32768 at k = 10 in row 0 / at k = 11 in row 127 only; so
+    //   B1[n][k] = w1f[c][k - 2 tap] s_w1 (0 <= k - 2 tap <= 4), b1[c] s_w1 (k = 9),
+    //              -32768 (k = 10 and tap 0, k = 11 and tap 2: the two conv1 outputs that are conv2's own
+    //              zero padding, q = -1 and q = 255, are driven far below zero and end as relu = 0), else 0,
+    // with s_w1 = s_h / 2048, i.e. the accumulator already carries the scale of conv2's A operand.
+    // K-major rows of 32 bytes in 8-row groups, 32-byte swizzle (16-byte piece ^ bit 2 of the row); hi | lo.
     {
-        __shared__ float s_w1_scale;
-        if (t == 0) {
-            float m = 1e-30f;
-            for (int i = 0; i < 160; i++) m = fmaxf(m, fabsf(w1f[i]));
-            for (int c = 0; c < 32; c++) m = fmaxf(m, fabsf(b1[c]));
-            int e;
-            frexpf(m, &e);
-            s_w1_scale = ldexpf(1.0f, min(max(14 - e, -100), 100));
-            float *sc = (float *)(ws + L.scales);
-            sc[4] = 2048.0f;                                        // s_x: the scan inputs lie in [-0.5, 0.5]
-            sc[5] = s_h_scale / (2048.0f * s_w1_scale);             // conv1 accumulator -> A operand of conv2
-        }
-        __syncthreads();
+        const float s_w1 = s_h_scale * (1.0f / 2048.0f);
         __half *img1 = (__half *)(ws + L.conv1_img);
         for (int i = t; i < 96 * 16; i += 1024) {
-            const int n = i >> 4, k = i & 15, tap = n >> 5, c = n & 31, kk = k - 2 * tap;
-            const float x = (kk >= 0 && kk <= 4) ? w1f[c * 5 + kk] * s_w1_scale : (k == 9 ? b1[c] * s_w1_scale : 0.0f);
+            const int n = i >> 4, k = i & 15, c = n / 3, tap = n - 3 * c, kk = k - 2 * tap;
+            float x = 0.0f;
+            if (kk >= 0 && kk <= 4 && k <= 8) x = w1f[c * 5 + kk] * s_w1;
+            else if (k == 9) x = b1[c] * s_w1;
+            else if ((k == 10 && tap == 0) || (k == 11 && tap == 2)) x = -32768.0f;
             const __half hi = __float2half_rn(x);
-            const uint32_t off = (uint32_t)(n >> 3) * 256u + (uint32_t)(k >> 3) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 7) * 2u;
+            const uint32_t off = (uint32_t)n * 32u + ((((uint32_t)k >> 3) ^ (((uint32_t)n >> 2) & 1u)) << 4) + ((uint32_t)k & 7u) * 2u;
             img1[off >> 1] = hi;
             img1[(3072u + off) >> 1] = __float2half_rn(x - __half2float(hi));
+        }
+        // conv2's weight for the same kernel: B2[co][k = 3 ci + tap] (no padded fourth tap), three K
+        // blocks of [32 co][32 k]: K-major rows of 64 bytes, 64-byte swizzle (piece ^ bits 1-2 of the row)
+        __half *img2 = (__half *)(ws + L.conv2_img);
+        for (int i = t; i < 32 * 96; i += 1024) {
+            const int co = i / 96, k = i - 96 * co, kb = k >> 5, kk = k & 31;
+            const float x = w2[co * 96 + k] * s_w2_scale;
+            const __half hi = __float2half_rn(x);
+            const uint32_t off = (uint32_t)kb * 2048u + (uint32_t)co * 64u + ((((uint32_t)kk >> 3) ^ (((uint32_t)co >> 1) & 3u)) << 4) +
+                                 ((uint32_t)kk & 7u) * 2u;
+            img2[off >> 1] = hi;
+            img2[(6144u + off) >> 1] = __float2half_rn(x - __half2float(hi));
         }
     }
     // conv2's weight as the B operand of policy_features_umma_kernel, byte for byte as it sits in
@@ -726,6 +734,242 @@ policy_features_umma_kernel(const float *__restrict__ scan, int n, const uint4 *
     tc_fence_before();
     __syncthreads();
     if (warp == pc::MMA_WARP) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ front end, both convolutions on the tensor cores
+// policy_features_umma2_kernel: conv1 is a GEMM too (M 128 positions x N 96 = 32 channels x 3 taps x
+// K 16: the 9 inputs a position's three conv1 outputs need, a bias column, two padding columns; see
+// policy_prepare_kernel), so the CUDA cores only convert: scan -> A1 (preprocess, split), D1 -> A2
+// (ReLU, split: D1's column order 3 c + tap IS conv2's K order, a thread's accumulator row goes
+// straight into its A2 row), D2 -> features.  Per pedestrian 3 + 18 tcgen05.mma (f16x3) and ~1000
+// instructions per position instead of ~1750.
+// Four worker groups of four warps (a warp reaches the TMEM lanes 32 (warp % 4) .. + 31 = its 32
+// positions) take pedestrians round robin and run them start to end:
+//   P1  the scan, clipped and centred (float64, env.py:627-629), into the group's staging row; every
+//       thread builds its A1 row -> arrive a1full -> [issuer: 3 MMAs into D1, commit d1full]
+//   P2  D1 from TMEM, ReLU, hi/lo split, into the A2 row (K = 96 in three 64-byte-swizzled K blocks;
+//       A1 lives in the first bytes of the same buffer: it has been consumed by then)
+//       -> arrive a2full -> [issuer: 18 MMAs into three accumulators that overwrite D1, commit d2full]
+//   P3  the three accumulators summed, bias, ReLU, feature scale, split, position-major store.
+// A group waits for its own MMAs twice per pedestrian; the other three groups fill the gaps.  One thread
+// (warp 16) issues every MMA, polling the groups' barriers in turn.
+namespace pf {
+constexpr int GROUPS = 4, THREADS = (4 * GROUPS + 1) * 32, MMA_WARP = 4 * GROUPS;
+constexpr uint32_t A2_HALF = 3 * 8192;                 // hi (or lo): 3 K blocks of [128][32] f16
+constexpr uint32_t GBUF = 2 * A2_HALF;                 // 48 KB per group; A1 = its first 8 KB (hi | lo, [128][16] f16 each)
+constexpr uint32_t A1_HALF = 4096;
+constexpr uint32_t B2_HALF = 3 * 2048, B1_HALF = 3072;
+constexpr uint32_t XS_FLOATS = 520;
+constexpr uint32_t OFF_B2 = GROUPS * GBUF, OFF_B1 = OFF_B2 + 2 * B2_HALF, OFF_XS = OFF_B1 + 2 * B1_HALF;
+constexpr uint32_t OFF_B2S = OFF_XS + GROUPS * XS_FLOATS * 4;   // conv2 bias, 32 floats
+constexpr uint32_t OFF_BAR = OFF_B2S + 128;
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;
+constexpr uint32_t IDESC1 = (1u << 4) | ((uint32_t)(96 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
+// K-major tile of 32-byte rows, 32-byte swizzle: 8-row groups 256 B apart, layout type 6
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr)
+{
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+}  // namespace pf
+
+__global__ void __launch_bounds__(pf::THREADS, 1)
+policy_features_umma2_kernel(const float *__restrict__ scan, int n, const uint4 *__restrict__ conv1_img,
+                             const uint4 *__restrict__ conv2_img, const float *__restrict__ b2,
+                             const float *__restrict__ scales, __half *__restrict__ out_hi, __half *__restrict__ out_lo)
+{
+    using namespace pg;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t base = smem_u32(sm);
+    const uint32_t bars = base + pf::OFF_BAR;            // group g: a1full, d1full, a2full, d2full at bars + 32 g
+    const uint32_t tmem_slot = bars + 32 * pf::GROUPS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int i = threadIdx.x; i < (int)(2 * pf::B2_HALF / 16); i += pf::THREADS) reinterpret_cast<uint4 *>(sm + pf::OFF_B2)[i] = conv2_img[i];
+    for (int i = threadIdx.x; i < (int)(2 * pf::B1_HALF / 16); i += pf::THREADS) reinterpret_cast<uint4 *>(sm + pf::OFF_B1)[i] = conv1_img[i];
+    for (int i = threadIdx.x; i < (int)(pf::GROUPS * pf::XS_FLOATS); i += pf::THREADS) reinterpret_cast<float *>(sm + pf::OFF_XS)[i] = 0.0f;
+    if (threadIdx.x < 32) reinterpret_cast<float *>(sm + pf::OFF_B2S)[threadIdx.x] = b2[threadIdx.x];
+    if (threadIdx.x == 0) {
+        for (int g = 0; g < pf::GROUPS; g++) {
+            mbar_init(bars + 32 * g, 128); mbar_init(bars + 32 * g + 8, 1);
+            mbar_init(bars + 32 * g + 16, 128); mbar_init(bars + 32 * g + 24, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == pf::MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the B operands were written with ordinary stores
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+    const int my_count = blockIdx.x < n ? (n - 1 - blockIdx.x) / gridDim.x + 1 : 0;   // pedestrians of this CTA
+
+    if (warp < pf::MMA_WARP) {
+        const int g = warp >> 2, q = warp & 3, tg = threadIdx.x & 127, pos = tg;
+        float *xs = reinterpret_cast<float *>(sm + pf::OFF_XS) + g * pf::XS_FLOATS;   // xs[3 + i] = input i; the rest stays 0
+        uint8_t *gb = sm + g * pf::GBUF;
+        const uint32_t a1full = bars + 32 * g, d1full = a1full + 8, a2full = a1full + 16, d2full = a1full + 24;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)g * 128u;
+        const float descale = scales[3], fscale = scales[0];
+        const float *b2s = reinterpret_cast<const float *>(sm + pf::OFF_B2S);
+        uint32_t par = 0;
+        for (int j = g; j < my_count; j += pf::GROUPS, par ^= 1) {
+            const int ped = blockIdx.x + j * gridDim.x;
+            // ---- P1
+            float raw[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) raw[i] = scan[(size_t)ped * 512 + tg + 128 * i];
+            if (j + pf::GROUPS < my_count && tg < 16)   // the next scan's 16 lines, on their way to L2 meanwhile
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(scan + (size_t)(blockIdx.x + (j + pf::GROUPS) * gridDim.x) * 512 + tg * 32));
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");   // everyone has built its A1 row from the previous scan
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const double r = fmin(fmax((double)raw[i], 0.0), 6.0);
+                xs[3 + tg + 128 * i] = (float)(r / 6.0 - 0.5);  // env.py:627-629, 648
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+            {
+                const float4 xa = *reinterpret_cast<const float4 *>(xs + 4 * pos), xb = *reinterpret_cast<const float4 *>(xs + 4 * pos + 4);
+                const float x8 = xs[4 * pos + 8];
+                uint32_t h[4], l[4], h8, l8;
+                split2(xa.x * 2048.0f, xa.y * 2048.0f, h[0], l[0]);
+                split2(xa.z * 2048.0f, xa.w * 2048.0f, h[1], l[1]);
+                split2(xb.x * 2048.0f, xb.y * 2048.0f, h[2], l[2]);
+                split2(xb.z * 2048.0f, xb.w * 2048.0f, h[3], l[3]);
+                split2(x8 * 2048.0f, 2048.0f, h8, l8);   // k = 8, and the bias column k = 9
+                const uint32_t padw = (pos == 0 ? 0x7800u : 0u) | (pos == 127 ? 0x78000000u : 0u);   // 32768 at k = 10 / k = 11
+                const uint32_t sw = ((uint32_t)pos >> 2) & 1u;
+                uint8_t *rowp = gb + pos * 32;
+                *reinterpret_cast<uint4 *>(rowp + ((0u ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4 *>(rowp + ((1u ^ sw) << 4)) = make_uint4(h8, padw, 0u, 0u);
+                *reinterpret_cast<uint4 *>(rowp + pf::A1_HALF + ((0u ^ sw) << 4)) = make_uint4(l[0], l[1], l[2], l[3]);
+                *reinterpret_cast<uint4 *>(rowp + pf::A1_HALF + ((1u ^ sw) << 4)) = make_uint4(l8, 0u, 0u, 0u);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // visible to the tensor core's reads
+            mbar_arrive(a1full);
+            // ---- P2
+            mbar_wait(d1full, par);
+            tc_fence_after();
+            {
+                const uint32_t sw = ((uint32_t)pos >> 1) & 3u;
+#pragma unroll
+                for (int cb = 0; cb < 3; cb++) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + cb * 32, v);
+                    uint8_t *rowp = gb + cb * 8192 + pos * 64;
+#pragma unroll
+                    for (int ch = 0; ch < 4; ch++) {
+                        uint32_t h[4], l[4];
+#pragma unroll
+                        for (int m = 0; m < 4; m++)
+                            split2(fmaxf(__uint_as_float(v[8 * ch + 2 * m]), 0.0f), fmaxf(__uint_as_float(v[8 * ch + 2 * m + 1]), 0.0f), h[m], l[m]);
+                        const uint32_t off = ((uint32_t)ch ^ sw) << 4;
+                        *reinterpret_cast<uint4 *>(rowp + off) = make_uint4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<uint4 *>(rowp + pf::A2_HALF + off) = make_uint4(l[0], l[1], l[2], l[3]);
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(a2full);
+            // ---- P3
+            mbar_wait(d2full, par);
+            tc_fence_after();
+            float acc[32];
+            {
+                uint32_t v[32];
+                tmem_ld32(taddr, v);
+#pragma unroll
+                for (int c = 0; c < 32; c++) acc[c] = __uint_as_float(v[c]);
+                tmem_ld32(taddr + 32, v);
+#pragma unroll
+                for (int c = 0; c < 32; c++) acc[c] += __uint_as_float(v[c]);
+                tmem_ld32(taddr + 64, v);   // hi x hi last
+#pragma unroll
+                for (int c = 0; c < 32; c++) acc[c] += __uint_as_float(v[c]);
+            }
+            tc_fence_before();   // ordered before the next a1full arrival: the next MMAs overwrite the accumulators
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+                const float a = fmaxf(fmaf(acc[c], descale, b2s[c]), 0.0f) * fscale;
+                const float b = fmaxf(fmaf(acc[c + 1], descale, b2s[c + 1]), 0.0f) * fscale;
+                split2(a, b, hi[c >> 1], lo[c >> 1]);
+            }
+            uint4 *oh = reinterpret_cast<uint4 *>(out_hi + (size_t)ped * 4096 + pos * 32);
+            uint4 *ol = reinterpret_cast<uint4 *>(out_lo + (size_t)ped * 4096 + pos * 32);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                oh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+                ol[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+            }
+        }
+    } else if (lane == 0) {
+        // ---- MMA issuer: the groups' barriers polled in turn
+        const uint32_t b1h = base + pf::OFF_B1, b1l = b1h + pf::B1_HALF, b2h = base + pf::OFF_B2, b2l = b2h + pf::B2_HALF;
+        int it[pf::GROUPS], stage[pf::GROUPS], cnt[pf::GROUPS];
+        int left = 2 * my_count;
+#pragma unroll
+        for (int g = 0; g < pf::GROUPS; g++) { it[g] = 0; stage[g] = 0; cnt[g] = my_count > g ? (my_count - g + pf::GROUPS - 1) / pf::GROUPS : 0; }
+        while (left > 0) {
+            const int before = left;
+#pragma unroll
+            for (int g = 0; g < pf::GROUPS; g++) {
+                if (it[g] >= cnt[g]) continue;
+                const uint32_t gbar = bars + 32 * g, gbuf = base + g * pf::GBUF, d = tmem_base + (uint32_t)g * 128u;
+                if (stage[g] == 0) {
+                    if (!pf::mbar_test(gbar, it[g] & 1)) continue;
+                    tc_fence_after();
+                    const uint64_t ah = pf::umma_desc_sw32(gbuf), al = pf::umma_desc_sw32(gbuf + pf::A1_HALF);
+                    umma_f16(d, al, pf::umma_desc_sw32(b1h), pf::IDESC1, 0);
+                    umma_f16(d, ah, pf::umma_desc_sw32(b1l), pf::IDESC1, 1);
+                    umma_f16(d, ah, pf::umma_desc_sw32(b1h), pf::IDESC1, 1);
+                    umma_commit(gbar + 8);
+                    stage[g] = 1;
+                } else {
+                    if (!pf::mbar_test(gbar + 16, it[g] & 1)) continue;
+                    tc_fence_after();
+#pragma unroll
+                    for (int ks = 0; ks < 6; ks++) {
+                        const uint32_t ko = (uint32_t)(ks >> 1) * 8192u + (uint32_t)(ks & 1) * 32u, kw = (uint32_t)(ks >> 1) * 2048u + (uint32_t)(ks & 1) * 32u;
+                        const uint64_t ah = umma_desc_sw64(gbuf + ko), al = umma_desc_sw64(gbuf + pf::A2_HALF + ko);
+                        const uint64_t wh = umma_desc_sw64(b2h + kw), wl = umma_desc_sw64(b2l + kw);
+                        umma_f16(d, al, wh, pf::IDESC2, ks != 0);
+                        umma_f16(d + 32, ah, wl, pf::IDESC2, ks != 0);
+                        umma_f16(d + 64, ah, wh, pf::IDESC2, ks != 0);
+                    }
+                    umma_commit(gbar + 24);
+                    stage[g] = 0;
+                    it[g]++;
+                }
+                left--;
+            }
+            if (left == before) __nanosleep(64);   // nothing was ready: leave the issue slots to the workers
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == pf::MMA_WARP) {
         __syncwarp();
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
