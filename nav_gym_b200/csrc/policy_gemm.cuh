@@ -457,16 +457,18 @@ __global__ void __launch_bounds__(1024) policy_prepare_kernel(const navgym_polic
             img1[(3072u + off) >> 1] = __float2half_rn(x - __half2float(hi));
         }
         // conv2's weight for the same kernel: B2[co][k = 3 ci + tap] (no padded fourth tap), three K
-        // blocks of [32 co][32 k]: K-major rows of 64 bytes, 64-byte swizzle (piece ^ bits 1-2 of the row)
+        // blocks of 64 rows -- [32 co][32 k] high parts, then the same rows' low parts, so that one
+        // N = 64 MMA multiplies an A tile by both: K-major rows of 64 bytes, 64-byte swizzle (piece ^
+        // bits 1-2 of the row)
         __half *img2 = (__half *)(ws + L.conv2_img);
         for (int i = t; i < 32 * 96; i += 1024) {
             const int co = i / 96, k = i - 96 * co, kb = k >> 5, kk = k & 31;
             const float x = w2[co * 96 + k] * s_w2_scale;
             const __half hi = __float2half_rn(x);
-            const uint32_t off = (uint32_t)kb * 2048u + (uint32_t)co * 64u + ((((uint32_t)kk >> 3) ^ (((uint32_t)co >> 1) & 3u)) << 4) +
+            const uint32_t off = (uint32_t)kb * 4096u + (uint32_t)co * 64u + ((((uint32_t)kk >> 3) ^ (((uint32_t)co >> 1) & 3u)) << 4) +
                                  ((uint32_t)kk & 7u) * 2u;
             img2[off >> 1] = hi;
-            img2[(6144u + off) >> 1] = __float2half_rn(x - __half2float(hi));
+            img2[(2048u + off) >> 1] = __float2half_rn(x - __half2float(hi));
         }
     }
     // conv2's weight as the B operand of policy_features_umma_kernel, byte for byte as it sits in
@@ -745,31 +747,47 @@ policy_features_umma_kernel(const float *__restrict__ scan, int n, const uint4 *
 // K 16: the 9 inputs a position's three conv1 outputs need, a bias column, two padding columns; see
 // policy_prepare_kernel), so the CUDA cores only convert: scan -> A1 (preprocess, split), D1 -> A2
 // (ReLU, split: D1's column order 3 c + tap IS conv2's K order, a thread's accumulator row goes
-// straight into its A2 row), D2 -> features.  Per pedestrian 3 + 18 tcgen05.mma (f16x3) and ~1000
+// straight into its A2 row), D2 -> features.  Per pedestrian 3 + 12 tcgen05.mma (f16x3) and ~1000
 // instructions per position instead of ~1750.
-// Four worker groups of four warps (a warp reaches the TMEM lanes 32 (warp % 4) .. + 31 = its 32
-// positions) take pedestrians round robin and run them start to end:
-//   P1  the scan, clipped and centred (float64, env.py:627-629), into the group's staging row; every
-//       thread builds its A1 row -> arrive a1full -> [issuer: 3 MMAs into D1, commit d1full]
-//   P2  D1 from TMEM, ReLU, hi/lo split, into the A2 row (K = 96 in three 64-byte-swizzled K blocks;
+// NAVGYM_PF_GROUPS (3) groups of NAVGYM_PF_GWARPS (8) worker warps + one issuing warp each take
+// pedestrians round robin and run them start to end.  A warp reaches the TMEM lanes 32 (warp % 4) .. + 31
+// = 32 positions; with 8 worker warps the two that share a quarter split the columns.
+//   P1a the scan, clipped and centred (float64, env.py:627-629), into the group's staging row
+//   P1b every thread builds its piece of the A1 rows -> arrive a1full -> 3 MMAs into D1, commit d1full
+//   P2  D1 from TMEM, ReLU, hi/lo split, into the A2 rows (K = 96 in three 64-byte-swizzled K blocks;
 //       A1 lives in the first bytes of the same buffer: it has been consumed by then)
-//       -> arrive a2full -> [issuer: 18 MMAs into three accumulators that overwrite D1, commit d2full]
-//   P3  the three accumulators summed, bias, ReLU, feature scale, split, position-major store.
-// A group waits for its own MMAs twice per pedestrian; the other three groups fill the gaps.  One thread
-// (warp 16) issues every MMA, polling the groups' barriers in turn.
+//       -> arrive a2full -> 12 MMAs (per K step: A hi x (B hi | B lo) as one N = 64 MMA, A lo x B hi)
+//       into accumulators that overwrite D1, commit d2full
+//   P3a the three accumulators summed into registers; P3b bias, ReLU, feature scale, split, store.
+// Order in the steady state: P2(i) | P1a(i + 1) behind conv2's MMAs | P3a(i) | P1b(i + 1) | P3b(i)
+// behind the next conv1's MMAs.  What bounds the kernel is the NUMBER of MMAs: a tcgen05.mma of this
+// size (N 32 .. 96) costs the tensor pipe ~45-50 cycles whatever N and whichever accumulator it adds
+// to, and one thread issues one every ~80 cycles at best (tools/umma_probe.cu) -- so every group has
+// its own issuing thread (a single one for all groups kept the kernel at 15 MMAs x ~150 cycles per
+// pedestrian: 0.39 ms), with the operand descriptors computed once.
+#ifndef NAVGYM_PF_GROUPS
+#define NAVGYM_PF_GROUPS 3   // 3 x 8 worker warps: 0.32 ms for 40 960 pedestrians; 4 x 4: 0.34 ms
+#endif
+#ifndef NAVGYM_PF_GWARPS
+#define NAVGYM_PF_GWARPS 8
+#endif
 namespace pf {
-constexpr int GROUPS = 4, THREADS = (4 * GROUPS + 1) * 32, MMA_WARP = 4 * GROUPS;
+constexpr int GROUPS = NAVGYM_PF_GROUPS, GWARPS = NAVGYM_PF_GWARPS, SUBS = GWARPS / 4, GTHREADS = 32 * GWARPS;
+constexpr int WORKERS = GROUPS * GTHREADS, THREADS = WORKERS + 32 * GROUPS;   // + one issuing warp per group
+static_assert(GWARPS == 4 || GWARPS == 8, "worker warps per group");
+static_assert(THREADS <= 1024 && GROUPS * 128 <= 512, "threads / TMEM columns");
 constexpr uint32_t A2_HALF = 3 * 8192;                 // hi (or lo): 3 K blocks of [128][32] f16
 constexpr uint32_t GBUF = 2 * A2_HALF;                 // 48 KB per group; A1 = its first 8 KB (hi | lo, [128][16] f16 each)
 constexpr uint32_t A1_HALF = 4096;
-constexpr uint32_t B2_HALF = 3 * 2048, B1_HALF = 3072;
+constexpr uint32_t B2_BYTES = 3 * 4096, B1_HALF = 3072;
 constexpr uint32_t XS_FLOATS = 520;
-constexpr uint32_t OFF_B2 = GROUPS * GBUF, OFF_B1 = OFF_B2 + 2 * B2_HALF, OFF_XS = OFF_B1 + 2 * B1_HALF;
+constexpr uint32_t OFF_B2 = GROUPS * GBUF, OFF_B1 = OFF_B2 + B2_BYTES, OFF_XS = OFF_B1 + 2 * B1_HALF;
 constexpr uint32_t OFF_B2S = OFF_XS + GROUPS * XS_FLOATS * 4;   // conv2 bias, 32 floats
 constexpr uint32_t OFF_BAR = OFF_B2S + 128;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;
 constexpr uint32_t IDESC1 = (1u << 4) | ((uint32_t)(96 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);    // N 32: A lo x B hi
+constexpr uint32_t IDESC2W = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // N 64: A hi x (B hi | B lo)
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
 // K-major tile of 32-byte rows, 32-byte swizzle: 8-row groups 256 B apart, layout type 6
 __device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr)
@@ -777,17 +795,29 @@ __device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr)
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
 }
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
 {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\t"
-                 "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                 "selp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 }  // namespace pf
 
+#ifdef NAVGYM_PF_PROF
+// per-phase cycle sums of the groups' first threads (tools/front_prof.py builds with -DNAVGYM_PF_PROF)
+__device__ unsigned long long g_pf_prof[16];
+extern "C" void navgym_pf_prof_read(unsigned long long *out, int reset)
+{
+    cudaMemcpyFromSymbol(out, g_pf_prof, sizeof(g_pf_prof));
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_pf_prof, z, sizeof(z)); }
+}
+#define PF_T(i) do { if (issuer) { const long long _n = clock64(); atomicAdd(&g_pf_prof[i], (unsigned long long)(_n - _pt)); _pt = _n; } } while (0)
+#else
+#define PF_T(i)
+#endif
 __global__ void __launch_bounds__(pf::THREADS, 1)
 policy_features_umma2_kernel(const float *__restrict__ scan, int n, const uint4 *__restrict__ conv1_img,
                              const uint4 *__restrict__ conv2_img, const float *__restrict__ b2,
@@ -801,18 +831,18 @@ policy_features_umma2_kernel(const float *__restrict__ scan, int n, const uint4 
     const uint32_t tmem_slot = bars + 32 * pf::GROUPS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    for (int i = threadIdx.x; i < (int)(2 * pf::B2_HALF / 16); i += pf::THREADS) reinterpret_cast<uint4 *>(sm + pf::OFF_B2)[i] = conv2_img[i];
+    for (int i = threadIdx.x; i < (int)(pf::B2_BYTES / 16); i += pf::THREADS) reinterpret_cast<uint4 *>(sm + pf::OFF_B2)[i] = conv2_img[i];
     for (int i = threadIdx.x; i < (int)(2 * pf::B1_HALF / 16); i += pf::THREADS) reinterpret_cast<uint4 *>(sm + pf::OFF_B1)[i] = conv1_img[i];
     for (int i = threadIdx.x; i < (int)(pf::GROUPS * pf::XS_FLOATS); i += pf::THREADS) reinterpret_cast<float *>(sm + pf::OFF_XS)[i] = 0.0f;
     if (threadIdx.x < 32) reinterpret_cast<float *>(sm + pf::OFF_B2S)[threadIdx.x] = b2[threadIdx.x];
     if (threadIdx.x == 0) {
         for (int g = 0; g < pf::GROUPS; g++) {
-            mbar_init(bars + 32 * g, 128); mbar_init(bars + 32 * g + 8, 1);
-            mbar_init(bars + 32 * g + 16, 128); mbar_init(bars + 32 * g + 24, 1);
+            mbar_init(bars + 32 * g, pf::GTHREADS); mbar_init(bars + 32 * g + 8, 1);
+            mbar_init(bars + 32 * g + 16, pf::GTHREADS); mbar_init(bars + 32 * g + 24, 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == pf::MMA_WARP) {
+    if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -823,67 +853,103 @@ policy_features_umma2_kernel(const float *__restrict__ scan, int n, const uint4 
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
     const int my_count = blockIdx.x < n ? (n - 1 - blockIdx.x) / gridDim.x + 1 : 0;   // pedestrians of this CTA
-
-    if (warp < pf::MMA_WARP) {
-        const int g = warp >> 2, q = warp & 3, tg = threadIdx.x & 127, pos = tg;
+    if (warp < pf::GROUPS * pf::GWARPS) {
+        const int g = warp / pf::GWARPS, wg = warp % pf::GWARPS, q = wg & 3, sub = wg >> 2, tg = threadIdx.x - g * pf::GTHREADS, pos = q * 32 + lane;
+        constexpr int SUBS = pf::SUBS, GT = pf::GTHREADS, PER = 512 / GT, NCOL = 96 / SUBS, NCH = 32 / SUBS;
         float *xs = reinterpret_cast<float *>(sm + pf::OFF_XS) + g * pf::XS_FLOATS;   // xs[3 + i] = input i; the rest stays 0
         uint8_t *gb = sm + g * pf::GBUF;
         const uint32_t a1full = bars + 32 * g, d1full = a1full + 8, a2full = a1full + 16, d2full = a1full + 24;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)g * 128u;
+        const uint32_t taddr = tmem_base + (uint32_t)g * 128u + ((uint32_t)(q * 32) << 16);
         const float descale = scales[3], fscale = scales[0];
         const float *b2s = reinterpret_cast<const float *>(sm + pf::OFF_B2S);
-        uint32_t par = 0;
-        for (int j = g; j < my_count; j += pf::GROUPS, par ^= 1) {
-            const int ped = blockIdx.x + j * gridDim.x;
-            // ---- P1
-            float raw[4];
+#ifdef NAVGYM_PF_PROF
+        const bool issuer = tg == 0;
+#endif
+        // P1a: a scan (loaded into registers a phase earlier), clipped and centred, into the staging row
+        // (barriers on both sides)
+        auto load_scan = [&](int p, float (&raw)[PER]) {
+#ifdef NAVGYM_PF_NOLOAD   // timing experiment: one pedestrian's scan for all (L1-resident)
+            p = 0;
+#endif
 #pragma unroll
-            for (int i = 0; i < 4; i++) raw[i] = scan[(size_t)ped * 512 + tg + 128 * i];
-            if (j + pf::GROUPS < my_count && tg < 16)   // the next scan's 16 lines, on their way to L2 meanwhile
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(scan + (size_t)(blockIdx.x + (j + pf::GROUPS) * gridDim.x) * 512 + tg * 32));
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");   // everyone has built its A1 row from the previous scan
+            for (int i = 0; i < PER; i++) raw[i] = scan[(size_t)p * 512 + tg + GT * i];
+        };
+        auto stage_scan = [&](const float (&raw)[PER]) {
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(GT) : "memory");   // everyone has built its A1 piece from the previous scan
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
+            for (int i = 0; i < PER; i++) {
+                // env.py:627-629, 648: clip(scan, 0, 6) / 6 - 0.5 in float64, then float32.  One fma
+                // instead of the division: within 1.2e-16 of the quotient form, which can move the
+                // float32 rounding for about one input in 10^8 (by one float32 ulp)
                 const double r = fmin(fmax((double)raw[i], 0.0), 6.0);
-                xs[3 + tg + 128 * i] = (float)(r / 6.0 - 0.5);  // env.py:627-629, 648
+                xs[3 + tg + GT * i] = (float)fma(r, 1.0 / 6.0, -0.5);
             }
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
-            {
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(GT) : "memory");
+        };
+        // P1b: this thread's piece of A1 row `pos` (k 0-7 | k 8, the bias and padding columns; with 8
+        // warps one piece each) -> arrive a1full
+        auto build_a1 = [&]() {
+            const uint32_t sw = ((uint32_t)pos >> 2) & 1u;
+            uint8_t *rowp = gb + pos * 32;
+            if (SUBS == 1 || sub == 0) {
                 const float4 xa = *reinterpret_cast<const float4 *>(xs + 4 * pos), xb = *reinterpret_cast<const float4 *>(xs + 4 * pos + 4);
-                const float x8 = xs[4 * pos + 8];
-                uint32_t h[4], l[4], h8, l8;
+                uint32_t h[4], l[4];
                 split2(xa.x * 2048.0f, xa.y * 2048.0f, h[0], l[0]);
                 split2(xa.z * 2048.0f, xa.w * 2048.0f, h[1], l[1]);
                 split2(xb.x * 2048.0f, xb.y * 2048.0f, h[2], l[2]);
                 split2(xb.z * 2048.0f, xb.w * 2048.0f, h[3], l[3]);
-                split2(x8 * 2048.0f, 2048.0f, h8, l8);   // k = 8, and the bias column k = 9
-                const uint32_t padw = (pos == 0 ? 0x7800u : 0u) | (pos == 127 ? 0x78000000u : 0u);   // 32768 at k = 10 / k = 11
-                const uint32_t sw = ((uint32_t)pos >> 2) & 1u;
-                uint8_t *rowp = gb + pos * 32;
                 *reinterpret_cast<uint4 *>(rowp + ((0u ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<uint4 *>(rowp + ((1u ^ sw) << 4)) = make_uint4(h8, padw, 0u, 0u);
                 *reinterpret_cast<uint4 *>(rowp + pf::A1_HALF + ((0u ^ sw) << 4)) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+            if (SUBS == 1 || sub == 1) {
+                uint32_t h8, l8;
+                split2(xs[4 * pos + 8] * 2048.0f, 2048.0f, h8, l8);   // k = 8, and the bias column k = 9
+                const uint32_t padw = (pos == 0 ? 0x7800u : 0u) | (pos == 127 ? 0x78000000u : 0u);   // 32768 at k = 10 / k = 11
+                *reinterpret_cast<uint4 *>(rowp + ((1u ^ sw) << 4)) = make_uint4(h8, padw, 0u, 0u);
                 *reinterpret_cast<uint4 *>(rowp + pf::A1_HALF + ((1u ^ sw) << 4)) = make_uint4(l8, 0u, 0u, 0u);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // visible to the tensor core's reads
             mbar_arrive(a1full);
-            // ---- P2
+        };
+        float raw[PER];
+        if (g < my_count) {
+            load_scan(blockIdx.x + g * gridDim.x, raw);
+            stage_scan(raw);
+            build_a1();
+        }
+#ifdef NAVGYM_PF_PROF
+        long long _pt = clock64();
+#endif
+        uint8_t *stg = gb + 2 * pf::A1_HALF;   // feature tile of the pedestrian just finished: hi 8 KB | lo 8 KB, behind A1
+        uint32_t par = 0;
+        for (int j = g; j < my_count; j += pf::GROUPS, par ^= 1) {
+            const int ped = blockIdx.x + j * gridDim.x;
+            const bool more = j + pf::GROUPS < my_count;
+            PF_T(7);
+            if (more) load_scan(blockIdx.x + (j + pf::GROUPS) * gridDim.x, raw);   // lands while P2 runs
+            if (j != g) {   // the previous feature tile has left shared memory before P2 writes over it
+                if (tg == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(GT) : "memory");
+            }
+            // ---- P2: columns NCOL sub .. of D1 = K indices of A2
             mbar_wait(d1full, par);
             tc_fence_after();
+            PF_T(0);   // wait for conv1's MMAs
             {
                 const uint32_t sw = ((uint32_t)pos >> 1) & 3u;
 #pragma unroll
-                for (int cb = 0; cb < 3; cb++) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + cb * 32, v);
-                    uint8_t *rowp = gb + cb * 8192 + pos * 64;
+                for (int b = 0; b < NCOL / 16; b++) {
+                    const int c0 = NCOL * sub + 16 * b;            // first column; K block c0 / 32, pieces (c0 % 32) / 8 and the next
+                    uint32_t v[16];
+                    pf::tmem_ld16(taddr + c0, v);
+                    uint8_t *rowp = gb + (c0 >> 5) * 8192 + pos * 64;
 #pragma unroll
-                    for (int ch = 0; ch < 4; ch++) {
+                    for (int c = 0; c < 2; c++) {
                         uint32_t h[4], l[4];
 #pragma unroll
                         for (int m = 0; m < 4; m++)
-                            split2(fmaxf(__uint_as_float(v[8 * ch + 2 * m]), 0.0f), fmaxf(__uint_as_float(v[8 * ch + 2 * m + 1]), 0.0f), h[m], l[m]);
-                        const uint32_t off = ((uint32_t)ch ^ sw) << 4;
+                            split2(fmaxf(__uint_as_float(v[8 * c + 2 * m]), 0.0f), fmaxf(__uint_as_float(v[8 * c + 2 * m + 1]), 0.0f), h[m], l[m]);
+                        const uint32_t off = ((uint32_t)(((c0 & 31) >> 3) + c) ^ sw) << 4;
                         *reinterpret_cast<uint4 *>(rowp + off) = make_uint4(h[0], h[1], h[2], h[3]);
                         *reinterpret_cast<uint4 *>(rowp + pf::A2_HALF + off) = make_uint4(l[0], l[1], l[2], l[3]);
                     }
@@ -892,84 +958,101 @@ policy_features_umma2_kernel(const float *__restrict__ scan, int n, const uint4 
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             tc_fence_before();
             mbar_arrive(a2full);
-            // ---- P3
+            PF_T(1);   // P2
+            // ---- P1a of the next pedestrian, in the shadow of conv2's MMAs
+            if (more) stage_scan(raw);
+            PF_T(4);   // P1a
+            // ---- P3a: channels NCH sub .. of the three accumulators (small products first)
             mbar_wait(d2full, par);
             tc_fence_after();
-            float acc[32];
-            {
-                uint32_t v[32];
-                tmem_ld32(taddr, v);
+            PF_T(5);   // rest of the wait for conv2's MMAs
+            float acc[NCH];
 #pragma unroll
-                for (int c = 0; c < 32; c++) acc[c] = __uint_as_float(v[c]);
-                tmem_ld32(taddr + 32, v);
+            for (int b = 0; b < NCH / 16; b++) {
+                uint32_t v[16];
+                pf::tmem_ld16(taddr + 32 + NCH * sub + 16 * b, v);
 #pragma unroll
-                for (int c = 0; c < 32; c++) acc[c] += __uint_as_float(v[c]);
-                tmem_ld32(taddr + 64, v);   // hi x hi last
+                for (int c = 0; c < 16; c++) acc[16 * b + c] = __uint_as_float(v[c]);
+                pf::tmem_ld16(taddr + 64 + NCH * sub + 16 * b, v);
 #pragma unroll
-                for (int c = 0; c < 32; c++) acc[c] += __uint_as_float(v[c]);
+                for (int c = 0; c < 16; c++) acc[16 * b + c] += __uint_as_float(v[c]);
+                pf::tmem_ld16(taddr + NCH * sub + 16 * b, v);
+#pragma unroll
+                for (int c = 0; c < 16; c++) acc[16 * b + c] += __uint_as_float(v[c]);
             }
-            tc_fence_before();   // ordered before the next a1full arrival: the next MMAs overwrite the accumulators
-            uint32_t hi[16], lo[16];
+            tc_fence_before();   // ordered before the a1full arrival below: the next MMAs overwrite the accumulators
+            PF_T(6);   // P3a
+            // ---- P1b of the next pedestrian (conv2's MMAs have read A2: its first bytes take A1)
+            if (more) build_a1();
+            PF_T(8);   // P1b
+            // ---- P3b: bias, ReLU, feature scale, split, position-major store -- in the shadow of conv1's MMAs
+            uint32_t hi[NCH / 2], lo[NCH / 2];
 #pragma unroll
-            for (int c = 0; c < 32; c += 2) {
-                const float a = fmaxf(fmaf(acc[c], descale, b2s[c]), 0.0f) * fscale;
-                const float b = fmaxf(fmaf(acc[c + 1], descale, b2s[c + 1]), 0.0f) * fscale;
+            for (int c = 0; c < NCH; c += 2) {
+                const float a = fmaxf(fmaf(acc[c], descale, b2s[NCH * sub + c]), 0.0f) * fscale;
+                const float b = fmaxf(fmaf(acc[c + 1], descale, b2s[NCH * sub + c + 1]), 0.0f) * fscale;
                 split2(a, b, hi[c >> 1], lo[c >> 1]);
             }
-            uint4 *oh = reinterpret_cast<uint4 *>(out_hi + (size_t)ped * 4096 + pos * 32);
-            uint4 *ol = reinterpret_cast<uint4 *>(out_lo + (size_t)ped * 4096 + pos * 32);
+            // the 128 x 32 tile is contiguous in global memory (position-major): staged in shared memory
+            // and written by two bulk copies of 8 KB (a thread's own 64-byte rows as STG.128 reached
+            // only a quarter of the store bandwidth: 16 bytes per lane at a 64-byte stride)
+            uint4 *sh = reinterpret_cast<uint4 *>(stg + pos * 64 + NCH * sub * 2);
+            uint4 *sl = reinterpret_cast<uint4 *>(stg + 8192 + pos * 64 + NCH * sub * 2);
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                oh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-                ol[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+            for (int i = 0; i < NCH / 8; i++) {
+                sh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+                sl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(GT) : "memory");
+            if (tg == 0) {
+#ifndef NAVGYM_PF_NOSTORE
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 8192;"
+                             ::"l"(out_hi + (size_t)ped * 4096), "r"(smem_u32(stg)) : "memory");
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 8192;"
+                             ::"l"(out_lo + (size_t)ped * 4096), "r"(smem_u32(stg + 8192)) : "memory");
+#endif
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         }
+        if (tg == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the last tile is on its way out
     } else if (lane == 0) {
-        // ---- MMA issuer: the groups' barriers polled in turn
-        const uint32_t b1h = base + pf::OFF_B1, b1l = b1h + pf::B1_HALF, b2h = base + pf::OFF_B2, b2l = b2h + pf::B2_HALF;
-        int it[pf::GROUPS], stage[pf::GROUPS], cnt[pf::GROUPS];
-        int left = 2 * my_count;
+        // ---- the group's MMA issuer; every operand descriptor is loop-invariant
+        const int g = warp - pf::GROUPS * pf::GWARPS;
+        const uint32_t gbuf = base + g * pf::GBUF, dcol = tmem_base + (uint32_t)g * 128u;
+        const uint32_t a1full = bars + 32 * g, d1full = a1full + 8, a2full = a1full + 16, d2full = a1full + 24;
+        const uint32_t b1h = base + pf::OFF_B1, b2w = base + pf::OFF_B2;
+        const uint64_t a1h = pf::umma_desc_sw32(gbuf), a1l = pf::umma_desc_sw32(gbuf + pf::A1_HALF);
+        const uint64_t w1h = pf::umma_desc_sw32(b1h), w1l = pf::umma_desc_sw32(b1h + pf::B1_HALF);
+        uint64_t ah[6], al[6], w2[6];
 #pragma unroll
-        for (int g = 0; g < pf::GROUPS; g++) { it[g] = 0; stage[g] = 0; cnt[g] = my_count > g ? (my_count - g + pf::GROUPS - 1) / pf::GROUPS : 0; }
-        while (left > 0) {
-            const int before = left;
+        for (int ks = 0; ks < 6; ks++) {
+            const uint32_t ko = (uint32_t)(ks >> 1) * 8192u + (uint32_t)(ks & 1) * 32u, kw = (uint32_t)(ks >> 1) * 4096u + (uint32_t)(ks & 1) * 32u;
+            ah[ks] = umma_desc_sw64(gbuf + ko);
+            al[ks] = umma_desc_sw64(gbuf + pf::A2_HALF + ko);
+            w2[ks] = umma_desc_sw64(b2w + kw);   // 64 rows: high parts, then low parts
+        }
+        uint32_t par = 0;
+        for (int j = g; j < my_count; j += pf::GROUPS, par ^= 1) {
+            mbar_wait(a1full, par);
+            tc_fence_after();
+            umma_f16(dcol, a1l, w1h, pf::IDESC1, 0);
+            umma_f16(dcol, a1h, w1l, pf::IDESC1, 1);
+            umma_f16(dcol, a1h, w1h, pf::IDESC1, 1);
+            umma_commit(d1full);
+            mbar_wait(a2full, par);
+            tc_fence_after();
 #pragma unroll
-            for (int g = 0; g < pf::GROUPS; g++) {
-                if (it[g] >= cnt[g]) continue;
-                const uint32_t gbar = bars + 32 * g, gbuf = base + g * pf::GBUF, d = tmem_base + (uint32_t)g * 128u;
-                if (stage[g] == 0) {
-                    if (!pf::mbar_test(gbar, it[g] & 1)) continue;
-                    tc_fence_after();
-                    const uint64_t ah = pf::umma_desc_sw32(gbuf), al = pf::umma_desc_sw32(gbuf + pf::A1_HALF);
-                    umma_f16(d, al, pf::umma_desc_sw32(b1h), pf::IDESC1, 0);
-                    umma_f16(d, ah, pf::umma_desc_sw32(b1l), pf::IDESC1, 1);
-                    umma_f16(d, ah, pf::umma_desc_sw32(b1h), pf::IDESC1, 1);
-                    umma_commit(gbar + 8);
-                    stage[g] = 1;
-                } else {
-                    if (!pf::mbar_test(gbar + 16, it[g] & 1)) continue;
-                    tc_fence_after();
-#pragma unroll
-                    for (int ks = 0; ks < 6; ks++) {
-                        const uint32_t ko = (uint32_t)(ks >> 1) * 8192u + (uint32_t)(ks & 1) * 32u, kw = (uint32_t)(ks >> 1) * 2048u + (uint32_t)(ks & 1) * 32u;
-                        const uint64_t ah = umma_desc_sw64(gbuf + ko), al = umma_desc_sw64(gbuf + pf::A2_HALF + ko);
-                        const uint64_t wh = umma_desc_sw64(b2h + kw), wl = umma_desc_sw64(b2l + kw);
-                        umma_f16(d, al, wh, pf::IDESC2, ks != 0);
-                        umma_f16(d + 32, ah, wl, pf::IDESC2, ks != 0);
-                        umma_f16(d + 64, ah, wh, pf::IDESC2, ks != 0);
-                    }
-                    umma_commit(gbar + 24);
-                    stage[g] = 0;
-                    it[g]++;
-                }
-                left--;
+            for (int ks = 0; ks < 6; ks++) {
+                umma_f16(dcol, ah[ks], w2[ks], pf::IDESC2W, ks != 0);        // columns 0-31 hi x hi, 32-63 hi x lo
+                umma_f16(dcol + 64, al[ks], w2[ks], pf::IDESC2, ks != 0);    // columns 64-95 lo x hi
             }
-            if (left == before) __nanosleep(64);   // nothing was ready: leave the issue slots to the workers
+            umma_commit(d2full);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == pf::MMA_WARP) {
+    if (warp == 0) {
         __syncwarp();
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
