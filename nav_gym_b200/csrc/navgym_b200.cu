@@ -298,11 +298,8 @@ int navgym_agent_scan_batch(const navgym_scan_args_t *args, void *stream)
     // crowd mode: one thread per other agent stages its footprint in a fixed shared-memory list
     const bool crowd = !args->segs && args->robot_state;
     if (crowd && args->agents_per_env > NAVGYM_SCAN_AGENTS) return (int)cudaErrorInvalidValue;
-    const int agents = args->num_envs * args->agents_per_env;
-    if ((crowd || !args->segs || args->max_seg <= NAVGYM_SCAN_SEGS) && args->env_mask)
-        agent_scan_kernel<true><<<(agents + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*args);
-    else if (crowd || !args->segs || args->max_seg <= NAVGYM_SCAN_SEGS)
-        agent_scan_kernel<false><<<agents, 128, 0, (cudaStream_t)stream>>>(*args);
+    if (crowd || !args->segs || args->max_seg <= NAVGYM_SCAN_SEGS)
+        agent_scan_kernel<<<args->num_envs * args->agents_per_env, 128, 0, (cudaStream_t)stream>>>(*args);
     else   // longer segment lists: every segment against every beam, straight from global memory
         agent_scan_generic_kernel<<<args->num_envs * args->agents_per_env, 128, 0, (cudaStream_t)stream>>>(*args);
     g_launches++;

@@ -211,36 +211,16 @@ __device__ __forceinline__ void agent_scan_one(const navgym_scan_args_t &a, cons
     }
 }
 
-// MASKED = false: CTA b scans agent b.  MASKED = true (env_mask given: the first scans of respawned
-// pedestrians, ~1 % of the environments per step): CTA b looks at agents 128 b .. 128 b + 127, lists
-// those of masked environments and scans them one after the other -- 1/128 of the CTAs to launch and
-// retire (a grid of one CTA per agent spent 44 us per step on CTAs that exit at once).
-template <bool MASKED>
+// One CTA per agent; CTAs of unmasked environments / dead slots exit at once.  (Round 2 tried one CTA
+// per 128 consecutive agents that lists the masked ones and scans them in turn for the ~1 % masked
+// launches: an environment's agents are consecutive, so its ten scans ran one after the other in one
+// CTA and the crowd step lost 0.23 ms; the full grid costs 25-44 us.)
 __global__ void __launch_bounds__(128, NAVGYM_AGENT_MIN_CTAS) agent_scan_kernel(const navgym_scan_args_t a)
 {
     __shared__ float4 near_segs[NAVGYM_SCAN_SEGS];
     __shared__ int4 near_win[NAVGYM_SCAN_SEGS];
     __shared__ int n_near;
-    if (!MASKED) {
-        agent_scan_one(a, (int)blockIdx.x, near_segs, near_win, n_near);
-        return;
-    }
-    __shared__ int todo[128];
-    __shared__ int n_todo;
-    if (threadIdx.x == 0) n_todo = 0;
-    __syncthreads();
-    const int n = (int)blockIdx.x * 128 + (int)threadIdx.x;
-    if (n < a.num_envs * a.agents_per_env) {
-        const int e = n / a.agents_per_env, slot = n - e * a.agents_per_env;
-        const int live = a.nagent ? min(a.nagent[e], a.agents_per_env) : a.agents_per_env;
-        if (a.env_mask[e] && slot < live) todo[atomicAdd(&n_todo, 1)] = n;
-    }
-    __syncthreads();
-    const int cnt = n_todo;
-    for (int i = 0; i < cnt; i++) {
-        agent_scan_one(a, todo[i], near_segs, near_win, n_near);
-        __syncthreads();   // the next agent resets the segment list
-    }
+    agent_scan_one(a, (int)blockIdx.x, near_segs, near_win, n_near);
 }
 
 // ------------------------------------------------------------------ pedestrian routes
