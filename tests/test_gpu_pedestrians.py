@@ -407,3 +407,74 @@ def test_respawn_follows_the_map_drawn_at_auto_reset():
             checked += 1
         env.done.zero_()               # consumed: the loop's next act() must not adopt again
     assert checked > 20 and moved > 5
+
+
+@pytest.mark.parametrize('agent_name', ['Human', 'KetiRobot'])
+def test_agent_scan_beam_windows_and_long_segment_lists(agent_name):
+    """The pedestrian-lidar kernel evaluates a segment only on the beams of its angular window: against
+    the oracle's all-beams loop on segments chosen to stress the window arithmetic -- touching the agent,
+    behind it (across the +-pi seam of the bearing), spanning more than half a turn, degenerate (zero
+    length), far out of range -- for the 180 degree / 6 m pedestrian lidar and the 360 degree / 25 m one
+    (whose windows wrap around the beam table).  The same list padded to more slots than the kernel
+    stages in shared memory takes the fallback kernel (every segment against every beam): identical."""
+    from oracle import oracle as orc
+    import synth
+    from nav_gym_b200 import robot as R
+    from nav_gym_b200.batched_env import MapPool
+    from nav_gym_b200.pedestrians import AgentScanner
+    agent = getattr(R, agent_name)
+    rng = np.random.RandomState(11)
+    m = synth.indoor_map(rng, cells=60, iterations=40)
+    occ = np.asarray(m['data']) >= 0.1
+    dist = orc.edt(occ)
+    B, P, S = 6, 5, 48
+    xy = synth.free_poses(rng, m, B * P, 6, dist).reshape(B, P, 2)
+    pose = np.concatenate([xy, rng.uniform(0, 2 * np.pi, (B, P, 1))], 2)
+    segs = np.zeros((B, S, 4), np.float32)
+    for e in range(B):
+        for s in range(S):
+            i = rng.randint(P)
+            c = xy[e, i]
+            kind = s % 6
+            if kind == 0:      # a short segment somewhere within range
+                a = c + rng.uniform(-5, 5, 2); b = a + rng.uniform(-0.6, 0.6, 2)
+            elif kind == 1:    # through (or touching) the agent's position
+                d = rng.uniform(-1, 1, 2); a = c - d * rng.uniform(0, 1); b = c + d
+            elif kind == 2:    # behind the agent, across the bearing seam
+                th = pose[e, i, 2] + np.pi; n = np.array([-np.sin(th), np.cos(th)])
+                mid = c + 2.0 * np.array([np.cos(th), np.sin(th)]); a = mid + n; b = mid - n
+            elif kind == 3:    # long: subtends more than half a turn
+                d = rng.uniform(-1, 1, 2); d /= np.linalg.norm(d) + 1e-9
+                off = 0.05 * np.array([-d[1], d[0]]); a = c + off - 30 * d; b = c + off + 30 * d
+            elif kind == 4:    # zero length
+                a = c + rng.uniform(-3, 3, 2); b = a.copy()
+            else:              # far out of range
+                a = c + np.array([60.0, 45.0]); b = a + rng.uniform(-1, 1, 2)
+            segs[e, s] = [a[0], a[1], b[0], b[1]]
+    nseg = np.full(B, S, np.int32)
+    nseg[1] = 0
+    nseg[2] = 7
+    lin = R.beam_table(agent)
+    want = np.empty((B, P, 512), np.float32)
+    res = np.float32(m['resolution'])
+    H, W = dist.shape
+    for e in range(B):
+        for i in range(P):
+            lx, ly, lt = np.float32(pose[e, i, 0]), np.float32(pose[e, i, 1]), np.float32(pose[e, i, 2])
+            head, dirs = orc.beam_dirs(lt, lin)
+            ci = orc.lib().nvo_xy_to_cell(float(lx), float(m['origin'][0]), float(m['resolution']), H, 0)
+            cj = orc.lib().nvo_xy_to_cell(float(ly), float(m['origin'][1]), float(m['resolution']), W, 0)
+            ins = np.column_stack([np.full(512, ci), np.full(512, cj), head]).astype(np.float32)
+            r = np.ascontiguousarray(orc.calc_range_many(dist, ins, float(W * H)) * res, np.float32)
+            orc.render_segments(r, dirs, segs[e, :nseg[e]], np.array([lx, ly], np.float32))
+            want[e, i] = np.clip(r, 0, np.float32(agent.range_max))
+    pool = MapPool([m], 'cuda:0')
+    map_id = torch.zeros(B, dtype=torch.int32, device='cuda:0')
+    tp = torch.from_numpy(pose).cuda().contiguous()
+    for slots in (S, 520):   # 520 > the 512 segments the kernel stages: the fallback kernel
+        padded = np.zeros((B, slots, 4), np.float32)
+        padded[:, :S] = segs
+        sc = AgentScanner(pool, B, P, slots, map_id, agent=agent, cell_rule='numpy1')
+        got = sc.scan(tp, torch.from_numpy(padded).cuda().contiguous(), torch.from_numpy(nseg).cuda()).cpu().numpy()
+        assert np.array_equal(got, want), (agent_name, slots, int((got != want).sum()))
+    assert np.isfinite(want).all() and want.max() <= agent.range_max
