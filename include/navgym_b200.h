@@ -403,9 +403,10 @@ void navgym_policy_destroy(navgym_policy_t *policy);
  * [n][2] (env.py:641-645), speed f32 [n][2] (the previous clipped mean) -> mean f32 [n][2]. */
 int navgym_policy_mean(navgym_policy_t *policy, const float *scan, const float *goal,
                        const float *speed, int n, float *mean, void *stream);
-/* byte offsets inside the workspace of {features hi, features lo, act_fc1 output, scales, total}
- * (tests compare the intermediate results against a float32 reference) */
-void navgym_policy_workspace_layout(int max_n, uint64_t *out5);
+/* byte offsets inside the workspace of {features hi, features lo, act_fc1 output as float32 (written
+ * by the comparison path NAVGYM_POLICY_FC2=1 only), scales, total, act_fc1 output hi, lo (f16 pairs
+ * times scales[6])} (tests compare the intermediate results against a float32 reference) */
+void navgym_policy_workspace_layout(int max_n, uint64_t *out7);
 
 /* ---- inner native boundary: range_libc --------------------------------------------- */
 /* PyOMap(bool[H,W]) + PyRayMarching(omap, max_range) (env.py:337-340): exact Euclidean

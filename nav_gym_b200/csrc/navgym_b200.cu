@@ -206,11 +206,18 @@ navgym_policy_t *navgym_policy_create(const navgym_policy_params_t *p, void *str
     cudaStream_t st = (cudaStream_t)stream;
     bool ok = cudaMemsetAsync(pol->ws + L.fh, 0, (size_t)np * 4096 * 2, st) == cudaSuccess &&
               cudaMemsetAsync(pol->ws + L.fl, 0, (size_t)np * 4096 * 2, st) == cudaSuccess;
-    ok = ok && policy_make_map(&pol->tm_fh, pol->ws + L.fh, np, pg::BM) == 0 &&
-         policy_make_map(&pol->tm_fl, pol->ws + L.fl, np, pg::BM) == 0 &&
-         policy_make_map(&pol->tm_wh, pol->ws + L.wh, 256, pg::BN) == 0 &&
-         policy_make_map(&pol->tm_wl, pol->ws + L.wl, 256, pg::BN) == 0;
-    ok = ok && cudaFuncSetAttribute(fc1_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pg::SMEM_BYTES) == cudaSuccess &&
+    ok = ok && cudaMemsetAsync(pol->ws + L.hh, 0, (size_t)np * 256 * 2, st) == cudaSuccess &&
+         cudaMemsetAsync(pol->ws + L.hl, 0, (size_t)np * 256 * 2, st) == cudaSuccess;
+    ok = ok && policy_make_map(&pol->tm_fh, pol->ws + L.fh, np, pg::BM, 4096) == 0 &&
+         policy_make_map(&pol->tm_fl, pol->ws + L.fl, np, pg::BM, 4096) == 0 &&
+         policy_make_map(&pol->tm_wh, pol->ws + L.wh, 256, 256, 4096) == 0 &&
+         policy_make_map(&pol->tm_wl, pol->ws + L.wl, 256, 256, 4096) == 0 &&
+         policy_make_map(&pol->tm_hh, pol->ws + L.hh, np, pg::BM, 256) == 0 &&
+         policy_make_map(&pol->tm_hl, pol->ws + L.hl, np, pg::BM, 256) == 0 &&
+         policy_make_map(&pol->tm_w2h, pol->ws + L.w2h, 128, 128, 256) == 0 &&
+         policy_make_map(&pol->tm_w2l, pol->ws + L.w2l, 128, 128, 256) == 0;
+    ok = ok && cudaFuncSetAttribute(dense_umma_kernel<pg::Fc1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, pg::Fc1::SMEM_BYTES) == cudaSuccess &&
+         cudaFuncSetAttribute(dense_umma_kernel<pg::Fc2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pg::Fc2::SMEM_BYTES) == cudaSuccess &&
          cudaFuncSetAttribute(policy_features_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pc::SMEM_BYTES) == cudaSuccess &&
          cudaFuncSetAttribute(policy_features_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pf::SMEM_BYTES) == cudaSuccess &&
          cudaFuncSetAttribute(fc2_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -246,22 +253,32 @@ int navgym_policy_mean(navgym_policy_t *pol, const float *scan, const float *goa
         policy_features_umma_kernel<<<n < pol->sms ? n : pol->sms, pc::THREADS, pc::SMEM_BYTES, st>>>(
             scan, n, (const uint4 *)(ws + L.conv_img), (const float *)(ws + L.w1s), (const float *)(ws + L.b2), scales,
             (__half *)(ws + L.fh), (__half *)(ws + L.fl));
-    const int tiles = (n + pg::BM - 1) / pg::BM;
-    fc1_umma_kernel<<<tiles < pol->sms ? tiles : pol->sms, pg::THREADS, pg::SMEM_BYTES, st>>>(
-        pol->tm_fh, pol->tm_fl, pol->tm_wh, pol->tm_wl, (const float *)(ws + L.fc1_b), scales, (float *)(ws + L.h), n, tiles);
-    const int tiles2 = (n + 63) / 64;
-    fc2_heads_kernel<<<tiles2 < pol->sms ? tiles2 : pol->sms, 256, (PF2_IN * 128 + 64 * PF2_ROW) * sizeof(float), st>>>(
-        (const float *)(ws + L.h), goal, speed, n, (const float *)(ws + L.w2t), (const float *)(ws + L.fc2_b),
-        (const float *)(ws + L.heads), mean);
+    // act_fc1, then act_fc2 + heads: both on the tensor cores (default), or act_fc2 + heads on the CUDA cores
+    // from a float32 copy of act_fc1's output (NAVGYM_POLICY_FC2=1, the comparison path)
+    static const int fc2_mode = env_int("NAVGYM_POLICY_FC2", 2);
+    const int tiles = (n + pg::BM - 1) / pg::BM, grid = tiles < pol->sms ? tiles : pol->sms;
+    dense_umma_kernel<pg::Fc1, 0><<<grid, pg::THREADS, pg::Fc1::SMEM_BYTES, st>>>(
+        pol->tm_fh, pol->tm_fl, pol->tm_wh, pol->tm_wl, (const float *)(ws + L.fc1_b), scales, n, tiles,
+        fc2_mode == 2 ? nullptr : (float *)(ws + L.h), (__half *)(ws + L.hh), (__half *)(ws + L.hl), nullptr, nullptr, nullptr);
+    if (fc2_mode == 2) {
+        dense_umma_kernel<pg::Fc2, 1><<<grid, pg::THREADS, pg::Fc2::SMEM_BYTES, st>>>(
+            pol->tm_hh, pol->tm_hl, pol->tm_w2h, pol->tm_w2l, (const float *)(ws + L.fc2_tab), scales, n, tiles,
+            nullptr, nullptr, nullptr, goal, speed, mean);
+    } else {
+        const int tiles2 = (n + 63) / 64;
+        fc2_heads_kernel<<<tiles2 < pol->sms ? tiles2 : pol->sms, 256, (PF2_IN * 128 + 64 * PF2_ROW) * sizeof(float), st>>>(
+            (const float *)(ws + L.h), goal, speed, n, (const float *)(ws + L.w2t), (const float *)(ws + L.fc2_b),
+            (const float *)(ws + L.heads), mean);
+    }
     g_launches += 3;
     return (int)cudaGetLastError();
 }
 
 /* test hook: byte offsets of the intermediate buffers inside the workspace */
-void navgym_policy_workspace_layout(int max_n, uint64_t *out /* [5]: fh, fl, h, scales, total */)
+void navgym_policy_workspace_layout(int max_n, uint64_t *out /* [7]: fh, fl, h (float32, comparison path only), scales, total, hh, hl */)
 {
     const policy_ws_t L = policy_ws_layout(max_n);
-    out[0] = L.fh; out[1] = L.fl; out[2] = L.h; out[3] = L.scales; out[4] = L.total;
+    out[0] = L.fh; out[1] = L.fl; out[2] = L.h; out[3] = L.scales; out[4] = L.total; out[5] = L.hh; out[6] = L.hl;
 }
 
 int navgym_peds_move(const navgym_move_args_t *args, void *stream)

@@ -2,8 +2,8 @@
 // The dense half of the pedestrian policy (human_policy.py:38-55 `act_fc1`, `act_fc2`, `actor1`,
 // `actor2`; called from env.py:649-656) as sm_100a kernels:
 //
-//   fc1_umma_kernel     H = relu(F W1^T + b1), F [n][4096], W1 [256][4096]: the one dense contraction of
-//                       the system, on the 5th-generation tensor cores.  tcgen05.mma (kind::f16,
+//   dense_umma_kernel   <Fc1, 0>: H = relu(F W1^T + b1), F [n][4096], W1 [256][4096]: the big dense contraction of
+//                       the system, on the 5th-generation tensor cores; <Fc2, 1>: act_fc2 + the two heads (N 128, K 256).  tcgen05.mma (kind::f16,
 //                       M 128 x N 256 x K 16 per instruction, issued by one thread), operands staged
 //                       in shared memory by TMA (cp.async.bulk.tensor, 128-byte swizzle),
 //                       accumulators in tensor memory (2 x 256 columns: the epilogue of one tile
@@ -35,13 +35,24 @@ namespace pg {
 // K block of a pipeline stage: 64 f16 = 128-byte rows (128-byte swizzle, 2 stages of 96 KB) or
 // 32 f16 = 64-byte rows (64-byte swizzle, 4 stages of 48 KB: the same bytes per MMA cycle, but
 // three stages in flight instead of one while a stage is being multiplied)
-constexpr int BM = 128, BN = 256, BK = NAVGYM_FC1_BK, UK = 16, KDIM = 4096;
+constexpr int BM = 128, BK = NAVGYM_FC1_BK, UK = 16;
 static_assert(BK == 64 || BK == 32, "K block = one swizzle row");
-constexpr uint32_t A_BYTES = BM * BK * 2;                      // 128 rows x (128 | 64) B
-constexpr uint32_t B_BYTES = BN * BK * 2;
-constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;    // Fh, Fl, Wh, Wl
-constexpr int STAGES = (192 * 1024) / STAGE_BYTES;
-constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 128 /* barriers */;
+// one dense layer on the tensor cores: BN outputs, KDIM inputs (act_fc1: 256 x 4096; act_fc2: 128 x 256)
+template <int BN_, int KDIM_>
+struct Dense {
+    static constexpr int BN = BN_, KDIM = KDIM_, KB = KDIM_ / BK;
+    static constexpr uint32_t A_BYTES = BM * BK * 2;                      // 128 rows x (128 | 64) B
+    static constexpr uint32_t B_BYTES = BN_ * BK * 2;
+    static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;    // A hi, A lo, W hi, W lo
+    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;
+    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+    // Instruction descriptor, kind::f16: D float32 (bits 4-5 = 1), A and B f16 (0), both K-major,
+    // N >> 3 at bit 17, M >> 4 at bit 24.
+    static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    static_assert(2 * BN_ <= 512, "two accumulators in tensor memory");
+};
+using Fc1 = Dense<256, 4096>;
+using Fc2 = Dense<128, 256>;
 constexpr int THREADS = 192;                                   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 constexpr uint32_t TMEM_COLS = 512;
 
@@ -105,10 +116,6 @@ __device__ __forceinline__ uint64_t umma_desc_fc1(uint32_t smem_addr)
 {
     return BK == 64 ? umma_desc_sw128(smem_addr) : umma_desc_sw64(smem_addr);
 }
-// Instruction descriptor, kind::f16: D float32 (bits 4-5 = 1), A and B f16 (0), both K-major,
-// N >> 3 at bit 17, M >> 4 at bit 24.
-constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -123,20 +130,45 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 }
 }  // namespace pg
 
-// scales[0] = feature scale s_f, scales[1] = 1 / (s_f s_w): written by policy_prepare_kernel
+__device__ __forceinline__ uint32_t pack_half2(float a, float b)
+{
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+// (hi, lo) f16 pairs of two floats: hi = half(x), lo = half(x - hi)
+__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo)
+{
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 back = __half22float2(h);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = pack_half2(a - back.x, b - back.y);
+}
+
+// dense_umma_kernel<L, EPI>: Y = A W^T in the f16x3 scheme, A = (a_hi, a_lo) [n][KDIM] and W = (w_hi, w_lo)
+// [BN][KDIM] f16 pairs behind TMA maps; 128-row tiles, persistent over tiles.
+//   EPI 0 (act_fc1): h = relu(Y descale + bias), written as f16 hi/lo pairs times s_h2 -- the A operand of the
+//          act_fc2 launch -- and, if h32 != NULL, as float32 (the comparison path fc2_heads_kernel reads it);
+//          scales[1] = descale, scales[6] = s_h2.
+//   EPI 1 (act_fc2 + heads, human_policy.py:51-55): y = relu(Y descale + b2 + [goal, speed] . w2[:, 256:260]),
+//          mean = (sigmoid(y . a1 + a1_b), tanh(y . a2 + a2_b)); tab = [7][128] b2, the four extra input columns
+//          of fc2's weight, a1_w, a2_w, then a1_b, a2_b; scales[7] = descale.  One thread per pedestrian.
+template <class L, int EPI>
 __global__ void __launch_bounds__(pg::THREADS, 1)
-fc1_umma_kernel(const __grid_constant__ CUtensorMap tm_fh, const __grid_constant__ CUtensorMap tm_fl,
-                const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_wl,
-                const float *__restrict__ bias, const float *__restrict__ scales, float *__restrict__ H, int n, int num_tiles)
+dense_umma_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ CUtensorMap tm_al,
+                  const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_wl,
+                  const float *__restrict__ bias_or_tab, const float *__restrict__ scales, int n, int num_tiles,
+                  float *__restrict__ h32, __half *__restrict__ h_hi, __half *__restrict__ h_lo,
+                  const float *__restrict__ goal, const float *__restrict__ speed, float *__restrict__ mean)
 {
     using namespace pg;
+    constexpr int BN = L::BN, KB = L::KB, STAGES = L::STAGES;
+    constexpr uint32_t A_BYTES = L::A_BYTES, B_BYTES = L::B_BYTES, STAGE_BYTES = L::STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzled tiles need 1024-byte alignment
     const uint32_t bars = base + STAGES * STAGE_BYTES;
     const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16;
     const uint32_t tmem_slot = tempty0 + 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int KB = KDIM / BK;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
@@ -162,8 +194,8 @@ fc1_umma_kernel(const __grid_constant__ CUtensorMap tm_fh, const __grid_constant
                     mbar_wait(empty0 + 8 * s, ph ^ 1);
                     const uint32_t st = base + s * STAGE_BYTES, fb = full0 + 8 * s;
                     mbar_expect_tx(fb, STAGE_BYTES);
-                    tma_load_2d(st, &tm_fh, kb * BK, tile * BM, fb);
-                    tma_load_2d(st + A_BYTES, &tm_fl, kb * BK, tile * BM, fb);
+                    tma_load_2d(st, &tm_ah, kb * BK, tile * BM, fb);
+                    tma_load_2d(st + A_BYTES, &tm_al, kb * BK, tile * BM, fb);
                     tma_load_2d(st + 2 * A_BYTES, &tm_wh, kb * BK, 0, fb);
                     tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tm_wl, kb * BK, 0, fb);
                     if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -189,9 +221,9 @@ fc1_umma_kernel(const __grid_constant__ CUtensorMap tm_fh, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < BK / UK; k++) {
                         const uint64_t adv = (uint64_t)((k * UK * 2) >> 4);   // 32 bytes along K inside the swizzle atom
-                        umma_f16(d, fl + adv, wh + adv, IDESC, (kb | k) != 0);
-                        umma_f16(d, fh + adv, wl + adv, IDESC, 1);
-                        umma_f16(d, fh + adv, wh + adv, IDESC, 1);
+                        umma_f16(d, fl + adv, wh + adv, L::IDESC, (kb | k) != 0);
+                        umma_f16(d, fh + adv, wl + adv, L::IDESC, 1);
+                        umma_f16(d, fh + adv, wh + adv, L::IDESC, 1);
                     }
                     umma_commit(empty0 + 8 * s);   // the stage is free once these MMAs have read it
                     if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -202,29 +234,78 @@ fc1_umma_kernel(const __grid_constant__ CUtensorMap tm_fh, const __grid_constant
     } else {
         // ---- epilogue: warp w reads the TMEM lanes 32 (w % 4) ... + 31 = rows of the tile
         const int q = warp & 3;
-        const float descale = scales[1];
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
             const uint32_t buf = it & 1;
             mbar_wait(tfull0 + 8 * buf, (it >> 1) & 1);
             tc_fence_after();
             const int row = tile * BM + q * 32 + lane;
-            float *out = H + (size_t)row * BN;
+            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+            if (EPI == 0) {
+                const float descale = scales[1], s_h2 = scales[6];
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; c++) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c * 32, v);
-                if (row < n) {
+                for (int c = 0; c < BN / 32; c++) {
+                    uint32_t v[32];
+                    tmem_ld32(t0 + c * 32, v);
+                    if (row < n) {
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b = *reinterpret_cast<const float4 *>(bias_or_tab + c * 32 + j);
+                            float4 o;
+                            o.x = fmaxf(fmaf(__uint_as_float(v[j]), descale, b.x), 0.0f);
+                            o.y = fmaxf(fmaf(__uint_as_float(v[j + 1]), descale, b.y), 0.0f);
+                            o.z = fmaxf(fmaf(__uint_as_float(v[j + 2]), descale, b.z), 0.0f);
+                            o.w = fmaxf(fmaf(__uint_as_float(v[j + 3]), descale, b.w), 0.0f);
+                            if (h32) *reinterpret_cast<float4 *>(h32 + (size_t)row * BN + c * 32 + j) = o;
+                            split2(o.x * s_h2, o.y * s_h2, hi[j >> 1], lo[j >> 1]);
+                            split2(o.z * s_h2, o.w * s_h2, hi[(j >> 1) + 1], lo[(j >> 1) + 1]);
+                        }
+                        uint4 *oh = reinterpret_cast<uint4 *>(h_hi + (size_t)row * BN + c * 32);
+                        uint4 *ol = reinterpret_cast<uint4 *>(h_lo + (size_t)row * BN + c * 32);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            oh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+                            ol[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+                        }
+                    }
+                }
+            } else {
+                const float descale = scales[7];
+                const float *tab = bias_or_tab;
+                float g0 = 0.f, g1 = 0.f, p0 = 0.f, p1 = 0.f;
+                if (row < n) {   // torch.cat((a, goal, speed)) (human_policy.py:51)
+                    g0 = goal[2 * (size_t)row]; g1 = goal[2 * (size_t)row + 1];
+                    p0 = speed[2 * (size_t)row]; p1 = speed[2 * (size_t)row + 1];
+                }
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; c++) {
+                    uint32_t v[32];
+                    tmem_ld32(t0 + c * 32, v);
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        const float4 b = *reinterpret_cast<const float4 *>(bias + c * 32 + j);
-                        float4 o;
-                        o.x = fmaxf(fmaf(__uint_as_float(v[j]), descale, b.x), 0.0f);
-                        o.y = fmaxf(fmaf(__uint_as_float(v[j + 1]), descale, b.y), 0.0f);
-                        o.z = fmaxf(fmaf(__uint_as_float(v[j + 2]), descale, b.z), 0.0f);
-                        o.w = fmaxf(fmaf(__uint_as_float(v[j + 3]), descale, b.w), 0.0f);
-                        *reinterpret_cast<float4 *>(out + c * 32 + j) = o;
+                        const int o = c * 32 + j;
+                        const float4 b = *reinterpret_cast<const float4 *>(tab + o);
+                        const float4 w0 = *reinterpret_cast<const float4 *>(tab + 128 + o), w1 = *reinterpret_cast<const float4 *>(tab + 256 + o);
+                        const float4 w2 = *reinterpret_cast<const float4 *>(tab + 384 + o), w3 = *reinterpret_cast<const float4 *>(tab + 512 + o);
+                        const float4 a1 = *reinterpret_cast<const float4 *>(tab + 640 + o), a2 = *reinterpret_cast<const float4 *>(tab + 768 + o);
+                        const float bb[4] = {b.x, b.y, b.z, b.w}, x0[4] = {w0.x, w0.y, w0.z, w0.w}, x1[4] = {w1.x, w1.y, w1.z, w1.w};
+                        const float x2[4] = {w2.x, w2.y, w2.z, w2.w}, x3[4] = {w3.x, w3.y, w3.z, w3.w};
+                        const float h1[4] = {a1.x, a1.y, a1.z, a1.w}, h2[4] = {a2.x, a2.y, a2.z, a2.w};
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            float y = fmaf(__uint_as_float(v[j + i]), descale, bb[i]);
+                            y = fmaf(g0, x0[i], y); y = fmaf(g1, x1[i], y); y = fmaf(p0, x2[i], y); y = fmaf(p1, x3[i], y);
+                            y = fmaxf(y, 0.0f);
+                            s1 = fmaf(y, h1[i], s1);
+                            s2 = fmaf(y, h2[i], s2);
+                        }
                     }
+                }
+                if (row < n) {   // human_policy.py:53-55: sigmoid / tanh heads
+                    mean[2 * (size_t)row] = 1.0f / (1.0f + expf(-(s1 + tab[896])));
+                    mean[2 * (size_t)row + 1] = tanhf(s2 + tab[897]);
                 }
             }
             tc_fence_before();
@@ -327,7 +408,8 @@ fc2_heads_kernel(const float *__restrict__ H, const float *__restrict__ goal, co
 // frames (env.py:647), transposes conv2 / fc2 for the kernels' access order, and chooses the two
 // power-of-two scales of the f16x3 scheme from bounds on the features and the fc1 weights.
 struct policy_ws_t {   // device workspace layout (byte offsets from the workspace base)
-    size_t fh, fl, wh, wl, h, w1f, b1, w2, b2, fc1_b, w2t, fc2_b, heads, scales, conv_img, w1s, conv1_img, conv2_img, total;
+    size_t fh, fl, wh, wl, h, w1f, b1, w2, b2, fc1_b, w2t, fc2_b, heads, scales, conv_img, w1s, conv1_img, conv2_img,
+        hh, hl, w2h, w2l, fc2_tab, total;
 };
 static policy_ws_t policy_ws_layout(int max_n)
 {
@@ -342,6 +424,8 @@ static policy_ws_t policy_ws_layout(int max_n)
     L.fc1_b = take(256 * 4); L.w2t = take((size_t)PF2_IN * 128 * 4); L.fc2_b = take(128 * 4);
     L.heads = take(258 * 4); L.scales = take(64);
     L.conv_img = take(16384); L.w1s = take(256 * 4); L.conv1_img = take(6144); L.conv2_img = take(12288);
+    L.hh = take(np * 256 * 2); L.hl = take(np * 256 * 2);                       // act_fc1's output as f16 pairs
+    L.w2h = take(128 * 256 * 2); L.w2l = take(128 * 256 * 2); L.fc2_tab = take(898 * 4);
     L.total = o;
     return L;
 }
@@ -417,6 +501,58 @@ __global__ void __launch_bounds__(1024) policy_prepare_kernel(const navgym_polic
         sc[3] = 1.0f / (s_h_scale * s_w2_scale);
     }
     __syncthreads();
+    // act_fc2 on the tensor cores: act_fc1's output h >= 0 is handed over as f16 pairs times s_h2, a power
+    // of two from a bound on h (|b| + the row's L1 norm x the feature bound 2^15 / s_f: generous, which only
+    // costs low-order bits of values far below the bound); fc2's first 256 weight columns are scaled and
+    // split like fc1's, the four extra input columns (goal, speed), the bias and the two heads go into a
+    // float32 table for the epilogue.
+    {
+        __shared__ float s_h2, s_w2fc;
+        float l1 = 0.f;   // 4 threads per row of fc1_w
+        {
+            const int row = t >> 2, part = t & 3;
+            for (int k = part * 1024; k < part * 1024 + 1024; k++) l1 += fabsf(p.fc1_w[row * 4096 + k]);
+        }
+        red[t] = l1;
+        __syncthreads();
+        float rowb = 0.f;
+        if (t < 256) rowb = (red[4 * t] + red[4 * t + 1] + red[4 * t + 2] + red[4 * t + 3]) * (32768.0f / s_feat_scale) + fabsf(p.fc1_b[t]);
+        __syncthreads();
+        if (t < 256) red[t] = rowb;
+        __syncthreads();
+        if (t == 0) {
+            float m = 1e-30f;
+            for (int o = 0; o < 256; o++) m = fmaxf(m, red[o]);
+            int e;
+            frexpf(m, &e);
+            s_h2 = ldexpf(1.0f, min(max(15 - e, -100), 100));
+            float wm = 1e-30f;
+            for (int i = 0; i < 128 * PF2_IN; i++) if (i % PF2_IN < 256) wm = fmaxf(wm, fabsf(p.fc2_w[i]));
+            frexpf(wm, &e);
+            s_w2fc = ldexpf(1.0f, min(max(14 - e, -100), 100));
+            float *sc = (float *)(ws + L.scales);
+            sc[6] = s_h2;
+            sc[7] = 1.0f / (s_h2 * s_w2fc);
+        }
+        __syncthreads();
+        __half *w2h = (__half *)(ws + L.w2h), *w2l = (__half *)(ws + L.w2l);
+        for (int i = t; i < 128 * 256; i += 1024) {
+            const int o = i >> 8, k = i & 255;
+            const float x = p.fc2_w[o * PF2_IN + k] * s_w2fc;
+            const __half hi = __float2half_rn(x);
+            w2h[i] = hi;
+            w2l[i] = __float2half_rn(x - __half2float(hi));
+        }
+        float *tab = (float *)(ws + L.fc2_tab);
+        if (t < 128) {
+            tab[t] = p.fc2_b[t];
+            for (int e = 0; e < 4; e++) tab[128 * (1 + e) + t] = p.fc2_w[t * PF2_IN + 256 + e];
+            tab[640 + t] = p.a1_w[t];
+            tab[768 + t] = p.a2_w[t];
+        }
+        if (t == 0) { tab[896] = p.a1_b[0]; tab[897] = p.a2_b[0]; }
+        __syncthreads();
+    }
     // act_fc1's weight, columns permuted from torch's channel-major feature order (c * 128 + pos)
     // to the position-major order the front end writes (pos * 32 + c), scaled and split
     const float sw = s_w_scale;
@@ -490,7 +626,8 @@ struct navgym_policy {
     int max_n, device;
     uint8_t *ws;
     policy_ws_t L;
-    CUtensorMap tm_fh, tm_fl, tm_wh, tm_wl;
+    CUtensorMap tm_fh, tm_fl, tm_wh, tm_wl;          // act_fc1: features, weight
+    CUtensorMap tm_hh, tm_hl, tm_w2h, tm_w2l;        // act_fc2: act_fc1's output, weight
     int sms;
 };
 
@@ -498,8 +635,8 @@ typedef CUresult (*navgym_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, c
                                            const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                            CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// [rows][4096] f16, row-major: boxes of BK columns (one swizzle span) x box_rows rows
-static int policy_make_map(CUtensorMap *m, void *base, uint64_t rows, uint32_t box_rows)
+// [rows][kdim] f16, row-major: boxes of BK columns (one swizzle span) x box_rows rows
+static int policy_make_map(CUtensorMap *m, void *base, uint64_t rows, uint32_t box_rows, uint32_t kdim)
 {
     static navgym_encode_tiled_fn encode = nullptr;
     if (!encode) {
@@ -508,8 +645,8 @@ static int policy_make_map(CUtensorMap *m, void *base, uint64_t rows, uint32_t b
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return -1;
         encode = (navgym_encode_tiled_fn)fn;
     }
-    const cuuint64_t dims[2] = {(cuuint64_t)pg::KDIM, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)pg::KDIM * 2};
+    const cuuint64_t dims[2] = {(cuuint64_t)kdim, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)kdim * 2};
     const cuuint32_t box[2] = {(cuuint32_t)pg::BK, box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -546,20 +683,6 @@ constexpr uint32_t OFF_BAR = OFF_XS + 2 * XS_FLOATS * 4;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 128 + 1024;
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }  // namespace pc
-
-__device__ __forceinline__ uint32_t pack_half2(float a, float b)
-{
-    const __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<const uint32_t *>(&h);
-}
-// (hi, lo) f16 pairs of two floats: hi = half(x), lo = half(x - hi)
-__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo)
-{
-    const __half2 h = __floats2half2_rn(a, b);
-    const float2 back = __half22float2(h);
-    hi = *reinterpret_cast<const uint32_t *>(&h);
-    lo = pack_half2(a - back.x, b - back.y);
-}
 
 // conv_img: the B operand exactly as it sits in shared memory (policy_prepare_kernel), w1s
 // [32][8] = 5 conv1 taps and the bias, all times s_h, 2 pad; scales: see policy_prepare_kernel

@@ -151,16 +151,21 @@ class NativePolicy(object):
 
     def intermediates(self, n):
         """(features hi, features lo) f16 [n, 4096] put back into torch's channel-major order (the
-        kernels keep them position-major, [pos][channel]), act_fc1 output f32 [n, 256], scales
-        f32 [4] (feature scale, 1 / (feature scale x fc1 weight scale), conv1 output scale,
-        1 / (conv1 output scale x conv2 weight scale)): copies / views of the workspace (tests)."""
-        L = (C.c_uint64 * 5)()
+        kernels keep them position-major, [pos][channel]), act_fc1 output f32 [n, 256] (re-assembled
+        from the f16 pairs the tensor-core act_fc2 reads), scales f32 [8] (feature scale, 1 /
+        (feature scale x fc1 weight scale), conv1 output scale, 1 / (conv1 output scale x conv2
+        weight scale), -, -, act_fc1 output scale, 1 / (that x fc2 weight scale)): copies / views of
+        the workspace (tests)."""
+        L = (C.c_uint64 * 7)()
         self.lib.navgym_policy_workspace_layout(self.max_n, L)
         w = self._ws
         unperm = lambda t: t.view(torch.float16).reshape(n, 128, 32).permute(0, 2, 1).reshape(n, 4096)
         fh, fl = unperm(w[L[0]:L[0] + n * 8192]), unperm(w[L[1]:L[1] + n * 8192])
-        h = w[L[2]:L[2] + n * 1024].view(torch.float32).reshape(n, 256)
-        return fh, fl, h, w[L[3]:L[3] + 16].view(torch.float32)
+        scales = w[L[3]:L[3] + 32].view(torch.float32)
+        hh = w[L[5]:L[5] + n * 512].view(torch.float16).reshape(n, 256)
+        hl = w[L[6]:L[6] + n * 512].view(torch.float16).reshape(n, 256)
+        h = ((hh.double() + hl.double()) / float(scales[6])).float()
+        return fh, fl, h, scales
 
     def __del__(self):
         h, self.handle = getattr(self, 'handle', None), None
