@@ -312,7 +312,8 @@ def config_crowd(torch, dev, steps, warmup, world_mp):
     n = B * P
     scan, goal, speed = sim.scan.reshape(n, -1), sim.goal_local.reshape(n, 2), sim.prev_action.reshape(n, 2)
     ms_policy = timed(lambda i: sim.native.mean(scan, goal, speed, out=sim._mean), 20)
-    flop = 2.0 * n * 3 * (4096 * 256 + 128 * 32 * 128)   # f16x3: three MMAs per product; conv2 K padded to 128
+    # f16x3: three f16 products per contraction -- act_fc1, conv2 (K 96), conv1 (as M128 x N96 x K16), act_fc2 (K 256)
+    flop = 2.0 * n * 3 * (4096 * 256 + 128 * 32 * 96 + 128 * 96 * 16 + 256 * 128)
     tf = flop / (ms_policy * 1e-3) / 1e12
     peak_tf = None
     try:
@@ -327,8 +328,8 @@ def config_crowd(torch, dev, steps, warmup, world_mp):
                         "observe": timed(lambda i: sim.observe(), 20)},
            "roofline_policy": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s",
                                "frac": (tf / peak_tf) if peak_tf else None,
-                               "note": "tensor-core flop of the 3 kernels' MMAs (act_fc1 + conv2, three f16 products each) over the "
-                                       "whole policy forward, conv1 / act_fc2 / heads on CUDA cores included in the time"}}
+                               "note": "tensor-core flop of the three launches' MMAs (conv1, conv2, act_fc1, act_fc2: three f16 products each) "
+                                       "over the whole policy forward (operand conversion and epilogues on the CUDA cores included in the time)"}}
     return out
 
 

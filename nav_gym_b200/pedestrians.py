@@ -105,8 +105,8 @@ def _ptr(t):
 
 class NativePolicy(object):
     """HumanPolicy.mean (human_policy.py:38-55) through the library's own kernels
-    (navgym_policy_create / navgym_policy_mean): convolutional front end -> act_fc1 on the
-    tcgen05 tensor cores (f16x3 operand split, float32-grade) -> act_fc2 + heads.  No torch op
+    (navgym_policy_create / navgym_policy_mean): convolutional front end -> act_fc1 -> act_fc2 +
+    heads, every contraction on the tcgen05 tensor cores (f16x3 operand split, float32-grade).  No torch op
     and no library GEMM runs in `mean`; torch only owns the workspace memory.  The weights are
     copied (pre-split) at construction: build a new NativePolicy after changing them."""
 
@@ -227,7 +227,7 @@ class PedestrianSim(object):
     waypoint f64, goal_local f32.
 
     precision: 'f16x3' (default) runs the whole policy through the library's own kernels
-    (NativePolicy: act_fc1 on the tcgen05 tensor cores with hi/lo f16 operand splits, float32-grade:
+    (NativePolicy: both convolutions, act_fc1 and act_fc2 on the tcgen05 tensor cores with hi/lo f16 operand splits, float32-grade:
     the mean matches the reference's CPU forward to ~1e-5).  The other modes keep the dense layers
     in torch / cuBLAS for comparison: 'fp32', 'tf32x3' (three TF32 products of the operands' high
     and low halves, same tolerance), 'tf32' or 'bf16' (means move by ~1e-3, the pedestrians' paths
