@@ -210,8 +210,8 @@ navgym_policy_t *navgym_policy_create(const navgym_policy_params_t *p, void *str
          cudaMemsetAsync(pol->ws + L.hl, 0, (size_t)np * 256 * 2, st) == cudaSuccess;
     ok = ok && policy_make_map(&pol->tm_fh, pol->ws + L.fh, np, pg::BM, 4096) == 0 &&
          policy_make_map(&pol->tm_fl, pol->ws + L.fl, np, pg::BM, 4096) == 0 &&
-         policy_make_map(&pol->tm_wh, pol->ws + L.wh, 256, 256, 4096) == 0 &&
-         policy_make_map(&pol->tm_wl, pol->ws + L.wl, 256, 256, 4096) == 0 &&
+         policy_make_map(&pol->tm_wh, pol->ws + L.wh, 256, pg::Fc1::WBOX, 4096) == 0 &&
+         policy_make_map(&pol->tm_wl, pol->ws + L.wl, 256, pg::Fc1::WBOX, 4096) == 0 &&
          policy_make_map(&pol->tm_hh, pol->ws + L.hh, np, pg::BM, 256) == 0 &&
          policy_make_map(&pol->tm_hl, pol->ws + L.hl, np, pg::BM, 256) == 0 &&
          policy_make_map(&pol->tm_w2h, pol->ws + L.w2h, 128, 128, 256) == 0 &&

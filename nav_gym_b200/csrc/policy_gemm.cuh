@@ -41,6 +41,7 @@ static_assert(BK == 64 || BK == 32, "K block = one swizzle row");
 template <int BN_, int KDIM_>
 struct Dense {
     static constexpr int BN = BN_, KDIM = KDIM_, KB = KDIM_ / BK;
+    static constexpr int WBOX = BN_ > 128 ? 64 : BN_;   // weight rows per TMA box (a leftover tile's N parts are multiples of it)
     static constexpr uint32_t A_BYTES = BM * BK * 2;                      // 128 rows x (128 | 64) B
     static constexpr uint32_t B_BYTES = BN_ * BK * 2;
     static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;    // A hi, A lo, W hi, W lo
@@ -185,19 +186,36 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_consta
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
+    // Work items of this CTA: whole tiles round robin while every CTA gets one; the tiles left over
+    // for a last, partly filled round (40 960 pedestrians = 320 tiles on 148 SMs: 24) are split along N
+    // into SPLIT parts of BN / SPLIT outputs, so that the round costs a fraction of a tile time instead
+    // of a whole one (the launch lasted 3 tile times where the average is 2.16).  All three roles walk
+    // the same list.
+    const int full_rounds = num_tiles / (int)gridDim.x, full = full_rounds * (int)gridDim.x, rem = num_tiles - full;
+    int SPLIT = 1;
+    if (L::WBOX < BN && rem > 0) SPLIT = rem * 4 <= (int)gridDim.x ? 4 : (rem * 2 <= (int)gridDim.x ? 2 : 1);
+    const int n_items = full_rounds + ((int)blockIdx.x < rem * SPLIT ? 1 : 0);
+    auto item = [&](int i, int &tile, int &n0, int &bn) {
+        if (i < full_rounds) { tile = (int)blockIdx.x + i * (int)gridDim.x; n0 = 0; bn = BN; }
+        else { tile = full + (int)blockIdx.x / SPLIT; bn = BN / SPLIT; n0 = ((int)blockIdx.x % SPLIT) * bn; }
+    };
     if (warp == 0) {
-        // ---- TMA producer: one thread streams the operand tiles of this CTA's tiles
+        // ---- TMA producer: one thread streams the operand tiles of this CTA's items
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int i = 0; i < n_items; i++) {
+                int tile, n0, bn;
+                item(i, tile, n0, bn);
                 for (int kb = 0; kb < KB; kb++) {
                     mbar_wait(empty0 + 8 * s, ph ^ 1);
                     const uint32_t st = base + s * STAGE_BYTES, fb = full0 + 8 * s;
-                    mbar_expect_tx(fb, STAGE_BYTES);
+                    mbar_expect_tx(fb, 2 * A_BYTES + 2 * (uint32_t)bn * BK * 2);
                     tma_load_2d(st, &tm_ah, kb * BK, tile * BM, fb);
                     tma_load_2d(st + A_BYTES, &tm_al, kb * BK, tile * BM, fb);
-                    tma_load_2d(st + 2 * A_BYTES, &tm_wh, kb * BK, 0, fb);
-                    tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tm_wl, kb * BK, 0, fb);
+                    for (int r = 0; r < bn; r += L::WBOX) {   // weight rows n0 .. n0 + bn, WBOX rows per box
+                        tma_load_2d(st + 2 * A_BYTES + (uint32_t)r * BK * 2, &tm_wh, kb * BK, n0 + r, fb);
+                        tma_load_2d(st + 2 * A_BYTES + B_BYTES + (uint32_t)r * BK * 2, &tm_wl, kb * BK, n0 + r, fb);
+                    }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -206,8 +224,10 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_consta
         // ---- MMA issuer: one thread issues every tcgen05.mma of the CTA
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
+            for (int it = 0; it < n_items; it++) {
+                int tile, n0, bn;
+                item(it, tile, n0, bn);
+                const uint32_t idesc = (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
                 const uint32_t buf = it & 1;
                 mbar_wait(tempty0 + 8 * buf, ((it >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
                 tc_fence_after();
@@ -221,9 +241,9 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < BK / UK; k++) {
                         const uint64_t adv = (uint64_t)((k * UK * 2) >> 4);   // 32 bytes along K inside the swizzle atom
-                        umma_f16(d, fl + adv, wh + adv, L::IDESC, (kb | k) != 0);
-                        umma_f16(d, fh + adv, wl + adv, L::IDESC, 1);
-                        umma_f16(d, fh + adv, wh + adv, L::IDESC, 1);
+                        umma_f16(d, fl + adv, wh + adv, idesc, (kb | k) != 0);
+                        umma_f16(d, fh + adv, wl + adv, idesc, 1);
+                        umma_f16(d, fh + adv, wh + adv, idesc, 1);
                     }
                     umma_commit(empty0 + 8 * s);   // the stage is free once these MMAs have read it
                     if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -234,8 +254,9 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_consta
     } else {
         // ---- epilogue: warp w reads the TMEM lanes 32 (w % 4) ... + 31 = rows of the tile
         const int q = warp & 3;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
+        for (int it = 0; it < n_items; it++) {
+            int tile, n0, bn;
+            item(it, tile, n0, bn);
             const uint32_t buf = it & 1;
             mbar_wait(tfull0 + 8 * buf, (it >> 1) & 1);
             tc_fence_after();
@@ -244,25 +265,26 @@ dense_umma_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_consta
             if (EPI == 0) {
                 const float descale = scales[1], s_h2 = scales[6];
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; c++) {
+                for (int c = 0; c < bn / 32; c++) {
                     uint32_t v[32];
                     tmem_ld32(t0 + c * 32, v);
                     if (row < n) {
+                        const int col = n0 + c * 32;
                         uint32_t hi[16], lo[16];
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            const float4 b = *reinterpret_cast<const float4 *>(bias_or_tab + c * 32 + j);
+                            const float4 b = *reinterpret_cast<const float4 *>(bias_or_tab + col + j);
                             float4 o;
                             o.x = fmaxf(fmaf(__uint_as_float(v[j]), descale, b.x), 0.0f);
                             o.y = fmaxf(fmaf(__uint_as_float(v[j + 1]), descale, b.y), 0.0f);
                             o.z = fmaxf(fmaf(__uint_as_float(v[j + 2]), descale, b.z), 0.0f);
                             o.w = fmaxf(fmaf(__uint_as_float(v[j + 3]), descale, b.w), 0.0f);
-                            if (h32) *reinterpret_cast<float4 *>(h32 + (size_t)row * BN + c * 32 + j) = o;
+                            if (h32) *reinterpret_cast<float4 *>(h32 + (size_t)row * BN + col + j) = o;
                             split2(o.x * s_h2, o.y * s_h2, hi[j >> 1], lo[j >> 1]);
                             split2(o.z * s_h2, o.w * s_h2, hi[(j >> 1) + 1], lo[(j >> 1) + 1]);
                         }
-                        uint4 *oh = reinterpret_cast<uint4 *>(h_hi + (size_t)row * BN + c * 32);
-                        uint4 *ol = reinterpret_cast<uint4 *>(h_lo + (size_t)row * BN + c * 32);
+                        uint4 *oh = reinterpret_cast<uint4 *>(h_hi + (size_t)row * BN + col);
+                        uint4 *ol = reinterpret_cast<uint4 *>(h_lo + (size_t)row * BN + col);
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
                             oh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);

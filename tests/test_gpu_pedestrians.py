@@ -123,13 +123,14 @@ def _f32_reference(fn):
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
 
 
-@pytest.mark.parametrize('n', [1, 77, 128, 300, 1029])
+@pytest.mark.parametrize('n', [1, 77, 128, 300, 1029, 19200])
 def test_native_policy_stage_by_stage(n):
     """navgym_policy_mean (front end -> tcgen05 act_fc1 in the f16x3 scheme -> act_fc2 + heads)
     against torch float32 / float64 on random scans, one stage at a time: the feature halves
     re-assemble the float32 features, the tensor-core layer equals a float64 product of those
     very features to float32 rounding, the means equal torch's float32 forward.  n covers a
-    single row, partial 128-row tiles and several tiles per CTA."""
+    single row, partial 128-row tiles, several tiles per CTA, and (19 200 = 150 tiles on 148 SMs) a last
+    round whose left-over tiles act_fc1 splits along N."""
     import torch.nn.functional as F
     from nav_gym_b200.pedestrians import HumanPolicy, NativePolicy, preprocess_scan
     torch.manual_seed(7)
