@@ -53,6 +53,7 @@ typedef struct {
  *   actions f32 [num_envs][2]                 map_id   i32 [num_envs]
  *   discs   f32 [num_envs][max_disc][3] (x,y,r)   ndisc i32 [num_envs]
  *   segs    f32 [num_envs][max_seg][4] (ax,ay,bx,by)  nseg i32 [num_envs]
+ *           (max_disc + max_seg <= 256: the kernel parks one beam window per obstacle in shared memory)
  *   noise   f32 [num_envs][2][512] additive, slot 0 = the step's scan, slot 1 = the crash
  *           re-scan (parity traces); NULL -> Philox N(0, noise_std[env]) (production)
  *   obs     f32 [num_envs][obs_stride], first S*512+7 columns written per row (S = num_scan_stack;

@@ -70,6 +70,8 @@ template <bool RESET>
 static cudaError_t launch_step(const navgym_step_args_t &a, cudaStream_t st)
 {
     const int count = a.env_count > 0 ? a.env_count : a.num_envs - a.env_begin;
+    // the obstacle windows of an environment are parked in NB / 2 shared-memory slots
+    if ((a.discs ? a.max_disc : 0) + (a.segs ? a.max_seg : 0) > NB / 2) return cudaErrorInvalidValue;
     // tail regime B (see step_kernel) while the launch is at most ~2.4 waves of CTAs (measured
     // crossover on B200: 5120 envs -2 %, 6144 envs +2 %); NAVGYM_COOP_MAX_ENVS overrides
     static const int coop_max = env_int("NAVGYM_COOP_MAX_ENVS", coop_default_max());

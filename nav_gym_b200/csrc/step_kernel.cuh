@@ -538,15 +538,23 @@ __device__ __forceinline__ void step_body(const navgym_step_args_t &a, EnvSmem &
         }
         PROF_MARK(3);
         // ---- pedestrians: segments (env.py:430-431) and discs (env.py:432), min-merged.
-        // One warp per obstacle, lanes across the beams of its angular window.
+        // Two steps.  (A) lanes across obstacles: every thread loads one obstacle and works out the
+        // angular window of beams that can see it (or that it is out of sight) -- all obstacle
+        // loads of the environment are in flight together, and the window trigonometry runs 32
+        // obstacles wide; the windows are parked in the survivor list's shared memory (free since
+        // the tail phase).  (B) one warp per visible obstacle, lanes across the beams of its window.
+        // (One warp per obstacle for both steps walked the list through one global-memory round
+        // trip per obstacle and computed every window 32 times over.)
         if (ns + nd > 0) {
             cta_sync<WPE>();
             // (the first scan after an auto-reset sees the next episode's pedestrians, if given)
             const bool nxt = !IS_RESET_KERNEL && pass == PASS_RESET && a.discs_reset != nullptr;
             const float *discs = (nxt ? a.discs_reset : a.discs) + (size_t)e * a.max_disc * 3;
             const float *segs = (nxt ? a.segs_reset : a.segs) + (size_t)e * a.max_seg * 4;
-            for (int o = warp; o < ns + nd; o += WPE) {
-                int k0, cnt;
+            int *win = reinterpret_cast<int *>(sm.alive);   // [NB / 2]: k0 (16 bits, signed) | cnt << 16; cnt = 0: out of sight
+            const int n_obs = min(ns + nd, NB / 2);         // (host: max_seg + max_disc <= NB / 2)
+            for (int o = tid; o < n_obs; o += TPB) {
+                int k0 = 0, cnt = 0;
                 if (o < ns) {
                     const float4 sg = *reinterpret_cast<const float4 *>(segs + 4 * o);
                     const float ax = sg.x, ay = sg.y, bx = sg.z, by = sg.w;
@@ -557,28 +565,42 @@ __device__ __forceinline__ void step_body(const navgym_step_args_t &a, EnvSmem &
                     // range_max two phases on -- the same value as no hit (env.py:435)
                     const float len2 = (bx - ax) * (bx - ax) + (by - ay) * (by - ay);
                     const float reach = a.range_max * 1.001f + sqrtf(len2) + 0.01f;
-                    if (fminf(da2, db2) > reach * reach) continue;
-                    float pa = atan2f(ay - ly, ax - lx), pb = atan2f(by - ly, bx - lx);
-                    float dl = pb - pa;
-                    dl -= 6.2831853f * rintf(dl * 0.15915494f);
-                    if (fabsf(dl) > 3.0f || da2 < 1e-6f || db2 < 1e-6f) { k0 = 0; cnt = NB; }
-                    else beam_window(dl >= 0 ? pa : pb, fabsf(dl), lt, k0, cnt);
-                    for (int i = lane; i < cnt; i += 32) {
-                        const int k = (k0 + i) & (NB - 1);
-                        const float tt = seg_hit(lx, ly, sm.dir[k].x, sm.dir[k].y, ax, ay, bx, by);
-                        if (tt < CUDART_INF_F) atomicMin(&sm.scan[k], __float_as_int(tt));
+                    if (!(fminf(da2, db2) > reach * reach)) {
+                        float pa = atan2f(ay - ly, ax - lx), pb = atan2f(by - ly, bx - lx);
+                        float dl = pb - pa;
+                        dl -= 6.2831853f * rintf(dl * 0.15915494f);
+                        if (fabsf(dl) > 3.0f || da2 < 1e-6f || db2 < 1e-6f) { k0 = 0; cnt = NB; }
+                        else beam_window(dl >= 0 ? pa : pb, fabsf(dl), lt, k0, cnt);
                     }
                 } else {
                     const int q = o - ns;
                     const float X = discs[3 * q], Y = discs[3 * q + 1], Rd = discs[3 * q + 2];
                     const float cx = X - lx, cy = Y - ly;
                     const float dc = sqrtf(cx * cx + cy * cy);
-                    if (dc > a.range_max * 1.001f + fabsf(Rd) + 0.01f) continue;   // out of sight (see the segments)
-                    if (dc <= Rd * 1.05f + 1e-3f) { k0 = 0; cnt = NB; }
-                    else {
-                        const float half = asinf(fminf(Rd / dc, 1.0f)) * 1.01f + 1e-4f;
-                        beam_window(atan2f(cy, cx) - half, 2.0f * half, lt, k0, cnt);
+                    if (!(dc > a.range_max * 1.001f + fabsf(Rd) + 0.01f)) {   // else out of sight (see the segments)
+                        if (dc <= Rd * 1.05f + 1e-3f) { k0 = 0; cnt = NB; }
+                        else {
+                            const float half = asinf(fminf(Rd / dc, 1.0f)) * 1.01f + 1e-4f;
+                            beam_window(atan2f(cy, cx) - half, 2.0f * half, lt, k0, cnt);
+                        }
                     }
+                }
+                win[o] = (k0 & 0xffff) | (cnt << 16);
+            }
+            cta_sync<WPE>();
+            for (int o = warp; o < n_obs; o += WPE) {
+                const int w = win[o], cnt = w >> 16, k0 = (int)(short)(w & 0xffff);
+                if (cnt == 0) continue;
+                if (o < ns) {
+                    const float4 sg = *reinterpret_cast<const float4 *>(segs + 4 * o);
+                    for (int i = lane; i < cnt; i += 32) {
+                        const int k = (k0 + i) & (NB - 1);
+                        const float tt = seg_hit(lx, ly, sm.dir[k].x, sm.dir[k].y, sg.x, sg.y, sg.z, sg.w);
+                        if (tt < CUDART_INF_F) atomicMin(&sm.scan[k], __float_as_int(tt));
+                    }
+                } else {
+                    const int q = o - ns;
+                    const float X = discs[3 * q], Y = discs[3 * q + 1], Rd = discs[3 * q + 2];
                     for (int i = lane; i < cnt; i += 32) {
                         const int k = (k0 + i) & (NB - 1);
                         const float tt = disc_hit(lx, ly, sm.dir[k].x, sm.dir[k].y, X, Y, Rd);
