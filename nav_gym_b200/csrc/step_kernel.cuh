@@ -14,7 +14,7 @@ __device__ unsigned long long g_prof[16];
 struct EnvSmem {
     int scan[NB];          // float bits of the ranges [m] (non-negative floats order like ints)
     float2 dir[NB];        // beam directions (cos, sin) of the current pass
-    double red[16];
+    double red[4];         // per-warp partial minima (NAVGYM_CTA_THREADS / 32 <= 4)
     // per-environment scalars parked here between the phases that need them, so the march
     // loop runs with a small register footprint
     double px, py, th, gx, gy, ppx, ppy, pyaw, pv, pw, act_v, act_w;
@@ -55,6 +55,12 @@ __device__ __forceinline__ float edt_at(const EnvSmem &sm, const float *__restri
 #endif
 }
 
+#if !defined(NAVGYM_PROFILE) && !defined(NAVGYM_SMEM_WINDOW)
+// 16 resident CTAs x (sizeof(EnvSmem) + 1 KB the system reserves per CTA) must fit the 132 KB
+// shared-memory configuration: 64 bytes more and the driver picks the 164 KB one, taking 32 KB
+// from the L1 the EDT gathers go through.
+static_assert(sizeof(EnvSmem) <= 132 * 1024 / 16 - 1024, "EnvSmem outgrew the 132 KB carve-out at 16 CTAs/SM");
+#endif
 enum { PASS_STEP = 0, PASS_RESCAN = 1, PASS_RESET = 2, PASS_END = 3 };
 #ifndef NAVGYM_HEAD_STEPS
 #define NAVGYM_HEAD_STEPS 4  // samples every beam marches in the lockstep head phase
@@ -166,8 +172,11 @@ __device__ __forceinline__ void march_tail_dealt(EnvSmem &sm, const float *__res
     float2 dd = sm.dir[kb >= 0 ? kb : 0];
     unsigned live = __ballot_sync(FULL, kb >= 0);
     if (!live) return;
-    // ---- regime A
-    while (!COOP || NAVGYM_COOP_ENTER == 0 || warp + WPE * next_j < n_alive || __popc(live) > NAVGYM_COOP_ENTER) {
+    // ---- regime A.  The warp's dealing state (next_j, live) and with it the switch to regime B
+    // only change in an iteration in which some beam ended: all of that sits behind one
+    // warp-uniform test of the ballot.
+    bool to_b = COOP && NAVGYM_COOP_ENTER != 0 && !(warp + WPE * next_j < n_alive) && __popc(live) <= NAVGYM_COOP_ENTER;
+    while (!to_b) {
         const int cx = __float2int_rz(march_pos(dd.x, t, x0));
         const int cy = __float2int_rz(march_pos(dd.y, t, y0));
         const bool inb = ((unsigned)cx < (unsigned)W) & ((unsigned)cy < (unsigned)H);
@@ -176,23 +185,26 @@ __device__ __forceinline__ void march_tail_dealt(EnvSmem &sm, const float *__res
         t = __fadd_rn(t, fmaxf(__fmul_rn(d, 0.999f), 1.0f));
         const bool fin = (kb >= 0) & (!inb | hit | !(t < t_stop));
         const unsigned fm = __ballot_sync(FULL, fin);
-        if (fin) {
-            // absolute hit cell, (y << 16 | x), or -1 for "no hit"
-            sm.scan[kb] = hit ? (cy << 16 | cx) : -1;
-            idx = warp + WPE * (next_j + __popc(fm & ((1u << lane) - 1u)));
-            kb = -1;
-            if (idx < n_alive) {
-                kb = sm.alive[idx];
-                t = __int_as_float(sm.scan[kb]);
-                dd = sm.dir[kb];
-            }
-        }
-        next_j += __popc(fm);
-        live = __ballot_sync(FULL, kb >= 0);
 #ifdef NAVGYM_PROFILE
         if (lane == 0) sm.prof_iters_a[warp]++;
 #endif
-        if (!live) return;
+        if (fm) {
+            if (fin) {
+                // absolute hit cell, (y << 16 | x), or -1 for "no hit"
+                sm.scan[kb] = hit ? (cy << 16 | cx) : -1;
+                idx = warp + WPE * (next_j + __popc(fm & ((1u << lane) - 1u)));
+                kb = -1;
+                if (idx < n_alive) {
+                    kb = sm.alive[idx];
+                    t = __int_as_float(sm.scan[kb]);
+                    dd = sm.dir[kb];
+                }
+            }
+            next_j += __popc(fm);
+            live = __ballot_sync(FULL, kb >= 0);
+            if (!live) return;
+            to_b = COOP && NAVGYM_COOP_ENTER != 0 && !(warp + WPE * next_j < n_alive) && __popc(live) <= NAVGYM_COOP_ENTER;
+        }
     }
     // ---- regime B: `live` marks the lanes that hold a marching beam (kb, t, dd)
 #ifdef NAVGYM_PROFILE
@@ -696,9 +708,10 @@ __device__ __forceinline__ void step_body(const navgym_step_args_t &a, EnvSmem &
                 const double ddx = __dsub_rn(gx, qx), ddy = __dsub_rn(gy, qy);
                 const double dq = sqrt(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)));
                 const double dist_g = __shfl_sync(FULL, dq, 0), pdist = __shfl_sync(FULL, dq, 1);
-                __syncwarp();  // lane 1 has read sm.ppx / sm.ppy before lane 0 may rewrite the pose below
+                const int steps_now = sm.steps;
+                __syncwarp();  // every lane has read sm.ppx / sm.ppy / sm.steps before lane 0 may rewrite them below
                 const int success = dist_g < a.dist_thresh;
-                const int trunc = a.max_episode_steps > 0 && sm.steps >= a.max_episode_steps && !(success || crash);
+                const int trunc = a.max_episode_steps > 0 && steps_now >= a.max_episode_steps && !(success || crash);
                 const int done = success || crash || trunc;
                 if (lane == 0) {
                     const double pv = sm.pv, pw = sm.pw;
