@@ -254,16 +254,19 @@ def config_c5(torch, dev, steps, warmup, world_mp):
     env = BatchedNavGym(B, world_mp, device=dev, seed=7, auto_reset=True)
     env.reset_from_spawn_pool(np.random.RandomState(3))
     torch.manual_seed(0)
-    net = torch.nn.Sequential(torch.nn.Linear(519, 256), torch.nn.Tanh(), torch.nn.Linear(256, 256),
+    # the 519 observation columns are handed over as rows of 520 bf16 (one zero column): a 519-wide
+    # bf16 row is 1038 bytes, which no tensor-core GEMM can load with aligned vectors
+    net = torch.nn.Sequential(torch.nn.Linear(520, 256), torch.nn.Tanh(), torch.nn.Linear(256, 256),
                               torch.nn.Tanh(), torch.nn.Linear(256, 2)).to(dev).to(torch.bfloat16)
     lo = torch.tensor(ACTION_LO, device=dev)
     hi = torch.tensor(ACTION_HI, device=dev)
-    scale = torch.ones(519, device=dev, dtype=torch.bfloat16)
+    scale = torch.ones(519, device=dev)
     scale[:512] = 1.0 / 25.0
+    x = torch.zeros(B, 520, device=dev, dtype=torch.bfloat16)
 
     @torch.no_grad()
     def policy(i):
-        x = env.obs.to(torch.bfloat16) * scale
+        torch.mul(env.obs, scale, out=x[:, :519])      # scale + cast in one pass over the rows
         return lo + (hi - lo) * torch.sigmoid(net(x).float())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for i in range(warmup):
@@ -278,7 +281,7 @@ def config_c5(torch, dev, steps, warmup, world_mp):
     bank = _bank(torch, dev, 32, B, 55)
     ms_env, _ = device_leg(torch, env, lambda i: bank[i % 32], steps, warmup)
     ms_env = float(ms_env.mean())
-    return {"envs": B, "policy": "torch MLP 519-256-256-2 bf16 on device, obs consumed in place",
+    return {"envs": B, "policy": "torch MLP 519-256-256-2 bf16 on device (input rows zero-padded to 520 columns), obs consumed in place",
             "steps": steps, "warmup": warmup, "ms_per_step": ms, "env_steps_per_s": B / ms * 1e3,
             "ms_per_step_env_only": ms_env,
             "roofline_gather": gather_block(B, ms_env, GATHERS_PER_ENV_STEP, "as C2 (same world)")}
@@ -385,7 +388,19 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+        # NCCL prints its version banner on stdout when the first communicator comes up; stdout
+        # is for the one JSON line, so file descriptor 1 points at stderr meanwhile
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     from nav_gym_b200 import _lib
     from nav_gym_b200.batched_env import BatchedNavGym, MapPool
     import ctypes as C

@@ -175,7 +175,8 @@ __device__ __forceinline__ void march_tail_dealt(EnvSmem &sm, const float *__res
     // ---- regime A.  The warp's dealing state (next_j, live) and with it the switch to regime B
     // only change in an iteration in which some beam ended: all of that sits behind one
     // warp-uniform test of the ballot.
-    bool to_b = COOP && NAVGYM_COOP_ENTER != 0 && !(warp + WPE * next_j < n_alive) && __popc(live) <= NAVGYM_COOP_ENTER;
+    constexpr int coop_enter = NAVGYM_COOP_ENTER;
+    bool to_b = COOP && NAVGYM_COOP_ENTER != 0 && !(warp + WPE * next_j < n_alive) && __popc(live) <= coop_enter;
     while (!to_b) {
         const int cx = __float2int_rz(march_pos(dd.x, t, x0));
         const int cy = __float2int_rz(march_pos(dd.y, t, y0));
@@ -203,7 +204,7 @@ __device__ __forceinline__ void march_tail_dealt(EnvSmem &sm, const float *__res
             next_j += __popc(fm);
             live = __ballot_sync(FULL, kb >= 0);
             if (!live) return;
-            to_b = COOP && NAVGYM_COOP_ENTER != 0 && !(warp + WPE * next_j < n_alive) && __popc(live) <= NAVGYM_COOP_ENTER;
+            to_b = COOP && NAVGYM_COOP_ENTER != 0 && !(warp + WPE * next_j < n_alive) && __popc(live) <= coop_enter;
         }
     }
     // ---- regime B: `live` marks the lanes that hold a marching beam (kb, t, dd)
