@@ -411,7 +411,8 @@ void navgym_policy_workspace_layout(int max_n, uint64_t *out7);
 
 /* ---- inner native boundary: range_libc --------------------------------------------- */
 /* PyOMap(bool[H,W]) + PyRayMarching(omap, max_range) (env.py:337-340): exact Euclidean
- * distance transform of occ_dev (u8, non-zero = occupied, [H][W], row = y) into dist_dev. */
+ * distance transform of occ_dev (u8, non-zero = occupied, [H][W], row = y) into dist_dev.
+ * W <= 12000 and H <= 32767 cells (cudaErrorInvalidValue otherwise). */
 int navgym_edt_build(const uint8_t *occ_dev, int H, int W, float *dist_dev, int32_t *scratch_dev,
                      void *stream);
 /* PyRayMarching.calc_range_many(ins f32[N,3], outs f32[N]) (env.py:425), ranges in cells. */

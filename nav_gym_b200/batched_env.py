@@ -64,6 +64,8 @@ class MapPool(object):
         self.offsets = []
         off = 0
         for m in maps:
+            if not (0 < int(m['width']) <= 12000 and 0 < int(m['height']) <= 32767):
+                raise ValueError('map of %d x %d cells: at most 12000 wide and 32767 high' % (int(m['width']), int(m['height'])))
             self.offsets.append(off)
             off += int(m['height']) * int(m['width'])
         self.edt_pool = torch.empty(off, dtype=torch.float32, device=self.device)

@@ -327,7 +327,9 @@ int navgym_agent_scan_batch(const navgym_scan_args_t *args, void *stream)
 
 int navgym_edt_build(const uint8_t *occ_dev, int H, int W, float *dist_dev, int32_t *scratch_dev, void *stream)
 {
-    if (H <= 0 || W <= 0 || W > 12000) return (int)cudaErrorInvalidValue;
+    // W: one row of int32 in the default 48 KB of dynamic shared memory; H: hit cells travel as
+    // (y << 16 | x) through the march
+    if (H <= 0 || W <= 0 || W > 12000 || H > 32767) return (int)cudaErrorInvalidValue;
     cudaStream_t st = (cudaStream_t)stream;
     edt_columns_kernel<<<(W + 127) / 128, 128, 0, st>>>(occ_dev, H, W, scratch_dev);
     edt_rows_kernel<<<H, 256, (size_t)W * sizeof(int32_t), st>>>(scratch_dev, H, W, dist_dev);

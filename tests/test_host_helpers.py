@@ -175,3 +175,27 @@ def test_bench_world_fixture_obeys_the_episode_law():
                         params=dict(t_stop=502.0))
     obs = o.reset_obs(want_hits=False)
     assert not (obs[:, :512] < o.dthr[None, :]).any()
+
+
+def test_map_pool_rejects_oversized_maps():
+    """Hit cells travel as (y << 16 | x) and an EDT row is staged in 48 KB of shared memory: the
+    pool refuses maps beyond 12000 x 32767 cells before any device work."""
+    import pytest
+    from nav_gym_b200 import batched_env, _lib
+    lib = None
+    try:
+        lib = _lib.load()
+    except Exception:
+        pytest.skip('library not built')
+
+    m = dict(width=13000, height=10, origin=(0., 0.), resolution=0.05, data=None)
+    orig = _lib.require_device
+    _lib.require_device = lambda: lib          # the check comes before the first device call
+    try:
+        with pytest.raises(ValueError):
+            batched_env.MapPool([m], 'cpu')
+        m = dict(width=10, height=40000, origin=(0., 0.), resolution=0.05, data=None)
+        with pytest.raises(ValueError):
+            batched_env.MapPool([m], 'cpu')
+    finally:
+        _lib.require_device = orig
