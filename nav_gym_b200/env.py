@@ -8,10 +8,12 @@
 helpers ``ros_env.py`` imports.  Every per-step number comes from the CUDA kernels behind
 include/navgym_b200.h (a batch of one environment); this module is host glue.
 
-What differs from the reference, by design: pedestrians are scripted
-walkers on the device instead of a CNN policy whose weights are not distributed; episodes are
-sampled with this package's map generator and spawn sampler (``maps.py``) rather than
-map_generator.py + pyastar2d; ``render`` is not provided.
+What differs from the reference, by design: episodes are sampled with this
+package's map generator and spawn sampler (``maps.py``: maps in the reference's style, spawns
+obeying env.py:379, 761, 779-783) rather than map_generator.py + pyastar2d; the pedestrians are
+the reference's policy-driven ones (``pedestrians.PedestrianSim``, env.py:617-693) following
+geodesic distance fields instead of pyastar2d paths, with random-init policy weights unless
+NAVGYM_HUMAN_POLICY names the reference's undistributed ``human_policy.pth``.
 """
 import numpy as np
 
