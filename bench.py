@@ -35,6 +35,7 @@ sys.path.insert(0, ROOT)
 
 ENVS_PER_GPU = 4096
 NB = 512
+OBS_DIM = NB + 7
 METRIC = "env-steps/sec"
 BYTES_PER_ENV_STEP = 2197  # obs 2076 + reward 4 + done 1 + info 12 + action 8 + state 96
 WORKLOAD = ("NavGym-v0 x%d envs/GPU, static indoor map 1000x1000 @0.05m (reference "
@@ -287,6 +288,36 @@ def config_c5(torch, dev, steps, warmup, world_mp):
             "roofline_gather": gather_block(B, ms_env, GATHERS_PER_ENV_STEP, "as C2 (same world)")}
 
 
+def config_her(torch, dev, env):
+    """compute_rewards / compute_terminals / compute_info for stored observations
+    (the reference's HER relabelling entry points, env.py:491-589) as one streaming kernel over
+    2^20 rows.  HBM-bound: 2095 algorithmic bytes per row (2076 row + 8 goal in, 11 out)."""
+    N, per_row = 1 << 20, 2095
+    g = torch.Generator(device=dev)
+    g.manual_seed(11)
+    obs = torch.rand(N, OBS_DIM, device=dev, generator=g) * 10.0 + 1.5   # mostly clear of the thresholds
+    obs[:, NB:NB + 4] = torch.rand(N, 4, device=dev, generator=g) * 50.0
+    goals = torch.rand(N, 2, device=dev, generator=g) * 50.0
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ts = []
+    for i in range(13):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = env.compute_rewards(obs, goals)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        if i >= 3:
+            ts.append(e0.elapsed_time(e1))
+    ms = float(np.mean(ts))
+    peak, src = measured_peak()
+    gbs = N * per_row / (ms * 1e-3) / 1e9
+    return {"rows": N, "ms": ms, "rows_per_s": N / ms * 1e3, "l2": "flushed before every call",
+            "crash_frac": float(out['is_crash'].float().mean()),
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                         "peak_source": src, "kernel": "her_kernel", "algorithmic_bytes_per_row": per_row}}
+
+
 def config_crowd(torch, dev, steps, warmup, world_mp):
     """the C2 world with the reference's policy-driven pedestrians on the device
     (PedestrianSim: 10 per environment, each with its own 512-beam scan and a CNN policy forward
@@ -517,6 +548,7 @@ def main():
             cfg['c3'] = config_c3(torch, dev, ks, kw)
             cfg['c5'] = config_c5(torch, dev, ks, kw, mp)
             cfg['crowd'] = config_crowd(torch, dev, ks, kw, mp)
+            cfg['her'] = config_her(torch, dev, env)
 
     t = torch.tensor([total_ms] + (e2e or [0.0, 0.0, 0.0]) + [c4_ms], dtype=torch.float64, device=dev)
     if world > 1:

@@ -154,7 +154,16 @@ int navgym_compute_rewards(const navgym_her_args_t *args, void *stream)
     if (args->count <= 0) return 0;
     if (args->obs_stride < (args->num_scan_stack > 1 ? args->num_scan_stack : 1) * NB + NAVGYM_OBS_TAIL)
         return (int)cudaErrorInvalidValue;
-    her_kernel<<<(args->count + 7) / 8, 256, 0, (cudaStream_t)stream>>>(*args);
+    // warps stride over the rows: at most one full wave of CTAs
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    const int warps_per_cta = NAVGYM_HER_THREADS / 32;
+    const int want = (args->count + warps_per_cta - 1) / warps_per_cta;
+    const int ctas = want < sms * NAVGYM_HER_CTAS_PER_SM ? want : sms * NAVGYM_HER_CTAS_PER_SM;
+    her_kernel<<<ctas, NAVGYM_HER_THREADS, 0, (cudaStream_t)stream>>>(*args);
     g_launches++;
     return (int)cudaGetLastError();
 }

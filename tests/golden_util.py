@@ -12,7 +12,7 @@ NB = 512
 def trace_names():
     """the robot-step traces (humans_*.npz hold the pedestrian pipeline, see human_trace_names)"""
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, '*.npz'))
-                  if os.path.basename(p) not in ('known_answers.npz', 'bench_world.npz', 'native_calls.npz')
+                  if os.path.basename(p) not in ('known_answers.npz', 'bench_world.npz', 'native_calls.npz', 'her_batch.npz')
                   and not os.path.basename(p).startswith('humans_'))
 
 

@@ -65,3 +65,40 @@ def random_geometry(rng, B, start, max_disc, max_seg, spread=6.0):
             w = np.column_stack([co * fp[:, 0] - si * fp[:, 1] + cx, si * fp[:, 0] + co * fp[:, 1] + cy])
             segs[e, 4 * b:4 * b + 4] = np.concatenate([w, np.roll(w, -1, axis=0)], axis=1)
     return discs, ndisc, segs, nseg
+
+
+def her_batch(seed=5, n=6000):
+    """Stored observations for the HER entry points (compute_rewards / compute_terminals,
+    env.py:491-589): float32 rows [scan(512) | prev_pose pose vel yaw] and goals, a mix of rows
+    clear of every threshold, rows in discomfort (some beams between the crash and the discomfort
+    threshold of their angle), crashed rows and rows at the goal.  The same seed gives the same
+    batch in oracle/make_golden_her.py (which pushes it through the reference's own functions)
+    and in the tests; thresholds are passed in because they come from the implementation under
+    test / the reference."""
+    rng = np.random.RandomState(seed)
+    scan = rng.uniform(2.0, 25.0, (n, 512)).astype(np.float32)
+    kind = rng.randint(0, 4, n)                      # 0 clear, 1 discomfort, 2 crash, 3 clear + at goal
+    frac = rng.uniform(0.02, 0.98, (n, 512)).astype(np.float32)
+    pick = rng.uniform(0, 1, (n, 512)) < 0.02        # ~10 beams per row carry the close return
+    pose = rng.uniform(5, 45, (n, 2))
+    prev = pose + rng.uniform(-0.1, 0.1, (n, 2))
+    vel = np.column_stack([rng.uniform(0, 0.5, n), rng.uniform(-0.64, 0.64, n)])
+    yaw = rng.uniform(-np.pi, np.pi, n)
+    goal = pose + rng.uniform(-15, 15, (n, 2))
+    at_goal = kind == 3
+    goal[at_goal] = pose[at_goal] + rng.uniform(-0.3, 0.3, (int(at_goal.sum()), 2))
+    tail = np.column_stack([prev, pose, vel, yaw]).astype(np.float32)
+    return dict(scan=scan, kind=kind, frac=frac, pick=pick, tail=tail, goal=goal.astype(np.float32))
+
+
+def her_rows(batch, thr, dthr):
+    """The observation rows of her_batch() for the given crash / discomfort threshold vectors."""
+    scan = batch['scan'].copy()
+    thr, dthr = np.asarray(thr, np.float32), np.asarray(dthr, np.float32)
+    between = (thr + batch['frac'] * (dthr - thr)).astype(np.float32)     # inside the discomfort band
+    below = (thr * batch['frac']).astype(np.float32)                       # inside the footprint
+    d = (batch['kind'] == 1)[:, None] & batch['pick']
+    c = (batch['kind'] == 2)[:, None] & batch['pick']
+    scan[d] = between[d]
+    scan[c] = below[c]
+    return np.concatenate([scan, batch['tail']], axis=1).astype(np.float32)

@@ -161,3 +161,30 @@ def test_gym_make_scan_stack():
     o2 = o2['observation']
     if not info['is_crash']:
         assert np.array_equal(o2[:512], s0) and np.array_equal(o2[512:1024], s1)
+
+
+def test_her_kernel_known_answers_batch():
+    """6000 stored observations (clear / in discomfort / crashed / at the goal; more rows than one
+    wave of the kernel's warps, so every warp strides over several) against the outputs of the
+    reference's own compute_rewards / compute_terminals on the same float64 rows
+    (tests/golden/her_batch.npz, minted by oracle/make_golden_her.py)."""
+    import os
+    import synth
+    from nav_gym_b200.batched_env import BatchedNavGym
+    G = np.load(os.path.join(gu.GOLDEN, 'her_batch.npz'))
+    rng = np.random.RandomState(0)
+    env = BatchedNavGym(1, [synth.outdoor_map(rng, size=100, n_obs=2)], device='cuda:0')
+    assert np.array_equal(env.scan_threshold, G['thr']) and np.array_equal(env.scan_discomfort_threshold, G['dthr'])
+    b = synth.her_batch()
+    rows = synth.her_rows(b, G['thr'], G['dthr'])
+    out = env.compute_rewards(torch.from_numpy(rows).cuda(), torch.from_numpy(b['goal']).cuda())
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    assert np.array_equal(out['done'].astype(bool), G['done'])
+    # float32 output of the float64 sum the reference forms: half an ulp at |reward| <= 16
+    assert np.allclose(out['reward'], G['reward'], rtol=0, atol=1.0e-6)
+    assert (b['kind'] == 1).sum() > 1000 and (out['is_crash'] == 1).sum() > 1000
+    # a strided, padded view of the same rows (obs_stride > 519) gives the same answers
+    wide = torch.zeros(len(rows), 600, device='cuda')
+    wide[:, :519] = torch.from_numpy(rows).cuda()
+    out2 = env.compute_rewards(wide[:, :519], torch.from_numpy(b['goal']).cuda())
+    assert torch.equal(out2['reward'].cpu(), torch.from_numpy(out['reward']))
