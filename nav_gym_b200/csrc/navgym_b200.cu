@@ -32,6 +32,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 
 #include "../../include/navgym_b200.h"
 
@@ -376,27 +377,67 @@ int navgym_render_discs_in_lidar(float *ranges_dev, const float *headings_dev, i
     return (int)cudaGetLastError();
 }
 
+// Scratch of the host-buffer natives: one grow-only device buffer and one pinned staging buffer
+// per device, reused from call to call (the reference calls these natives 1 + num_humans times per
+// step: a cudaMalloc / cudaFree pair and four pageable copies per call cost several times the
+// kernel).  Calls are serialised by a mutex, like the GIL-holding originals.
+struct host_scratch {
+    float *dev = nullptr, *pin = nullptr;
+    size_t cap = 0;
+};
+static std::mutex g_scratch_mutex;
+static host_scratch g_scratch[64];
+static cudaError_t scratch_for(size_t nfloats, host_scratch *&out)
+{
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err) return err;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    host_scratch &s = g_scratch[dev];
+    if (s.cap < nfloats) {
+        if (s.dev) cudaFree(s.dev);
+        if (s.pin) cudaFreeHost(s.pin);
+        s.dev = s.pin = nullptr;
+        s.cap = 0;
+        size_t cap = 4096;
+        while (cap < nfloats) cap *= 2;
+        err = cudaMalloc(&s.dev, cap * sizeof(float));
+        if (!err) err = cudaMallocHost(&s.pin, cap * sizeof(float));
+        if (err) {
+            if (s.dev) cudaFree(s.dev);
+            s.dev = nullptr;
+            return err;
+        }
+        s.cap = cap;
+    }
+    out = &s;
+    return cudaSuccess;
+}
+
 int navgym_render_in_lidar_host(float *ranges_host, const float *headings_host, int K,
                                 const float *segs_host, int S, const float *discs_host, int D,
                                 float ox, float oy)
 {
     if (K <= 0) return 0;
-    float *buf = nullptr;
-    size_t nf = (size_t)2 * K + (size_t)4 * S + (size_t)3 * D;
-    CK(cudaMalloc(&buf, nf * sizeof(float)));
-    float *r = buf, *hd = buf + K, *sg = hd + K, *dc = sg + 4 * S;
-    cudaError_t err = cudaMemcpy(r, ranges_host, K * sizeof(float), cudaMemcpyHostToDevice);
-    if (!err) err = cudaMemcpy(hd, headings_host, K * sizeof(float), cudaMemcpyHostToDevice);
-    if (!err && S) err = cudaMemcpy(sg, segs_host, (size_t)4 * S * sizeof(float), cudaMemcpyHostToDevice);
-    if (!err && D) err = cudaMemcpy(dc, discs_host, (size_t)3 * D * sizeof(float), cudaMemcpyHostToDevice);
-    if (!err) {
-        render_in_lidar_kernel<<<(K + 127) / 128, 128>>>(r, hd, K, sg, S, dc, D, ox, oy);
-        g_launches++;
-        err = cudaGetLastError();
-    }
-    if (!err) err = cudaMemcpy(ranges_host, r, K * sizeof(float), cudaMemcpyDeviceToHost);
-    cudaFree(buf);
-    return (int)err;
+    if (S < 0 || D < 0) return (int)cudaErrorInvalidValue;
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
+    const size_t nf = (size_t)2 * K + (size_t)4 * S + (size_t)3 * D;
+    host_scratch *sc = nullptr;
+    CK(scratch_for(nf, sc));
+    // one staged copy in: [ranges | headings | segments | discs]
+    float *r = sc->dev, *hd = r + K, *sg = hd + K, *dc = sg + 4 * (size_t)S;
+    memcpy(sc->pin, ranges_host, K * sizeof(float));
+    memcpy(sc->pin + K, headings_host, K * sizeof(float));
+    if (S) memcpy(sc->pin + 2 * (size_t)K, segs_host, (size_t)4 * S * sizeof(float));
+    if (D) memcpy(sc->pin + 2 * (size_t)K + 4 * (size_t)S, discs_host, (size_t)3 * D * sizeof(float));
+    CK(cudaMemcpyAsync(sc->dev, sc->pin, nf * sizeof(float), cudaMemcpyHostToDevice, 0));
+    render_in_lidar_kernel<<<(K + 127) / 128, 128>>>(r, hd, K, sg, S, dc, D, ox, oy);
+    g_launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(sc->pin, r, K * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+    memcpy(ranges_host, sc->pin, K * sizeof(float));
+    return 0;
 }
 
 struct navgym_raymarching {
@@ -429,14 +470,19 @@ int navgym_raymarching_calc_range_many_host(navgym_raymarching_t *rm, const floa
 {
     if (!rm) return (int)cudaErrorInvalidValue;
     if (N <= 0) return 0;
-    float *buf = nullptr;
-    CK(cudaMalloc(&buf, (size_t)4 * N * sizeof(float)));
-    cudaError_t err = cudaMemcpy(buf, ins_host, (size_t)3 * N * sizeof(float), cudaMemcpyHostToDevice);
-    if (!err) err = (cudaError_t)navgym_calc_range_many(rm->dist, rm->W, rm->H, buf, buf + 3 * N, N,
-                                                        rm->max_range, rm->max_range, nullptr, nullptr);
-    if (!err) err = cudaMemcpy(outs_host, buf + 3 * N, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost);
-    cudaFree(buf);
-    return (int)err;
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
+    host_scratch *sc = nullptr;
+    CK(scratch_for((size_t)4 * N, sc));
+    memcpy(sc->pin, ins_host, (size_t)3 * N * sizeof(float));
+    CK(cudaMemcpyAsync(sc->dev, sc->pin, (size_t)3 * N * sizeof(float), cudaMemcpyHostToDevice, 0));
+    const int lerr = navgym_calc_range_many(rm->dist, rm->W, rm->H, sc->dev, sc->dev + 3 * (size_t)N, N,
+                                            rm->max_range, rm->max_range, nullptr, nullptr);
+    if (lerr) return lerr;
+    CK(cudaMemcpyAsync(sc->pin + 3 * (size_t)N, sc->dev + 3 * (size_t)N, (size_t)N * sizeof(float),
+                       cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+    memcpy(outs_host, sc->pin + 3 * (size_t)N, (size_t)N * sizeof(float));
+    return 0;
 }
 
 // Reset-path host helper (no device work): 4-connected BFS distance over a grid, the
