@@ -38,6 +38,15 @@ TRACES = [
     # signed linear velocities reach both branches of the clamp
     ('indoor_n2_turnradius', 18, 1.0, [2, 2], 'random_signed', 150, 1, 0.5),
     ('outdoor_n6_turnradius_seek', 19, 0.0, [6, 6], 'seek', 400, 1, 0.5),
+    # every constructor kwarg of the step path off its default (nav_gym_env/__init__.py:8-25): time
+    # step, goal radius and all seven reward factors -- reward_forward_factor is 0 by default, so
+    # only this trace sees the forward term of env.py:571
+    ('indoor_n4_params', 20, 1.0, [4, 4], 'seek', 500, 1, 0.0,
+     dict(time_step=0.1, distance_threshold=0.8, reward_scale=10., reward_success_factor=0.8,
+          reward_crash_factor=1.5, reward_progress_factor=0.002, reward_forward_factor=0.02,
+          reward_rotation_factor=0.01, reward_discomfort_factor=0.03)),
+    # (num_humans = 0 is not a configuration of the reference: HumanPolicy.forward fails on the empty
+    # batch, human_policy.py:45)
 ]
 
 
@@ -72,7 +81,7 @@ def _pack(recs, key, width):
     return out, cnt
 
 
-def run_trace(name, seed, indoor_ratio, nh, mode, max_steps, stack=1, min_turning_radius=0.0):
+def run_trace(name, seed, indoor_ratio, nh, mode, max_steps, stack=1, min_turning_radius=0.0, extra=None):
     np.random.seed(seed)
     import torch
     torch.manual_seed(seed)
@@ -81,7 +90,7 @@ def run_trace(name, seed, indoor_ratio, nh, mode, max_steps, stack=1, min_turnin
                obstacle_number=([10, 10], 'int'), obstacle_width=([0.3, 1.0], 'float'),
                scan_noise_std=([0., 0.05], 'float'))
     env = rh.make_env(indoor_ratio=indoor_ratio, env_param_range=epr, num_scan_stack=stack,
-                      min_turning_radius=min_turning_radius)
+                      min_turning_radius=min_turning_radius, **(extra or {}))
     NS = NB * stack
     rh.REC.clear()
     obs0 = env.reset()
@@ -99,6 +108,8 @@ def run_trace(name, seed, indoor_ratio, nh, mode, max_steps, stack=1, min_turnin
         discs0=first['discs'], segs0=first['segs'],
         noise0=first['noise'] if first['noise'] is not None else np.zeros(NB, np.float32),
     )
+    for k, v in (extra or {}).items():
+        G['kw_' + k] = np.float64(v)
     recs1, recs2, rows = [], [], []
     for t in range(max_steps):
         a = _action(mode, env, rng)

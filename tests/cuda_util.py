@@ -41,4 +41,5 @@ def golden_stepper(G, early_stop, cell_rule='numpy2'):
     return CudaStepper([gu.map_info(G)], np.zeros(1, np.int32), G['start'][None, :2], G['goal'][None],
                        G['start'][2:3], max_disc=md, max_seg=ms, early_stop=early_stop,
                        cell_rule=cell_rule, num_scan_stack=S,
-                       min_turning_radius=float(G['min_turning_radius']) if 'min_turning_radius' in G else 0.0)
+                       min_turning_radius=float(G['min_turning_radius']) if 'min_turning_radius' in G else 0.0,
+                       **gu.env_kwargs(G))

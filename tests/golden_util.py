@@ -47,6 +47,12 @@ def map_info(G):
                 width=d.shape[1], height=d.shape[0])
 
 
+def env_kwargs(G):
+    """Constructor kwargs a trace was minted with off their defaults (reference names:
+    time_step, distance_threshold, reward_*), stored as kw_<name> scalars."""
+    return {k[3:]: float(G[k]) for k in G if k.startswith('kw_')}
+
+
 def geom_dims(G):
     md = max(G['discs'].shape[1], len(G['discs0']), 1)
     ms = max(G['segs'].shape[1], len(G['segs0']), 1)

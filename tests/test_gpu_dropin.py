@@ -16,7 +16,7 @@ def test_her_kernel_reproduces_reference_rewards(name):
     from nav_gym_b200.batched_env import BatchedNavGym
     G = gu.load(name)
     S = int(G['num_scan_stack']) if 'num_scan_stack' in G else 1
-    env = BatchedNavGym(1, [gu.map_info(G)], device='cuda:0', num_scan_stack=S)
+    env = BatchedNavGym(1, [gu.map_info(G)], device='cuda:0', num_scan_stack=S, **gu.env_kwargs(G))
     assert np.array_equal(env.scan_threshold, G['thr'])
     obs = np.concatenate([G['scan_stack'] if S > 1 else G['scan'], G['tail'].astype(np.float32)], axis=1)
     # on a crash the reference returns the re-scanned observation, whose reward terms were

@@ -15,6 +15,11 @@ def make_oracle(G, **params):
     p = dict(cell_rule=1)  # the fixtures were minted under NumPy 2 (float32 cell division)
     p['num_scan_stack'] = int(G['num_scan_stack']) if 'num_scan_stack' in G else 1
     p['min_turn_radius'] = float(G['min_turning_radius']) if 'min_turning_radius' in G else 0.0
+    names = dict(time_step='dt', distance_threshold='dist_thresh', reward_scale='r_scale',
+                 reward_success_factor='r_success', reward_crash_factor='r_crash',
+                 reward_progress_factor='r_progress', reward_forward_factor='r_forward',
+                 reward_rotation_factor='r_rotation', reward_discomfort_factor='r_discomfort')
+    p.update({names[k]: v for k, v in gu.env_kwargs(G).items()})
     p.update(params)
     return OracleStepper([gu.map_info(G)], np.zeros(1, np.int32), G['start'][None, :2], G['goal'][None],
                          G['start'][2:3], params=p, max_disc=md, max_seg=ms)
