@@ -172,6 +172,8 @@ int navgym_compute_rewards(const navgym_her_args_t *args, void *stream)
 int navgym_peds_advance(const navgym_peds_args_t *args, void *stream)
 {
     if (args->num_envs <= 0) return 0;
+    // rows of 16 floats are moved as four 16-byte words, box segments stored as float4
+    if (((uintptr_t)args->peds & 15) || ((uintptr_t)args->segs & 15)) return (int)cudaErrorMisalignedAddress;
     peds_advance_kernel<<<(args->num_envs + 3) / 4, 128, 0, (cudaStream_t)stream>>>(*args);  // a warp per environment
     g_launches++;
     return (int)cudaGetLastError();

@@ -543,16 +543,20 @@ __global__ void __launch_bounds__(128) peds_advance_kernel(const navgym_peds_arg
     for (int p0 = 0; p0 < P; p0 += 32) {
         const int p = p0 + lane;
         const bool live = p < P;
-        float *q = pp + (live ? p : 0) * NAVGYM_PED_F;
-        float x = q[0], y = q[1], th = q[2];
+        // the pedestrian's row as four 16-byte loads: {x, y, theta, speed} {waypoint a, waypoint b}
+        // {target, distance travelled x, y, theta} {has_legs, trunk radius, -, -}
+        float4 *q4 = reinterpret_cast<float4 *>(pp + (live ? p : 0) * NAVGYM_PED_F);
+        float4 r0 = q4[0], r2 = q4[2];
+        const float4 r1 = q4[1], r3 = q4[3];
+        float x = r0.x, y = r0.y, th = r0.z;
         if (live && a.advance) {
-            const float v = q[3];
-            float tgt = q[8];
-            float gx = tgt > 0.5f ? q[6] : q[4], gy = tgt > 0.5f ? q[7] : q[5];
+            const float v = r0.w;
+            float tgt = r2.x;
+            float gx = tgt > 0.5f ? r1.z : r1.x, gy = tgt > 0.5f ? r1.w : r1.y;
             if ((gx - x) * (gx - x) + (gy - y) * (gy - y) < 0.25f) {  // reached: turn back
                 tgt = 1.0f - tgt;
-                gx = tgt > 0.5f ? q[6] : q[4];
-                gy = tgt > 0.5f ? q[7] : q[5];
+                gx = tgt > 0.5f ? r1.z : r1.x;
+                gy = tgt > 0.5f ? r1.w : r1.y;
             }
             float err = atan2f(gy - y, gx - x) - th;
             err -= 6.2831853f * rintf(err * 0.15915494f);
@@ -563,14 +567,16 @@ __global__ void __launch_bounds__(128) peds_advance_kernel(const navgym_peds_arg
             y += sinf(thn) * v * a.dt;
             // leg gait odometry in the base frame (env.py:251-255)
             const float c = cosf(thn), s_ = sinf(thn);
-            q[9] += (c * vx + s_ * vy) * a.dt;
-            q[10] += (-s_ * vx + c * vy) * a.dt;
-            q[11] += w * a.dt;
+            r2.y += (c * vx + s_ * vy) * a.dt;
+            r2.z += (-s_ * vx + c * vy) * a.dt;
+            r2.w += w * a.dt;
             th = thn - 6.2831853f * floorf(thn * 0.15915494f);
-            q[0] = x; q[1] = y; q[2] = th; q[8] = tgt;
+            r0.x = x; r0.y = y; r0.z = th; r2.x = tgt;
+            q4[0] = r0;
+            q4[2] = r2;
         }
         // what this pedestrian contributes: 1 trunk disc | 2 leg discs | 4 box segments
-        const bool legs = q[12] > 0.5f;
+        const bool legs = r3.x > 0.5f;
         const int want_d = !live ? 0 : (a.trunk_mode ? 1 : (legs ? 2 : 0));
         const int want_s = (!live || a.trunk_mode || legs || !segs) ? 0 : 4;
         int pre_d = want_d, pre_s = want_s;   // inclusive warp prefix sums
@@ -585,10 +591,10 @@ __global__ void __launch_bounds__(128) peds_advance_kernel(const navgym_peds_arg
         const bool put_d = want_d && at_d + want_d <= a.max_disc, put_s = want_s && at_s + want_s <= a.max_seg;
         const float c = cosf(th), s_ = sinf(th);
         if (put_d && a.trunk_mode) {
-            discs[3 * at_d] = x; discs[3 * at_d + 1] = y; discs[3 * at_d + 2] = q[13];
+            discs[3 * at_d] = x; discs[3 * at_d + 1] = y; discs[3 * at_d + 2] = r3.y;
         } else if (put_d) {  // legs
-            const float front = 0.3f * cosf(q[9] * (2.0f / 0.3f) + q[11]);
-            const float side = 0.1f * cosf(q[10] * (2.0f / 0.1f) + q[11]) + 0.1f;
+            const float front = 0.3f * cosf(r2.y * (2.0f / 0.3f) + r2.w);
+            const float side = 0.1f * cosf(r2.z * (2.0f / 0.1f) + r2.w) + 0.1f;
             discs[3 * at_d] = x + c * front - s_ * side; discs[3 * at_d + 1] = y + s_ * front + c * side;
             discs[3 * at_d + 2] = 0.03f;
             discs[3 * at_d + 3] = x - c * front + s_ * side; discs[3 * at_d + 4] = y - s_ * front - c * side;
