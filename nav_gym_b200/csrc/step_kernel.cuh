@@ -20,7 +20,7 @@ struct EnvSmem {
     double px, py, th, gx, gy, ppx, ppy, pyaw, pv, pw, act_v, act_w;
     double th_spec, yaw_spec;  // heading warp 1 assumed for the final pose, and its yaw
     int map, steps, episode, next_pass;
-    int next_beam;         // next undealt entry of the survivor list
+    int n_vis_seg, n_vis_disc;  // visible box segments / discs listed by the obstacle phase
     int n_alive;           // beams still marching after the head phase
     short alive[NB];       // their indices
     float noise_std;
@@ -114,7 +114,7 @@ __device__ __forceinline__ double turned_heading(double th0, double w, double dt
 
 // Per-pass scan setup from the pose in shared memory: float32 lidar pose, origin cell
 // (env.py:386, 419), map geometry.  Run by one thread.
-__device__ __forceinline__ void pass_setup(EnvSmem &sm, const navgym_map_t &m, const navgym_step_args_t &a, int next_beam)
+__device__ __forceinline__ void pass_setup(EnvSmem &sm, const navgym_map_t &m, const navgym_step_args_t &a)
 {
     sm.lx = (float)sm.px; sm.ly = (float)sm.py; sm.lt = (float)sm.th;
     sm.ci = xy_to_cell(sm.lx, m.ox, m.res, m.H, a.cell_rule);
@@ -124,7 +124,6 @@ __device__ __forceinline__ void pass_setup(EnvSmem &sm, const navgym_map_t &m, c
     sm.max_range = (float)((double)m.W * (double)m.H);
     sm.t_stop = fminf(fminf(a.t_stop, sm.max_range), 8.0e6f);
     sm.n_alive = 0;
-    sm.next_beam = next_beam;
 }
 
 template <int WPE>
@@ -493,7 +492,7 @@ __device__ __forceinline__ void step_body(const navgym_step_args_t &a, EnvSmem &
             sm.noise_std = noise_std0;
             if (IS_RESET_KERNEL) { sm.ppx = px; sm.ppy = py; sm.pyaw = 0; sm.pv = 0; sm.pw = 0; }
             if (WPE == 1) sm.th_spec = CUDART_NAN;
-            pass_setup(sm, m0, a, TPB * MARCH_SLOTS);  // first pass: the map descriptor is already here
+            pass_setup(sm, m0, a);  // first pass: the map descriptor is already here
         }
     }
     int nd = a.discs ? min(a.ndisc[e], a.max_disc) : 0;
@@ -508,7 +507,7 @@ __device__ __forceinline__ void step_body(const navgym_step_args_t &a, EnvSmem &
         cta_sync<WPE>();
         if (!first) {
             t_pass = clock64();
-            if (tid == 0) pass_setup(sm, a.maps[sm.map], a, TPB * MARCH_SLOTS);
+            if (tid == 0) pass_setup(sm, a.maps[sm.map], a);
             cta_sync<WPE>();
         }
         margin = CUDART_INF_F;
@@ -559,14 +558,19 @@ __device__ __forceinline__ void step_body(const navgym_step_args_t &a, EnvSmem &
         // (One warp per obstacle for both steps walked the list through one global-memory round
         // trip per obstacle and computed every window 32 times over.)
         if (ns + nd > 0) {
+            if (tid == 0) { sm.n_vis_seg = 0; sm.n_vis_disc = 0; }
             cta_sync<WPE>();
             // (the first scan after an auto-reset sees the next episode's pedestrians, if given)
             const bool nxt = !IS_RESET_KERNEL && pass == PASS_RESET && a.discs_reset != nullptr;
             const float *discs = (nxt ? a.discs_reset : a.discs) + (size_t)e * a.max_disc * 3;
             const float *segs = (nxt ? a.segs_reset : a.segs) + (size_t)e * a.max_seg * 4;
-            int *win = reinterpret_cast<int *>(sm.alive);   // [NB / 2]: k0 (16 bits, signed) | cnt << 16; cnt = 0: out of sight
+            // The visible obstacles are listed in the survivor list's shared memory (free since the tail
+            // phase), segments from the front and discs from the back of its NB / 2 words:
+            // index (8 bits) | k0 + 2 (10 bits) << 8 | cnt (10 bits) << 18.
+            int *vis = reinterpret_cast<int *>(sm.alive);
             const int n_obs = min(ns + nd, NB / 2);         // (host: max_seg + max_disc <= NB / 2)
-            for (int o = tid; o < n_obs; o += TPB) {
+            for (int o0 = 0; o0 < n_obs; o0 += TPB) {
+                const int o = o0 + tid;
                 int k0 = 0, cnt = 0;
                 if (o < ns) {
                     const float4 sg = *reinterpret_cast<const float4 *>(segs + 4 * o);
@@ -585,7 +589,7 @@ __device__ __forceinline__ void step_body(const navgym_step_args_t &a, EnvSmem &
                         if (fabsf(dl) > 3.0f || da2 < 1e-6f || db2 < 1e-6f) { k0 = 0; cnt = NB; }
                         else beam_window(dl >= 0 ? pa : pb, fabsf(dl), lt, k0, cnt);
                     }
-                } else {
+                } else if (o < n_obs) {
                     const int q = o - ns;
                     const float X = discs[3 * q], Y = discs[3 * q + 1], Rd = discs[3 * q + 2];
                     const float cx = X - lx, cy = Y - ly;
@@ -598,24 +602,47 @@ __device__ __forceinline__ void step_body(const navgym_step_args_t &a, EnvSmem &
                         }
                     }
                 }
-                win[o] = (k0 & 0xffff) | (cnt << 16);
+                // list the visible ones (the order within a list does not matter: hits are min-merged)
+                const bool is_seg = o < ns;
+                const unsigned ms_ = __ballot_sync(FULL, cnt > 0 && is_seg), md_ = __ballot_sync(FULL, cnt > 0 && !is_seg);
+                int bs = 0, bd = 0;
+                if (lane == 0) {
+                    if (ms_) bs = atomicAdd(&sm.n_vis_seg, __popc(ms_));
+                    if (md_) bd = atomicAdd(&sm.n_vis_disc, __popc(md_));
+                }
+                bs = __shfl_sync(FULL, bs, 0);
+                bd = __shfl_sync(FULL, bd, 0);
+                if (cnt > 0) {
+                    const int word = (is_seg ? o : o - ns) | ((k0 + 2) & 0x3ff) << 8 | cnt << 18;   // k0 in [-2, 510], cnt <= NB = 512
+                    const unsigned below = (1u << lane) - 1u;
+                    if (is_seg) vis[bs + __popc(ms_ & below)] = word;
+                    else vis[NB / 2 - 1 - (bd + __popc(md_ & below))] = word;
+                }
             }
             cta_sync<WPE>();
-            for (int o = warp; o < n_obs; o += WPE) {
-                const int w = win[o], cnt = w >> 16, k0 = (int)(short)(w & 0xffff);
-                if (cnt == 0) continue;
-                if (o < ns) {
-                    const float4 sg = *reinterpret_cast<const float4 *>(segs + 4 * o);
-                    for (int i = lane; i < cnt; i += 32) {
-                        const int k = (k0 + i) & (NB - 1);
+            // hits: 16 lanes per visible obstacle across the beams of its window (a window is typically
+            // a dozen beams wide), segments first, then discs
+            {
+                const int grp = tid >> 4, l16 = tid & 15;
+                constexpr int NG = TPB / 16;
+                const int nvs = sm.n_vis_seg, nvd = sm.n_vis_disc;
+                for (int i = grp; i < nvs; i += NG) {
+                    const int w = vis[i];
+                    const int cnt = w >> 18, k0 = ((w >> 8) & 0x3ff) - 2;
+                    const float4 sg = *reinterpret_cast<const float4 *>(segs + 4 * (w & 0xff));
+                    for (int j = l16; j < cnt; j += 16) {
+                        const int k = (k0 + j) & (NB - 1);
                         const float tt = seg_hit(lx, ly, sm.dir[k].x, sm.dir[k].y, sg.x, sg.y, sg.z, sg.w);
                         if (tt < CUDART_INF_F) atomicMin(&sm.scan[k], __float_as_int(tt));
                     }
-                } else {
-                    const int q = o - ns;
+                }
+                for (int i = grp; i < nvd; i += NG) {
+                    const int w = vis[NB / 2 - 1 - i];
+                    const int cnt = w >> 18, k0 = ((w >> 8) & 0x3ff) - 2;
+                    const int q = w & 0xff;
                     const float X = discs[3 * q], Y = discs[3 * q + 1], Rd = discs[3 * q + 2];
-                    for (int i = lane; i < cnt; i += 32) {
-                        const int k = (k0 + i) & (NB - 1);
+                    for (int j = l16; j < cnt; j += 16) {
+                        const int k = (k0 + j) & (NB - 1);
                         const float tt = disc_hit(lx, ly, sm.dir[k].x, sm.dir[k].y, X, Y, Rd);
                         if (tt < CUDART_INF_F) atomicMin(&sm.scan[k], __float_as_int(tt));
                     }
