@@ -636,12 +636,13 @@ __device__ __forceinline__ void step_body(const navgym_step_args_t &a, EnvSmem &
                         if (tt < CUDART_INF_F) atomicMin(&sm.scan[k], __float_as_int(tt));
                     }
                 }
-                for (int i = grp; i < nvd; i += NG) {
+                // (8 lanes per disc: a leg's window is 6-8 beams)
+                for (int i = tid >> 3; i < nvd; i += TPB / 8) {
                     const int w = vis[NB / 2 - 1 - i];
                     const int cnt = w >> 18, k0 = ((w >> 8) & 0x3ff) - 2;
                     const int q = w & 0xff;
                     const float X = discs[3 * q], Y = discs[3 * q + 1], Rd = discs[3 * q + 2];
-                    for (int j = l16; j < cnt; j += 16) {
+                    for (int j = tid & 7; j < cnt; j += 8) {
                         const int k = (k0 + j) & (NB - 1);
                         const float tt = disc_hit(lx, ly, sm.dir[k].x, sm.dir[k].y, X, Y, Rd);
                         if (tt < CUDART_INF_F) atomicMin(&sm.scan[k], __float_as_int(tt));
