@@ -112,6 +112,57 @@ def test_batched_step_matches_oracle(B, T, seed):
     assert n_crash > 0 and n_succ > 0
 
 
+def test_obstacle_lists_at_capacity():
+    """The obstacle phase lists the visible obstacles in 256 shared-memory words (segments from the
+    front, discs from the back): 128 segments + 64 discs per environment, every list full and
+    everything close to the robot (nothing out of sight, some obstacles touching it: whole-scan
+    windows), some environments with far-away obstacles only (empty lists) -- scans bit-exact
+    against the oracle's all-beams loop."""
+    import cuda_util
+    rng = np.random.RandomState(21)
+    B, md, ms = 96, 64, 128
+    maps = _maps(31)
+    map_id = rng.randint(0, len(maps), B).astype(np.int32)
+    edts = [orc.edt(np.asarray(m['data']) >= 0.1) for m in maps]
+    start = np.zeros((B, 2))
+    for i, m in enumerate(maps):
+        sel = np.where(map_id == i)[0]
+        start[sel] = synth.free_poses(rng, m, len(sel), 14, edts[i])
+    goal = start + rng.uniform(-3, 3, (B, 2))
+    theta = rng.uniform(0, 2 * np.pi, B)
+    o = orc.OracleBatch(maps, map_id, start, goal, theta, params=dict(t_stop=502.0), max_disc=md, max_seg=ms)
+    c = cuda_util.CudaStepper(maps, map_id, start, goal, theta, max_disc=md, max_seg=ms, early_stop=True)
+
+    def geometry(pos):
+        discs, ndisc, segs, nseg = synth.random_geometry(rng, B, pos, md, ms, spread=3.0)
+        ndisc[:], nseg[:] = md, ms                      # full lists (unused rows of segs are filled below)
+        for e in range(B):
+            for b in range(ms // 4):
+                if not segs[e, 4 * b:4 * b + 4].any():   # a copy of the first box, shifted
+                    segs[e, 4 * b:4 * b + 4] = segs[e, 0:4] + np.tile(rng.uniform(-3, 3, 2).astype(np.float32), 2)
+        discs[:8, 0, :2] = pos[:8] + 0.01                # a disc on top of the robot
+        segs[8:16, 0] = np.concatenate([pos[8:16] - 0.5, pos[8:16] + 0.5], axis=1)   # a segment through it
+        far = np.arange(B) % 7 == 3                      # environments that see nothing
+        discs[far, :, :2] += 400.0
+        segs[far] += 400.0
+        return discs, ndisc, segs, nseg
+
+    noise = np.zeros((B, 2, 512), np.float32)
+    g = geometry(start)
+    o.reset_obs(*g, noise=noise)
+    c.reset_obs(*g, noise=noise)
+    _compare(o, c, 'reset', first=True)
+    hit_any = 0
+    for t in range(6):
+        act = rng.uniform([0.0, -0.64], [0.5, 0.64], (B, 2)).astype(np.float32)
+        g = geometry(o.state[:2].T.copy())
+        o.step(act, *g, noise=noise)
+        c.step(act, *g, noise=noise)
+        _compare(o, c, 'step %d' % t)
+        hit_any += int((o.obs[:, :512] < 3.0).sum())
+    assert hit_any > 10000
+
+
 def _compare(o, c, tag, first=False):
     assert np.array_equal(c.hits, o.hits), tag + ' hit cells'
     assert np.array_equal(c.obs[:, :512], o.obs[:, :512]), tag + ' scan'
