@@ -206,9 +206,11 @@ typedef struct {
 } navgym_her_args_t;
 int navgym_compute_rewards(const navgym_her_args_t *args, void *stream);
 
-/* ---- scripted pedestrians (stand-in for the reference's CNN-driven humans, env.py:617-662,
- * whose weights are not distributed): advance every pedestrian one time step and emit the
- * geometry the robot's lidar sees into the discs / segs buffers of navgym_step_args_t.
+/* ---- pedestrian geometry, and scripted pedestrians: emit the geometry the robot's lidar sees
+ * (leg discs env.py:398-402, box footprints env.py:404-414, or one trunk disc each) into the discs /
+ * segs buffers of navgym_step_args_t -- with advance = 1 after moving every pedestrian one time
+ * step as a waypoint walker (BASELINE configs C3 / C4), with advance = 0 for poses the caller
+ * moved itself (the policy-driven pedestrians of env.py:617-662: navgym_peds_move below).
  *   peds f32 [num_envs][max_ped][NAVGYM_PED_F] (16-byte aligned, as is segs: cudaErrorMisalignedAddress otherwise):
  *     0 x, 1 y, 2 theta, 3 speed | 4 ax, 5 ay, 6 bx, 7 by (the two waypoints) | 8 target (0/1),
  *     9..11 distance travelled in the base frame (x, y, theta; leg gait, env.py:237-255) |
