@@ -12,8 +12,8 @@ over [num_envs, max_ped] on the GPU:
   PedestrianSim            device state + the per-step sequence of env.py:617-693
 
 Everything on the per-step path is a kernel of the library, the policy forward included
-(NativePolicy: tcgen05 tensor cores for the one dense layer that matters); torch owns the device
-memory and, in the comparison modes only, runs the dense layers.  Nothing here touches the CPU
+(NativePolicy: both convolutions, act_fc1 and act_fc2 on the tcgen05 tensor cores, DESIGN 4.3);
+torch owns the device memory and, in the comparison modes only, runs the dense layers.  Nothing here touches the CPU
 oracle.
 """
 import ctypes as C
