@@ -51,8 +51,7 @@ static unsigned long long g_launches = 0;
 #include "policy_gemm.cuh"
 
 // ------------------------------------------------------------------ C ABI
-// Launch shape of the fused kernel: warps per environment (WPE) and march slots per lane.
-// NAVGYM_WPE / NAVGYM_SLOTS override the defaults for tuning runs.
+// Integer tuning knobs read from the environment (documented in README.md).
 static int env_int(const char *name, int dflt)
 {
     const char *s = getenv(name);

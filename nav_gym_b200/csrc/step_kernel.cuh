@@ -402,7 +402,6 @@ __device__ __forceinline__ void step_body(const navgym_step_args_t &a, EnvSmem &
 {
     constexpr int BPL = NB / (32 * WPE);  // beams per lane
     constexpr int TPB = WPE * 32;         // threads of the CTA
-    constexpr int MARCH_SLOTS = 1;
     const int lane = tid & 31, warp = tid >> 5;
     const int B = a.num_envs;
     const long long t_begin = clock64();
