@@ -21,8 +21,7 @@ struct EnvSmem {
     double th_spec, yaw_spec;  // heading warp 1 assumed for the final pose, and its yaw
     int map, steps, episode, next_pass;
     int n_vis_seg, n_vis_disc;  // visible box segments / discs listed by the obstacle phase
-    int n_alive;           // beams still marching after the head phase
-    short alive[NB];       // their indices
+    short alive[NB];       // beams still marching after the head phase: one list per warp, NB / WPE entries each
     float noise_std;
     // per-pass scan setup
     float lx, ly, lt, res32, max_range, t_stop;
@@ -123,7 +122,6 @@ __device__ __forceinline__ void pass_setup(EnvSmem &sm, const navgym_map_t &m, c
     sm.res32 = (float)m.res;
     sm.max_range = (float)((double)m.W * (double)m.H);
     sm.t_stop = fminf(fminf(a.t_stop, sm.max_range), 8.0e6f);
-    sm.n_alive = 0;
 }
 
 template <int WPE>
@@ -138,9 +136,10 @@ __device__ __forceinline__ int cta_or(int pred)
 }
 
 // Tail phase.  Two regimes:
-//  A  dealing: warp w owns list entries w, w + WPE, w + 2 WPE, ...; they are dealt to its lanes
-//     with ballot ranks (no atomics, no cross-warp traffic): a lane whose beam ends takes the
-//     warp's next undealt entry; one beam per lane, one EDT gather per lane and round trip.
+//  A  dealing: every warp has its own list of the beams it marched through the head phase and
+//     that are still alive; the entries are dealt to its lanes with ballot ranks (no atomics, no
+//     cross-warp traffic): a lane whose beam ends takes the warp's next undealt entry; one beam
+//     per lane, one EDT gather per lane and round trip.
 //  B  cooperative: once the warp's entries are all dealt and at most NAVGYM_COOP_ENTER beams are
 //     still marching, the idle lanes stop idling: the L live beams are regrouped onto G = 32 / L
 //     (power of two) lanes each, and lane j of a group fetches the cell the beam would sample
@@ -163,10 +162,12 @@ template <int WPE, bool COOP>
 __device__ __forceinline__ void march_tail_dealt(EnvSmem &sm, const float *__restrict__ dist, float x0, float y0,
                                                  int W, int H, float t_stop, int n_alive, int warp, int lane)
 {
+    // every warp deals from its own survivor list
+    const short *list = sm.alive + warp * (NB / WPE);
     const unsigned FULL = 0xffffffffu;
     int next_j = 32;                       // warp-uniform: entries dealt so far
-    int idx = warp + WPE * lane;
-    int kb = idx < n_alive ? (int)sm.alive[idx] : -1;
+    int idx = lane;
+    int kb = idx < n_alive ? (int)list[idx] : -1;
     float t = __int_as_float(sm.scan[kb >= 0 ? kb : 0]);
     float2 dd = sm.dir[kb >= 0 ? kb : 0];
     unsigned live = __ballot_sync(FULL, kb >= 0);
@@ -175,7 +176,7 @@ __device__ __forceinline__ void march_tail_dealt(EnvSmem &sm, const float *__res
     // only change in an iteration in which some beam ended: all of that sits behind one
     // warp-uniform test of the ballot.
     constexpr int coop_enter = NAVGYM_COOP_ENTER;
-    bool to_b = COOP && NAVGYM_COOP_ENTER != 0 && !(warp + WPE * next_j < n_alive) && __popc(live) <= coop_enter;
+    bool to_b = COOP && NAVGYM_COOP_ENTER != 0 && !(next_j < n_alive) && __popc(live) <= coop_enter;
     while (!to_b) {
         const int cx = __float2int_rz(march_pos(dd.x, t, x0));
         const int cy = __float2int_rz(march_pos(dd.y, t, y0));
@@ -192,10 +193,10 @@ __device__ __forceinline__ void march_tail_dealt(EnvSmem &sm, const float *__res
             if (fin) {
                 // absolute hit cell, (y << 16 | x), or -1 for "no hit"
                 sm.scan[kb] = hit ? (cy << 16 | cx) : -1;
-                idx = warp + WPE * (next_j + __popc(fm & ((1u << lane) - 1u)));
+                idx = (next_j + __popc(fm & ((1u << lane) - 1u)));
                 kb = -1;
                 if (idx < n_alive) {
-                    kb = sm.alive[idx];
+                    kb = list[idx];
                     t = __int_as_float(sm.scan[kb]);
                     dd = sm.dir[kb];
                 }
@@ -203,7 +204,7 @@ __device__ __forceinline__ void march_tail_dealt(EnvSmem &sm, const float *__res
             next_j += __popc(fm);
             live = __ballot_sync(FULL, kb >= 0);
             if (!live) return;
-            to_b = COOP && NAVGYM_COOP_ENTER != 0 && !(warp + WPE * next_j < n_alive) && __popc(live) <= coop_enter;
+            to_b = COOP && NAVGYM_COOP_ENTER != 0 && !(next_j < n_alive) && __popc(live) <= coop_enter;
         }
     }
     // ---- regime B: `live` marks the lanes that hold a marching beam (kb, t, dd)
@@ -318,6 +319,7 @@ __device__ __forceinline__ void march_scan(EnvSmem &sm, const navgym_step_args_t
         cta_sync<WPE>();
     }
 #endif
+    int n_mine = 0;   // warp-uniform: survivors in this warp's list
 #pragma unroll 1
     for (int r = r_begin; r < r_end; r++) {
         float th_[HB], dxh[HB], dyh[HB];
@@ -363,15 +365,16 @@ __device__ __forceinline__ void march_scan(EnvSmem &sm, const navgym_step_args_t
             const bool alive = th_[j] >= 0.0f;
             if (alive) sm.scan[k] = __float_as_int(th_[j]);
             const unsigned mk = __ballot_sync(FULL, alive);
-            int base = 0;
-            if (lane == 0 && mk) base = atomicAdd(&sm.n_alive, __popc(mk));
-            base = __shfl_sync(FULL, base, 0);
-            if (alive) sm.alive[base + __popc(mk & ((1u << lane) - 1u))] = (short)k;
+            if (alive) sm.alive[warp * (NB / WPE) + n_mine + __popc(mk & ((1u << lane) - 1u))] = (short)k;
+            n_mine += __popc(mk);
         }
     }
-    cta_sync<WPE>();  // any lane may be dealt any survivor
+    // A warp compacts and deals its own survivors (its beams are 32-beam sectors alternating with
+    // the other warp's, so the lists are about equally long): no atomic on a shared counter, and no
+    // CTA barrier between the head and the tail phase -- only the warp's own stores to wait for.
+    __syncwarp();
     {
-        const int n_alive = sm.n_alive;
+        const int n_alive = n_mine;
 #ifdef NAVGYM_PROFILE
         if (tid == 0) sm.prof_alive += n_alive;
 #endif
