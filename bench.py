@@ -12,11 +12,13 @@ per-episode scan noise, random actions, device-side auto-reset from a 65 536-tup
 N>1 (torchrun) shards environments: 4096 per GPU, no collective on the step path (weak scaling).
 
 Prints ONE JSON line (rank 0).  `value` = env-steps/s with inputs resident in HBM; `e2e` = the
-same through the host-buffer rollout (pinned actions in, obs/reward/done out, copies timed).
+same through the host-buffer C ABI (pinned actions in, obs/reward/done out, copies timed): the
+better of the C rollout with rotating env groups and the blocking chunked call, both kept.
 `configs` holds the other BASELINE configurations, device-resident: c3 (16 384 envs, 2000^2
 outdoor map, 20 pedestrians; N=1), c4 (8192 envs per GPU = 65 536 / 8, 8 indoor + 8 outdoor
-maps, 5..15 pedestrians, map re-drawn at reset; every N -- at N=8 this IS configs[3]) and c5
-(32 768 envs + on-device MLP policy, rollout loop; N=1).
+maps, 5..15 pedestrians, map re-drawn at reset; every N -- at N=8 this IS configs[3]), c5
+(32 768 envs + on-device MLP policy, rollout loop; N=1), crowd (policy-driven pedestrians; N=1)
+and her (the HER batch kernel with its HBM roofline; N=1).
 `--impl reference` times the CPU restatement of the reference's path (oracle/, OpenMP over all
 host cores) on the same world with the same 4096 environments per step.
 """
