@@ -334,8 +334,13 @@ __device__ __forceinline__ void march_scan(EnvSmem &sm, const navgym_step_args_t
             dyh[j] = (float)sd;
             sm.dir[k] = make_float2(dxh[j], dyh[j]);
             th_[j] = t1;
-            if (degenerate) { sm.scan[k] = (o_in & (d0 <= 0.0f)) ? (cj << 16 | ci) : -1; th_[j] = -1.0f; }
+            if (degenerate) { sm.scan[k] = (o_in & (d0 <= 0.0f)) ? (cj << 16 | ci) : -1; th_[j] = CUDART_NAN_F; }
         }
+        // An ended beam is marked by t = NaN: its sample position converts to cell (0, 0) (a valid
+        // load of element 0, like the idle lanes of the tail), its next t is NaN again, which fails
+        // "t < t_stop" and so counts as ended -- only the store of the hit cell asks whether the beam
+        // was still alive (one compare instead of a predicate carried through the whole step:
+        // 99 instead of 119 instructions per four samples).
 #pragma unroll 1
         for (int st = 0; st < NAVGYM_HEAD_STEPS; st++) {
             float dv[HB];
@@ -346,23 +351,22 @@ __device__ __forceinline__ void march_scan(EnvSmem &sm, const navgym_step_args_t
                 cx[j] = __float2int_rz(march_pos(dxh[j], th_[j], x0));
                 cy[j] = __float2int_rz(march_pos(dyh[j], th_[j], y0));
                 inb[j] = ((unsigned)cx[j] < (unsigned)W) & ((unsigned)cy[j] < (unsigned)H);
-                dv[j] = edt_at(sm, dist, cx[j], cy[j], W, inb[j] & (th_[j] >= 0.0f));
+                dv[j] = edt_at(sm, dist, cx[j], cy[j], W, inb[j]);
             }
 #pragma unroll
             for (int j = 0; j < HB; j++) {
-                const bool alive = th_[j] >= 0.0f;
                 const bool hit = inb[j] & (dv[j] <= 0.0f);
-                const float tn = __fadd_rn(th_[j], fmaxf(__fmul_rn(dv[j], 0.999f), 1.0f));
+                const float tn = __fadd_rn(th_[j], fmaxf(__fmul_rn(dv[j], 0.999f), 1.0f));   // NaN for an ended beam
                 const bool fin = !inb[j] | hit | !(tn < t_stop);
-                if (alive & fin) sm.scan[BEAM(r * HB + j)] = hit ? (cy[j] << 16 | cx[j]) : -1;
-                th_[j] = (alive & !fin) ? tn : -1.0f;
+                if (fin & (th_[j] == th_[j])) sm.scan[BEAM(r * HB + j)] = hit ? (cy[j] << 16 | cx[j]) : -1;
+                th_[j] = fin ? CUDART_NAN_F : tn;
             }
         }
         // survivors: park t in the scan slot and append the beam to the compact list
 #pragma unroll
         for (int j = 0; j < HB; j++) {
             const int k = BEAM(r * HB + j);
-            const bool alive = th_[j] >= 0.0f;
+            const bool alive = th_[j] == th_[j];
             if (alive) sm.scan[k] = __float_as_int(th_[j]);
             const unsigned mk = __ballot_sync(FULL, alive);
             if (alive) sm.alive[warp * (NB / WPE) + n_mine + __popc(mk & ((1u << lane) - 1u))] = (short)k;
