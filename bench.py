@@ -638,7 +638,7 @@ def main():
 
 # dram__bytes_read.sum + dram__bytes_write.sum of step_kernel<false> per launch, from the
 # `ncu --set full` capture summarised in profiles/ (None until measured).
-TRAFFIC_BYTES_PER_LAUNCH = 3686144  # dram read + write of one launch, profiles/r2_step_kernel_ncu_full_summary.txt (round 1: 3193600)
+TRAFFIC_BYTES_PER_LAUNCH = 3759616  # dram read + write of one launch, profiles/r2_step_kernel_ncu_full_summary.txt (final capture of round 2; round 1: 3193600)
 # EDT gathers per env-step = march samples of the 512 beams (the t = 0 sample shared per scan) x
 # scans per step, counted by the CPU checker on the same worlds: oracle/analysis/config_gathers.py
 GATHERS_PER_ENV_STEP = 3415   # C2 / C5 world: 3382 per scan x 1.01
